@@ -1,0 +1,248 @@
+/*
+ * wolfd2_b200.h -- C ABI of the B200-native wolfd2 time-step hot path.
+ *
+ * Two layers are exported by libwolfd2_b200.so:
+ *
+ *  (1) LITERAL SHIMS: the gfortran calling convention of the reference's
+ *      hot-path subroutines (lower-case name + '_', every argument a pointer,
+ *      INTEGER -> int32_t*, REAL -> double*, LOGICAL -> int32_t*; no CHARACTER
+ *      arguments on this path).  Arrays are caller-owned HOST buffers laid out
+ *      exactly as the reference declares them: REAL*8 f(0:mnx,0:mny), i fastest,
+ *      pitch mnx+1 (reference include/config.f:19-26, include/wolfd2.h:5-8).
+ *      Each shim uploads its arguments, runs the CUDA kernels and downloads the
+ *      in/out arrays.  They let an unmodified main.f link against this library.
+ *
+ *  (2) RESIDENCY API (wolfd2_b200_*): fields and metrics stay in HBM across time
+ *      steps; the whole step body of main.f:690-981 runs on the device and only a
+ *      small status tuple returns to the host per step.
+ *
+ * There is NO CPU fallback: every entry point fails loudly (message on stderr and
+ * a non-zero status / abort for the literal shims, which have no error channel in
+ * the reference either -- it uses `stop`) when no CUDA device is usable.
+ *
+ * Every declaration cites the reference interface it replaces (paths relative to
+ * the reference tree).
+ */
+#ifndef WOLFD2_B200_H
+#define WOLFD2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enum constants: include/wolfd2.h:15-59 ------------------------------------ */
+enum { W2_RM_BLOCKG = 0, W2_RM_INTERN = 1, W2_RM_POROUS = 2 };
+enum { W2_BM_INTERN = 0, W2_BM_WALL1 = 1, W2_BM_WALL2 = 2, W2_BM_INLET = 3,
+       W2_BM_OUTLT1 = 4, W2_BM_OUTLT2 = 5 };
+enum { W2_WEST = 1, W2_EAST = 2, W2_SOUTH = 3, W2_NORTH = 4 };
+enum { W2_U = 1, W2_V = 2, W2_P = 3, W2_T = 4 };
+/* ppe_solver ids: src/parse.f:440-465 */
+enum { W2_PPE_SOR = 1, W2_PPE_LSOR = 2, W2_PPE_RB_LSOR = 3, W2_PPE_PAR_RB_LSOR = 4,
+       W2_PPE_RB_SOR = 5, W2_PPE_PAR_RB_SOR = 6 };
+
+/* ---- plain-data descriptors shared by the residency API ------------------------ */
+
+/* Scalars of `section input_parameters` that the hot path reads
+ * (src/parse.f:117-193 defaults; src/file_manip.f:134-159 for dk, re, fr). */
+typedef struct wolfd2_params {
+    int32_t nx, ny;            /* grid points (src/grid.f:88-89)                     */
+    int32_t mqiter;            /* max_ql_iter            (default 20)                */
+    int32_t nmeiter;           /* max_me_iter; forced to 1 without thermal energy    */
+    int32_t nPpeSolver;        /* ppe_solver id 1..6                                 */
+    int32_t msorit;            /* max_sor_iter           (default 2000)              */
+    int32_t lCartesGrid;       /* grid_file ... cartesian_grid                       */
+    int32_t nfiltu, nfiltv;    /* filter_u / filter_v given                          */
+    int32_t reserved_;
+    double  dk;                /* non-dimensional time step                          */
+    double  re, fr;            /* Reynolds, Froude                                   */
+    double  qtol;              /* ql_tolerance           (default 1e-4)              */
+    double  sortol, sorrel;    /* sor_tolerance 1e-8, sor_relaxation 1.0             */
+    double  fpu, fpv;          /* Shuman filter parameters                           */
+} wolfd2_params;
+
+/* Region / boundary tables as built by SetUpBCs (src/bound_cond.f:34-443),
+ * Fortran layout: nRegBrd(mgri,mgrj,4), nRegType(mgri,mgrj), nMomBdTp(mgri,mgrj,4),
+ * dBCVal(mgri,mgrj,4,4), dPRporos/c1/c2(mgri,mgrj); nReg(2).                        */
+typedef struct wolfd2_regions {
+    const int32_t *nReg;
+    const int32_t *nRegBrd;
+    const int32_t *nRegType;
+    const int32_t *nMomBdTp;
+    const double  *dBCVal;
+    const double  *dPRporos;
+    const double  *dPRporc1;
+    const double  *dPRporc2;
+} wolfd2_regions;
+
+/* The 30 metric arrays produced by Metric (src/grid.f:368-535), each
+ * REAL*8 (0:mnx,0:mny), zero outside 1..nx,1..ny (static storage in main.f). */
+typedef struct wolfd2_metrics {
+    const double *rau, *rbu, *rbv, *rgv;
+    const double *ran, *rbn, *rgn;
+    const double *rac, *rbc, *rgc;
+    const double *dju, *djv, *djc, *djn;
+    const double *xen, *yen, *xzn, *yzn;
+    const double *xec, *yec, *xzc, *yzc;
+    const double *xeu, *yeu, *xzv, *yzv;
+    const double *xzu, *yzu, *xev, *yev;
+} wolfd2_metrics;
+
+/* Per-step tuple printed by PrintDiff (src/string.f:547-559) plus a status word. */
+typedef struct wolfd2_step_log {
+    int32_t nQLiter;      /* return value of nAuxMomentum (-1: not converged)       */
+    int32_t nSorConv;     /* SOR iterations (msorit if not converged, pressure.f:242)*/
+    int32_t sor_converged;/* 0 when the msorit cap was hit                           */
+    int32_t diverged;     /* difmax > 1e12 (src/main.f:969-972)                      */
+    double  dif[4];       /* |p1-pn|, |u1-un|, |v1-vn|, |t1-tn|  (main.f:962-965)    */
+} wolfd2_step_log;
+
+enum { W2_OK = 0, W2_ERR_NO_DEVICE = 1, W2_ERR_BAD_ARG = 2, W2_ERR_UNSUPPORTED = 3,
+       W2_ERR_CUDA = 4, W2_ERR_DIVERGED = 5 };
+
+/* field selectors for wolfd2_b200_upload_field / download_field */
+enum { W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_US = 3, W2_F_VS = 4, W2_F_UN = 5,
+       W2_F_VN = 6, W2_F_PN = 7, W2_F_D = 8, W2_F_DN = 9, W2_F_B = 10, W2_F_COUNT = 11 };
+
+/* ---- library-wide configuration ------------------------------------------------ */
+
+/* The reference fixes mnx,mny,mgri,mgrj at compile time (include/config.f:19-26);
+ * the library takes them once at run time.  Must be called before any literal shim.
+ * Returns W2_OK or an error code. */
+int wolfd2_b200_config(int32_t mnx, int32_t mny, int32_t mgri, int32_t mgrj);
+/* Select the CUDA device (default 0). */
+int wolfd2_b200_set_device(int32_t device);
+const char *wolfd2_b200_last_error(void);
+const char *wolfd2_b200_version(void);
+
+/* ---- (2) residency API ---------------------------------------------------------- */
+typedef struct wolfd2_ctx wolfd2_ctx;
+
+/* Create a device context for an nx*ny grid whose host arrays have pitch mnx+1 and
+ * mny+1 rows (set by wolfd2_b200_config).  Uploads metrics and region tables
+ * (what main.f holds after Grid/SetUpBCs, src/main.f:434-448). */
+int wolfd2_b200_create(wolfd2_ctx **out, const wolfd2_params *par,
+                       const wolfd2_regions *reg, const wolfd2_metrics *met);
+void wolfd2_b200_destroy(wolfd2_ctx *ctx);
+int wolfd2_b200_set_params(wolfd2_ctx *ctx, const wolfd2_params *par);
+
+/* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
+int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
+int wolfd2_b200_download_field(wolfd2_ctx *ctx, int32_t which, double *host);
+
+/* Cold-start projection, src/main.f:606-641. */
+int wolfd2_b200_coldstart(wolfd2_ctx *ctx, int32_t *nSorConv);
+/* nsteps iterations of the step body src/main.f:690-981 (cold flow: no thermal
+ * energy, no ATD) entirely on the device.  logs may be NULL or hold nsteps entries. */
+int wolfd2_b200_step(wolfd2_ctx *ctx, int32_t nsteps, wolfd2_step_log *logs);
+/* Same, but the state crosses the boundary in HOST buffers every call:
+ * u,v,p are uploaded, nsteps run, u,v,p downloaded (the e2e path of bench.py). */
+int wolfd2_b200_step_host(wolfd2_ctx *ctx, int32_t nsteps, double *u, double *v,
+                          double *p, wolfd2_step_log *logs);
+
+/* Device-timed sections of the last wolfd2_b200_step call (CUDA events on the
+ * library's stream), milliseconds: [0] total, [1] momentum (QL loop), [2] PPE
+ * (div+rhs+SOR), [3] projection + BC fills + norms.  Kernel launch counters since
+ * context creation in launches[0..3] likewise. */
+int wolfd2_b200_last_timing(wolfd2_ctx *ctx, double ms[4], int64_t launches[4]);
+/* Average device time of the SOR sweep kernel launches inside the last step (ms)
+ * and the number of SOR iterations they covered. */
+int wolfd2_b200_last_sor_timing(wolfd2_ctx *ctx, double *ms_total, int64_t *iterations);
+int wolfd2_b200_sync(wolfd2_ctx *ctx);
+
+/* ---- (1) literal shims: gfortran ABI of the reference subroutines --------------- */
+
+/* src/momentum.f:33-48  INTEGER function nAuxMomentum(...) */
+int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int32_t *mqiter,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *nMomBdTp,
+    const double *dk, const double *re, const double *fr, const double *qtol,
+    const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+    const double *dBCVal,
+    const double *ran, const double *rbn, const double *rgn,
+    const double *rac, const double *rbc, const double *rgc,
+    const double *dju, const double *djv,
+    const double *xec, const double *yec, const double *xzn, const double *yzn,
+    const double *xen, const double *yen, const double *xzc, const double *yzc,
+    const double *xeu, const double *yeu, const double *xzu, const double *yzu,
+    const double *xev, const double *yev, const double *xzv, const double *yzv,
+    const double *d, const double *dn,
+    const double *un, const double *vn, double *us, double *vs);
+
+/* src/momentum.f:199-208 */
+void xmomentum_(const int32_t *nx, const int32_t *ny,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *nMomBdTp, const double *dk, const double *re,
+    const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+    const double *rbn, const double *rgn, const double *rac, const double *rbc,
+    const double *dju,
+    const double *xec, const double *yec, const double *xzn, const double *yzn,
+    const double *xeu, const double *yeu, const double *xzu, const double *yzu,
+    const double *us, const double *vs, const double *un, const double *vn,
+    double *dus);
+
+/* src/momentum.f:520-530 */
+void ymomentum_(const int32_t *nx, const int32_t *ny,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *nMomBdTp, const double *dk, const double *re, const double *fr,
+    const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+    const double *ran, const double *rbn, const double *rbc, const double *rgc,
+    const double *djv,
+    const double *xen, const double *yen, const double *xzc, const double *yzc,
+    const double *xev, const double *yev, const double *xzv, const double *yzv,
+    const double *d, const double *dn,
+    const double *us, const double *vs, const double *un, const double *vn,
+    double *dvs);
+
+/* src/momentum.f:1307  subroutine AltTridLU(n, a, b): a(3,n) AoS, solution in b */
+void alttridlu_(const int32_t *n, double *a, double *b);
+
+/* src/pressure.f:30-38 */
+void ppe_(const int32_t *nx, const int32_t *ny,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *lCartesGrid,
+    const int32_t *nPpeSolver, const int32_t *msorit, int32_t *nSorConv,
+    const double *dk, const double *sortol, const double *sorrel,
+    const double *rau, const double *rbu, const double *rbv, const double *rgv,
+    const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+    const double *u, const double *v, double *p);
+
+/* src/pressure.f:265-267 */
+void divergence_(const int32_t *nx, const int32_t *ny, const int32_t *nloc,
+    const double *xet, const double *yet, const double *xzi, const double *yzi,
+    const double *u, const double *v, double *div);
+
+/* src/utility.f:253-259 */
+void project_(const int32_t *nx, const int32_t *ny,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *nMomBdTp, const double *dk,
+    const double *dju, const double *djv,
+    const double *yeu, const double *xzv, const double *yzu, const double *xev,
+    const double *p, double *u, double *v);
+
+/* src/bound_cond.f:511-513 */
+void velboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg,
+    const int32_t *nRegBrd, const int32_t *nMomBdTp, const double *dBCVal,
+    double *u, double *v);
+/* src/bound_cond.f:853-856 */
+void presboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg,
+    const int32_t *nRegBrd, const int32_t *nRegType, const int32_t *nMomBdTp,
+    const double *dBCVal, double *p);
+/* src/bound_cond.f:1656-1659 */
+void veloutflowbcs_(const int32_t *nx, const int32_t *ny, const int32_t *nReg,
+    const int32_t *nRegBrd, const int32_t *nMomBdTp, const double *dBCVal,
+    double *u, double *v);
+/* src/utility.f:33-36 */
+void filter_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp,
+    const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+    const int32_t *nMomBdTp, const int32_t *nTRgType, const double *fp, double *qu);
+/* src/utility.f:446, 479 */
+double diffmaxnorm_(const int32_t *nx, const int32_t *ny, const double *un,
+                    const double *u);
+double dmaxnorm_(const int32_t *nx, const int32_t *ny, const double *u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WOLFD2_B200_H */

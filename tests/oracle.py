@@ -1,0 +1,95 @@
+"""Loader for the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+nothing under wolfd2_b200/ may import this module."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from wolfd2_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+
+
+def _build(target="liboracle.so"):
+    path = os.path.join(ODIR, target)
+    src = os.path.join(ODIR, "wolfd2_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ODIR, target], stdout=subprocess.DEVNULL)
+    return path
+
+
+class Oracle:
+    def __init__(self, target="liboracle.so"):
+        self.lib = C.CDLL(_build(target))
+        table = dict(_abi.SIGNATURES)
+        table.update(_abi.ORACLE_ONLY)
+        self.f = _abi.bind(self.lib, prefix="orc_", table=table)
+        self.lib.orc_config.argtypes = [C.c_int32] * 4
+        self.lib.orc_get_errflag.restype = C.c_int32
+        self.lib.orc_coldstart.argtypes = [C.POINTER(_abi.Params), C.POINTER(_abi.Regions),
+                                           C.POINTER(_abi.Metrics), _abi.c_f64p, _abi.c_f64p,
+                                           _abi.c_f64p, _abi.c_i32p]
+        self.lib.orc_step.argtypes = [C.POINTER(_abi.Params), C.POINTER(_abi.Regions),
+                                      C.POINTER(_abi.Metrics)] + [_abi.c_f64p] * 5 + \
+                                     [C.c_int32, C.POINTER(_abi.StepLog)]
+        self.lib.orc_step.restype = C.c_int32
+        self.lib.orc_ppe_matrix.argtypes = [C.c_int32, C.c_int32, _abi.c_i32p, _abi.c_i32p, _abi.c_i32p,
+                                            _abi.c_f64p, _abi.c_f64p, _abi.c_f64p, _abi.c_f64p]
+        self.lib.orc_grid.argtypes = [C.c_int32, C.c_int32, C.c_double, _abi.c_f64p, _abi.c_f64p,
+                                      C.POINTER(_abi.c_f64p)]
+        self._dims = None
+
+    def config(self, mnx, mny, mgri=20, mgrj=10):
+        if self._dims != (mnx, mny, mgri, mgrj):
+            self.lib.orc_config(mnx, mny, mgri, mgrj)
+            self._dims = (mnx, mny, mgri, mgrj)
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["f"][name]
+        except KeyError:
+            raise AttributeError(name)
+
+    # ---- whole-run drivers -------------------------------------------------
+    def grid_metrics(self, x_nodes, y_nodes, mnx, mny, dlref=1.0):
+        """orc_grid: src/grid.f Grid minus the file reader. Returns dict of 30 arrays."""
+        self.config(mnx, mny)
+        ny, nx = x_nodes.shape
+        gx = np.zeros((mny + 1, mnx + 1)); gy = np.zeros((mny + 1, mnx + 1))
+        gx[1:ny + 1, 1:nx + 1] = x_nodes
+        gy[1:ny + 1, 1:nx + 1] = y_nodes
+        m = {n: np.zeros((mny + 1, mnx + 1)) for n in _abi.METRIC_NAMES}
+        ptrs = (_abi.c_f64p * 30)(*[m[n].ctypes.data_as(_abi.c_f64p) for n in _abi.METRIC_NAMES])
+        self.lib.orc_grid(nx, ny, dlref, gx.ctypes.data_as(_abi.c_f64p), gy.ctypes.data_as(_abi.c_f64p), ptrs)
+        return m
+
+    def coldstart(self, deck, u, v, p):
+        self.config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        par, reg, met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
+        n = C.c_int32(0)
+        self.lib.orc_coldstart(C.byref(par), C.byref(reg), C.byref(met),
+                               u.ctypes.data_as(_abi.c_f64p), v.ctypes.data_as(_abi.c_f64p),
+                               p.ctypes.data_as(_abi.c_f64p), C.byref(n))
+        return n.value
+
+    def step(self, deck, u, v, p, nsteps=1, t=None, d=None):
+        self.config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        par, reg, met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
+        t = deck.new_field() if t is None else t
+        d = deck.new_field() if d is None else d
+        logs = (_abi.StepLog * nsteps)()
+        rc = self.lib.orc_step(C.byref(par), C.byref(reg), C.byref(met),
+                               *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)
+        return rc, [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, dif=list(l.dif)) for l in logs]
+
+
+_ORACLE = None
+
+
+def get_oracle():
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE

@@ -1,0 +1,178 @@
+"""Python face of libwolfd2_b200.so (ctypes over the C ABI in include/wolfd2_b200.h).
+
+Two layers, as in the header:
+  * literal routines with the reference's names and argument lists -- ``nAuxMomentum``, ``XMomentum``,
+    ``YMomentum``, ``AltTridLU``, ``Ppe``, ``Divergence``, ``Project``, ``VelBoundCond``,
+    ``PresBoundCond``, ``VelOutflowBCs``, ``Filter``, ``DiffMaxNorm``, ``DMaxNorm`` -- taking host
+    numpy arrays laid out as REAL*8 f(0:mnx,0:mny);
+  * ``Context``: fields resident in HBM across time steps.
+
+There is no CPU path here: importing works anywhere, but every call needs the CUDA library and a
+B200; failures are loud (exception with the library's message, or abort() inside the literal shims,
+which -- like the reference's `stop` -- have no error channel).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import Metrics, Params, Regions, StepLog, c_f64p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwolfd2_b200.so")
+
+F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B = range(11)
+
+_lib = None
+_fn = None
+
+
+class Wolfd2Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; raise if it has not been built (no fallback)."""
+    global _lib, _fn
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Wolfd2Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). wolfd2_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.wolfd2_b200_last_error.restype = C.c_char_p
+    L.wolfd2_b200_version.restype = C.c_char_p
+    L.wolfd2_b200_config.argtypes = [C.c_int32] * 4
+    L.wolfd2_b200_set_device.argtypes = [C.c_int32]
+    L.wolfd2_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.POINTER(Regions), C.POINTER(Metrics)]
+    L.wolfd2_b200_destroy.argtypes = [C.c_void_p]
+    L.wolfd2_b200_destroy.restype = None
+    L.wolfd2_b200_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
+    L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
+    L.wolfd2_b200_coldstart.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.wolfd2_b200_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(StepLog)]
+    L.wolfd2_b200_step_host.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_f64p, c_f64p, C.POINTER(StepLog)]
+    L.wolfd2_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.wolfd2_b200_last_sor_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.wolfd2_b200_sync.argtypes = [C.c_void_p]
+    _lib = L
+    _fn = _abi.bind(L)
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise Wolfd2Error(f"{what} failed (code {rc}): {lib().wolfd2_b200_last_error().decode()}")
+
+
+def config(mnx, mny, mgri=20, mgrj=10):
+    """Run-time stand-in for the reference's compile-time include/config.f."""
+    _check(lib().wolfd2_b200_config(mnx, mny, mgri, mgrj), "wolfd2_b200_config")
+
+
+def set_device(dev):
+    _check(lib().wolfd2_b200_set_device(dev), "wolfd2_b200_set_device")
+
+
+def _routine(name):
+    def f(*args):
+        lib()
+        return _fn[name](*args)
+    f.__name__ = name
+    return f
+
+
+# literal routines, reference spelling (argument order = the Fortran declarations cited in _abi.py)
+nAuxMomentum = _routine("nauxmomentum")
+XMomentum = _routine("xmomentum")
+YMomentum = _routine("ymomentum")
+AltTridLU = _routine("alttridlu")
+Ppe = _routine("ppe")
+Divergence = _routine("divergence")
+Project = _routine("project")
+VelBoundCond = _routine("velboundcond")
+PresBoundCond = _routine("presboundcond")
+VelOutflowBCs = _routine("veloutflowbcs")
+Filter = _routine("filter")
+DiffMaxNorm = _routine("diffmaxnorm")
+DMaxNorm = _routine("dmaxnorm")
+
+
+class Context:
+    """Device-resident run: what `program wolfd2` holds after set-up, living in HBM."""
+
+    def __init__(self, deck):
+        L = lib()
+        self.deck = deck
+        config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        self._par, self._reg, self._met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
+        h = C.c_void_p()
+        _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
+               "wolfd2_b200_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().wolfd2_b200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self._par, k, v)
+        _check(lib().wolfd2_b200_set_params(self._h, C.byref(self._par)), "wolfd2_b200_set_params")
+
+    def upload(self, which, arr):
+        assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        assert arr.shape == (self.deck.mny + 1, self.deck.mnx + 1)
+        _check(lib().wolfd2_b200_upload_field(self._h, which, arr.ctypes.data_as(c_f64p)), "upload_field")
+
+    def download(self, which, out=None):
+        out = self.deck.new_field() if out is None else out
+        _check(lib().wolfd2_b200_download_field(self._h, which, out.ctypes.data_as(c_f64p)), "download_field")
+        return out
+
+    def coldstart(self):
+        n = C.c_int32(0)
+        _check(lib().wolfd2_b200_coldstart(self._h, C.byref(n)), "wolfd2_b200_coldstart")
+        return n.value
+
+    @staticmethod
+    def _logs(raw):
+        return [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, sor_converged=l.sor_converged,
+                     diverged=l.diverged, dif=list(l.dif)) for l in raw]
+
+    def step(self, nsteps=1):
+        raw = (StepLog * nsteps)()
+        _check(lib().wolfd2_b200_step(self._h, nsteps, raw), "wolfd2_b200_step")
+        return self._logs(raw)
+
+    def step_host(self, u, v, p, nsteps=1):
+        raw = (StepLog * nsteps)()
+        _check(lib().wolfd2_b200_step_host(self._h, nsteps, u.ctypes.data_as(c_f64p), v.ctypes.data_as(c_f64p),
+                                           p.ctypes.data_as(c_f64p), raw), "wolfd2_b200_step_host")
+        return self._logs(raw)
+
+    def timing(self):
+        ms = (C.c_double * 4)()
+        ln = (C.c_int64 * 4)()
+        _check(lib().wolfd2_b200_last_timing(self._h, ms, ln), "last_timing")
+        sm, si = C.c_double(0), C.c_int64(0)
+        _check(lib().wolfd2_b200_last_sor_timing(self._h, C.byref(sm), C.byref(si)), "last_sor_timing")
+        return dict(total_ms=ms[0], momentum_ms=ms[1], ppe_ms=ms[2], other_ms=ms[3],
+                    launches=dict(momentum=ln[1], ppe=ln[2], other=ln[3]),
+                    sor_ms=sm.value, sor_iters=si.value)
+
+    def sync(self):
+        _check(lib().wolfd2_b200_sync(self._h), "sync")

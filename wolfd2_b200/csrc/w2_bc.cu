@@ -1,0 +1,242 @@
+// w2_bc.cu -- ghost-cell fills: VelBoundCond (src/bound_cond.f:511-847), PresBoundCond
+// (:853-1024) and VelOutflowBCs (:1656-1874).
+//
+// The reference visits regions (jreg outer, ireg inner) and faces (W,E,S,N) strictly in order,
+// and later loops read what earlier ones wrote at region corners, so the order is part of the
+// result.  The work is O(perimeter): one CTA walks the same sequence, running each Fortran
+// loop in parallel across its threads with a barrier after every loop.  Loops with a carried
+// dependence (the OUTLT2 mass-conservation recurrences, e.g. bound_cond.f:611-614) are run by a
+// single thread.  HBM traffic is negligible (kernel K3).
+#include "w2.cuh"
+
+#define BC_THREADS 1024
+#define U(i, j) u[IDX(i, j)]
+#define V(i, j) v[IDX(i, j)]
+#define P(i, j) p[IDX(i, j)]
+#define PFOR(var, lo, hi) for (int var = (lo) + (int)threadIdx.x; var <= (hi); var += BC_THREADS)
+#define SEQ if (threadIdx.x == 0)
+
+template <bool kOutflowOnly>
+__global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__restrict__ R, int pitch,
+                                                            double *u, double *v) {
+    const double dZero = 0.0, dTwo = 2.0, dThree = 3.0, dFour = 4.0, dFive = 5.0, dEight = 8.0;
+    const int nreg = R->nreg;
+    for (int q = 0; q < nreg; ++q) {
+        const int iW = R->iW[q], iE = R->iE[q], jS = R->jS[q], jN = R->jN[q];
+        // ---------------- WEST (:561-619 / :1707-1736)
+        {
+            const int bt = R->bd[q][W2_WEST - 1];
+            const double valU = R->val[q][W2_WEST - 1][W2_U - 1], valV = R->val[q][W2_WEST - 1][W2_V - 1];
+            if (!kOutflowOnly && bt == W2_BM_WALL1) {
+                PFOR(j, jS, jN) U(iW, j) = dZero;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
+            } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
+                PFOR(j, jS, jN) U(iW, j) = dZero;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iW, j) = V(iW + 1, j);
+            } else if (!kOutflowOnly && bt == W2_BM_INLET) {
+                PFOR(j, jS, jN) U(iW, j) = valU;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
+            } else if (bt == W2_BM_OUTLT1) {
+                PFOR(j, jS, jN) U(iW - 1, j) = valU + U(iW, j);
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iW, j) = -V(iW + 1, j);
+            } else if (bt == W2_BM_OUTLT2) {
+                if (kOutflowOnly) {  // VelOutflowBCs :1725
+                    PFOR(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) - V(iW + 1, j) + V(iW + 1, j - 1);
+                } else {             // VelBoundCond :608
+                    PFOR(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) + V(iW + 1, j) - V(iW + 1, j - 1);
+                }
+                __syncthreads();
+                SEQ {  // carried value kept in a register; same arithmetic as :612-613
+                    double prev = V(iW, jS);
+                    for (int j = jS + 1; j <= jN; ++j) {
+                        prev = -prev + dFive * (V(iW + 1, j) - V(iW + 1, j - 1))
+                               + dEight * (U(iW + 1, j) - U(iW, j));
+                        V(iW, j) = prev;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---------------- EAST (:623-693 / :1740-1780)
+        {
+            const int bt = R->bd[q][W2_EAST - 1];
+            const double valU = R->val[q][W2_EAST - 1][W2_U - 1], valV = R->val[q][W2_EAST - 1][W2_V - 1];
+            if (!kOutflowOnly && bt == W2_BM_WALL1) {
+                PFOR(j, jS, jN) U(iE, j) = dZero;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
+            } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
+                PFOR(j, jS, jN) U(iE, j) = dZero;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iE + 1, j) = V(iE, j);
+            } else if (!kOutflowOnly && bt == W2_BM_INLET) {
+                PFOR(j, jS, jN) U(iE, j) = valU;
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
+            } else if (bt == W2_BM_OUTLT1) {
+                PFOR(j, jS, jN) U(iE + 1, j) = valU + U(iE, j);
+                __syncthreads();
+                PFOR(j, jS + 1, jN) V(iE + 1, j) = -V(iE, j);
+            } else if (bt == W2_BM_OUTLT2) {
+                PFOR(j, jS + 1, jN) U(iE, j) = U(iE - 1, j) - (V(iE, j) - V(iE, j - 1));
+                __syncthreads();
+                SEQ {
+                    double prev = V(iE + 1, jS);
+                    for (int j = jS + 1; j <= jN - 1; ++j) {
+                        prev = prev + dThree * (V(iE, j - 1) - V(iE, j)) - dFour * (U(iE, j) - U(iE - 1, j));
+                        V(iE + 1, j) = prev;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---------------- SOUTH (:697-766 / :1784-1824)
+        {
+            const int bt = R->bd[q][W2_SOUTH - 1];
+            const double valU = R->val[q][W2_SOUTH - 1][W2_U - 1], valV = R->val[q][W2_SOUTH - 1][W2_V - 1];
+            if (!kOutflowOnly && bt == W2_BM_WALL1) {
+                PFOR(i, iW + 1, iE) U(i, jS) = dTwo * valU - U(i, jS + 1);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jS) = dZero;
+            } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
+                PFOR(i, iW + 1, iE) U(i, jS) = U(i, jS + 1);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jS) = dZero;
+            } else if (!kOutflowOnly && bt == W2_BM_INLET) {
+                PFOR(i, iW + 1, iE) U(i, jS) = dTwo * valU - U(i, jS + 1);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jS) = valV;
+            } else if (bt == W2_BM_OUTLT1) {
+                PFOR(i, iW + 1, iE) U(i, jS) = -U(i, jS + 1);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jS) = valV + V(i, jS);  // sic: self-reference (:738)
+            } else if (bt == W2_BM_OUTLT2) {
+                PFOR(i, iW + 1, iE) V(i, jS) = V(i, jS + 1) + (U(i, jS + 1) - U(i - 1, jS + 1));
+                __syncthreads();
+                SEQ {
+                    double prev = U(iW, jS);
+                    for (int i = iW + 1; i <= iE - 1; ++i) {
+                        prev = prev + dThree * (U(i - 1, jS + 1) - U(i, jS + 1)) - dFour * (V(i, jS + 1) - V(i, jS));
+                        U(i, jS) = prev;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---------------- NORTH (:770-840 / :1828-1868)
+        {
+            const int bt = R->bd[q][W2_NORTH - 1];
+            const double valU = R->val[q][W2_NORTH - 1][W2_U - 1], valV = R->val[q][W2_NORTH - 1][W2_V - 1];
+            if (!kOutflowOnly && bt == W2_BM_WALL1) {
+                PFOR(i, iW + 1, iE) U(i, jN + 1) = dTwo * valU - U(i, jN);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jN) = dZero;
+            } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
+                PFOR(i, iW + 1, iE) U(i, jN + 1) = U(i, jN);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jN) = dZero;
+            } else if (!kOutflowOnly && bt == W2_BM_INLET) {
+                PFOR(i, iW + 1, iE) U(i, jN + 1) = dTwo * valU - U(i, jN);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jN) = valV;
+            } else if (bt == W2_BM_OUTLT1) {
+                PFOR(i, iW + 1, iE) U(i, jN + 1) = -U(i, jN);
+                __syncthreads();
+                PFOR(i, iW, iE) V(i, jN + 1) = valV + V(i, jN);
+            } else if (bt == W2_BM_OUTLT2) {
+                // v(i,jN) for i=iW..iE reads u(i-1,jN) and u(i,jN): no carried dependence
+                PFOR(i, iW, iE) V(i, jN) = V(i, jN - 1) - (U(i, jN) - U(i - 1, jN));
+                __syncthreads();
+                SEQ {
+                    double prev = U(iW, jN + 1);
+                    for (int i = iW + 1; i <= iE - 1; ++i) {
+                        prev = prev + dThree * (U(i - 1, jN) - U(i, jN)) - dFour * (V(i, jN) - V(i, jN - 1));
+                        U(i, jN + 1) = prev;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__restrict__ R, int pitch, double *p) {
+    const double dZero = 0.0, dTwo = 2.0;
+    const int nreg = R->nreg;
+    for (int q = 0; q < nreg; ++q) {
+        const int iW = R->iW[q], iE = R->iE[q], jS = R->jS[q], jN = R->jN[q];
+        const double vW = R->val[q][W2_WEST - 1][W2_P - 1], vE = R->val[q][W2_EAST - 1][W2_P - 1];
+        const double vS = R->val[q][W2_SOUTH - 1][W2_P - 1], vN = R->val[q][W2_NORTH - 1][W2_P - 1];
+        if (R->type[q] == W2_RM_BLOCKG) {  // :903-936
+            const int w = iE - iW, h = jN - jS;
+            for (int t = threadIdx.x; t < w * h; t += BC_THREADS) P(iW + 1 + t % w, jS + 1 + t / w) = dZero;
+            __syncthreads();
+            PFOR(j, jS + 1, jN) P(iW + 1, j) = vW + P(iW, j);
+            __syncthreads();
+            PFOR(j, jS + 1, jN) P(iE, j) = vE + P(iE + 1, j);
+            __syncthreads();
+            PFOR(i, iW + 1, iE) P(i, jS + 1) = vS + P(i, jS);
+            __syncthreads();
+            PFOR(i, iW + 1, iE) P(i, jN) = vN + P(i, jN + 1);
+            __syncthreads();
+            continue;
+        }
+        int bt = R->bd[q][W2_WEST - 1];
+        if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
+            PFOR(j, jS + 1, jN) P(iW, j) = vW + P(iW + 1, j);
+        } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
+            PFOR(j, jS + 1, jN) P(iW, j) = dTwo * vW - P(iW + 1, j);
+        }
+        __syncthreads();
+        bt = R->bd[q][W2_EAST - 1];
+        if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
+            PFOR(j, jS + 1, jN) P(iE + 1, j) = vE + P(iE, j);
+        } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
+            PFOR(j, jS + 1, jN) P(iE + 1, j) = dTwo * vE - P(iE, j);
+        }
+        __syncthreads();
+        bt = R->bd[q][W2_SOUTH - 1];
+        if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
+            PFOR(i, iW + 1, iE) P(i, jS) = vS + P(i, jS + 1);
+        } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
+            PFOR(i, iW + 1, iE) P(i, jS) = dTwo * vS - P(i, jS + 1);
+        }
+        __syncthreads();
+        bt = R->bd[q][W2_NORTH - 1];
+        if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
+            PFOR(i, iW + 1, iE) P(i, jN + 1) = vN + P(i, jN);
+        } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
+            PFOR(i, iW + 1, iE) P(i, jN + 1) = dTwo * vN - P(i, jN);
+        }
+        __syncthreads();
+    }
+}
+
+int w2_vel_bc(wolfd2_ctx *c, double *u, double *v) {
+    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, u, v);
+    c->launches[3]++;
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+int w2_outflow_bc(wolfd2_ctx *c, double *u, double *v) {
+    // skip the launch when no face is an outlet (VelOutflowBCs is then a no-op, :1709-1710)
+    bool any = false;
+    for (int q = 0; q < c->hreg.nreg && !any; ++q)
+        for (int k = 0; k < 4; ++k)
+            if (c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2) any = true;
+    if (!any) return W2_OK;
+    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, u, v);
+    c->launches[1]++;
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+int w2_pres_bc(wolfd2_ctx *c, double *p) {
+    pres_bc_kernel<<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, p);
+    c->launches[3]++;
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}

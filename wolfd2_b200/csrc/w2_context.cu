@@ -1,0 +1,269 @@
+// w2_context.cu -- library configuration, device context, host<->device field copies.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "w2.cuh"
+
+int g_mnx = 302, g_mny = 302, g_mgri = 20, g_mgrj = 10, g_device = 0;  // include/config.f:28-35
+static char g_err[1024] = "";
+
+void w2_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "wolfd2_b200: %s\n", g_err);
+}
+
+extern "C" const char *wolfd2_b200_last_error(void) { return g_err; }
+extern "C" const char *wolfd2_b200_version(void) { return "wolfd2_b200 0.1 (sm_100a, fp64, fmad=false)"; }
+
+extern "C" int wolfd2_b200_config(int32_t mnx, int32_t mny, int32_t mgri, int32_t mgrj) {
+    if (mnx < 4 || mny < 4 || mgri < 1 || mgrj < 1 || (long long)mgri * mgrj > W2_MAXREG) {
+        w2_set_error("wolfd2_b200_config: bad dimensions mnx=%d mny=%d mgri=%d mgrj=%d (mgri*mgrj <= %d)",
+                     mnx, mny, mgri, mgrj, W2_MAXREG);
+        return W2_ERR_BAD_ARG;
+    }
+    g_mnx = mnx; g_mny = mny; g_mgri = mgri; g_mgrj = mgrj;
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_set_device(int32_t device) {
+    g_device = device;
+    return W2_OK;
+}
+
+static int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        w2_set_error("no usable CUDA device (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return W2_ERR_NO_DEVICE;
+    }
+    if (g_device >= n) {
+        w2_set_error("device %d requested but only %d present", g_device, n);
+        return W2_ERR_NO_DEVICE;
+    }
+    W2_CUDA(cudaSetDevice(g_device));
+    return W2_OK;
+}
+
+static int dalloc(double **p, size_t n) {
+    W2_CUDA(cudaMalloc((void **)p, n * sizeof(double)));
+    W2_CUDA(cudaMemset(*p, 0, n * sizeof(double)));
+    return W2_OK;
+}
+
+// Translate the Fortran region tables (bound_cond.f SetUpBCs output) to the device struct.
+int w2_fill_regions(W2Regions *r, int nx, int ny, const int32_t *nReg, const int32_t *nRegBrd,
+                    const int32_t *nRegType, const int32_t *nMomBdTp, const double *dBCVal,
+                    const double *poros, const double *c1, const double *c2) {
+    memset(r, 0, sizeof(*r));
+    const int ni = nReg[0], nj = nReg[1];
+    if (ni < 1 || nj < 1 || ni > g_mgri || nj > g_mgrj || ni * nj > W2_MAXREG) {
+        w2_set_error("bad nReg = (%d,%d) for mgri=%d mgrj=%d", ni, nj, g_mgri, g_mgrj);
+        return W2_ERR_BAD_ARG;
+    }
+    r->nregI = ni; r->nregJ = nj; r->nreg = ni * nj;
+    for (int jr = 1; jr <= nj; ++jr)
+        for (int ir = 1; ir <= ni; ++ir) {
+            const int q = (ir - 1) + ni * (jr - 1);
+            const int base = (ir - 1) + g_mgri * (jr - 1);
+            const int plane = g_mgri * g_mgrj;
+            r->iW[q] = nRegBrd[base + plane * (W2_WEST - 1)];
+            r->iE[q] = nRegBrd[base + plane * (W2_EAST - 1)];
+            r->jS[q] = nRegBrd[base + plane * (W2_SOUTH - 1)];
+            r->jN[q] = nRegBrd[base + plane * (W2_NORTH - 1)];
+            if (r->iW[q] < 1 || r->iE[q] > nx || r->jS[q] < 1 || r->jN[q] > ny ||
+                r->iW[q] >= r->iE[q] || r->jS[q] >= r->jN[q]) {
+                w2_set_error("region (%d,%d) has bad borders W=%d E=%d S=%d N=%d for grid %dx%d", ir, jr,
+                             r->iW[q], r->iE[q], r->jS[q], r->jN[q], nx, ny);
+                return W2_ERR_BAD_ARG;
+            }
+            r->type[q] = nRegType ? nRegType[base] : W2_RM_INTERN;
+            if (r->type[q] == W2_RM_BLOCKG) r->has_blockage = 1;
+            if (r->type[q] == W2_RM_POROUS) r->has_porous = 1;
+            for (int k = 0; k < 4; ++k) {
+                r->bd[q][k] = nMomBdTp ? nMomBdTp[base + plane * k] : W2_BM_INTERN;
+                if (r->bd[q][k] < W2_BM_INTERN || r->bd[q][k] > W2_BM_OUTLT2) {
+                    // the reference prints 'Wrong nBdType? flag in region' and stops (e.g. momentum.f:472-474)
+                    w2_set_error("Wrong nBdType flag %d in region %d,%d face %d", r->bd[q][k], ir, jr, k + 1);
+                    return W2_ERR_BAD_ARG;
+                }
+                for (int l = 0; l < 4; ++l)
+                    r->val[q][k][l] = dBCVal ? dBCVal[base + plane * (k + 4 * l)] : 0.0;
+            }
+            r->poros[q] = poros ? poros[base] : 1.0;
+            r->porc1[q] = c1 ? c1[base] : 0.0;
+            r->porc2[q] = c2 ? c2[base] : 0.0;
+        }
+    for (int jr = 1; jr <= nj; ++jr)
+        for (int ir = 1; ir <= ni; ++ir) {
+            const int q = (ir - 1) + ni * (jr - 1);
+            r->nbW[q] = (ir > 1 && r->type[q - 1] == W2_RM_BLOCKG);
+            r->nbE[q] = (ir < ni && r->type[q + 1] == W2_RM_BLOCKG);
+            r->nbS[q] = (jr > 1 && r->type[q - ni] == W2_RM_BLOCKG);
+            r->nbN[q] = (jr < nj && r->type[q + ni] == W2_RM_BLOCKG);
+        }
+    return W2_OK;
+}
+
+int w2_ctx_set_regions(wolfd2_ctx *c, const W2Regions *r) {
+    if (r != &c->hreg) c->hreg = *r;
+    W2_CUDA(cudaMemcpyAsync(c->dreg, &c->hreg, sizeof(W2Regions), cudaMemcpyHostToDevice, c->stream));
+    W2_CUDA(cudaStreamSynchronize(c->stream));  // hreg may be overwritten by the next shim call
+    W2_TRY(w2_build_pmask(c));
+    W2_TRY(w2_build_mom_masks(c));
+    return W2_OK;
+}
+
+int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
+    *out = nullptr;
+    W2_TRY(check_device());
+    if (nx < 6 || ny < 6) {
+        w2_set_error("grid %dx%d too small (need nx,ny >= 6)", nx, ny);
+        return W2_ERR_BAD_ARG;
+    }
+    if (nx + 1 > g_mnx || ny + 1 > g_mny) {  // CheckGridSize, src/grid.f:551
+        w2_set_error("grid %dx%d does not fit mnx=%d mny=%d (need mnx>=nx+1, mny>=ny+1); call wolfd2_b200_config",
+                     nx, ny, g_mnx, g_mny);
+        return W2_ERR_BAD_ARG;
+    }
+    wolfd2_ctx *c = (wolfd2_ctx *)calloc(1, sizeof(wolfd2_ctx));
+    if (!c) return W2_ERR_BAD_ARG;
+    c->device = g_device;
+    c->nx = nx; c->ny = ny; c->mnx = g_mnx; c->mny = g_mny;
+    c->pitch = ((nx + 2 + 15) / 16) * 16;
+    c->rows = ny + 2;
+    c->nelem = (size_t)c->pitch * (size_t)(c->rows + 1);
+    cudaDeviceProp prop;
+    W2_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    c->num_sms = prop.multiProcessorCount;
+    c->coop_ok = prop.cooperativeLaunch;
+    if (prop.major < 10) {
+        w2_set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        free(c);
+        return W2_ERR_NO_DEVICE;
+    }
+    W2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; ++k) W2_CUDA(cudaEventCreate(&c->ev[k]));
+    W2_CUDA(cudaMalloc((void **)&c->dreg, sizeof(W2Regions)));
+    double **mp = &c->met.rau;
+    for (int k = 0; k < 30; ++k) W2_TRY(dalloc(&mp[k], c->nelem));
+    for (int k = 0; k < W2_F_COUNT; ++k) W2_TRY(dalloc(&c->fld[k], c->nelem));
+    W2_TRY(dalloc(&c->dus, c->nelem));
+    W2_TRY(dalloc(&c->dvs, c->nelem));
+    W2_TRY(dalloc(&c->div, c->nelem));
+    W2_CUDA(cudaMalloc((void **)&c->pmask, c->nelem));
+    W2_CUDA(cudaMemset(c->pmask, 0, c->nelem));
+    W2_CUDA(cudaMalloc((void **)&c->xmask, c->nelem));
+    W2_CUDA(cudaMalloc((void **)&c->ymask, c->nelem));
+    // chain arrays are read in whole segments by the tridiagonal solver: pad generously
+    const long long nmax = ((long long)nx * (long long)ny / 4096 + 3) * 4096;
+    W2_TRY(dalloc(&c->ta, (size_t)nmax));
+    W2_TRY(dalloc(&c->td, (size_t)nmax));
+    W2_TRY(dalloc(&c->tc, (size_t)nmax));
+    W2_TRY(dalloc(&c->tb, (size_t)nmax));
+    W2_TRY(dalloc(&c->tx, (size_t)nmax));
+    W2_TRY(w2_tri_prepare(c, nmax));
+    W2_CUDA(cudaMalloc((void **)&c->d_norm, 64 * sizeof(unsigned long long)));
+    W2_CUDA(cudaMemset(c->d_norm, 0, 64 * sizeof(unsigned long long)));
+    W2_CUDA(cudaMalloc((void **)&c->d_flags, 64 * sizeof(int)));
+    W2_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    W2_CUDA(cudaMallocHost((void **)&c->h_norm, 64 * sizeof(unsigned long long)));
+    W2_CUDA(cudaMallocHost((void **)&c->h_flags, 64 * sizeof(int)));
+    *out = c;
+    return W2_OK;
+}
+
+extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    double **mp = &c->met.rau;
+    for (int k = 0; k < 30; ++k) cudaFree(mp[k]);
+    for (int k = 0; k < W2_F_COUNT; ++k) cudaFree(c->fld[k]);
+    cudaFree(c->dus); cudaFree(c->dvs); cudaFree(c->div); cudaFree(c->qh); cudaFree(c->pmask); cudaFree(c->xmask); cudaFree(c->ymask);
+    cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
+    w2_tri_release(c);
+    cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);
+    cudaFreeHost(c->h_norm); cudaFreeHost(c->h_flags);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int k = 0; k < 8; ++k) cudaEventDestroy(c->ev[k]);
+    cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+// Host (0:mnx,0:mny) <-> device pitched copies of the (0..nx+1, 0..ny+1) window.
+int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host) {
+    W2_CUDA(cudaMemcpy2DAsync(dev, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
+                              (size_t)(c->nx + 2) * 8, (size_t)(c->ny + 2), cudaMemcpyHostToDevice,
+                              c->stream));
+    return W2_OK;
+}
+int w2_download2d(wolfd2_ctx *c, double *host, const double *dev) {
+    W2_CUDA(cudaMemcpy2DAsync(host, (size_t)(c->mnx + 1) * 8, dev, (size_t)c->pitch * 8,
+                              (size_t)(c->nx + 2) * 8, (size_t)(c->ny + 2), cudaMemcpyDeviceToHost,
+                              c->stream));
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_set_params(wolfd2_ctx *c, const wolfd2_params *par) {
+    if (!c || !par) return W2_ERR_BAD_ARG;
+    if (par->nx != c->nx || par->ny != c->ny) {
+        w2_set_error("set_params: grid size %dx%d differs from the context's %dx%d", par->nx, par->ny, c->nx, c->ny);
+        return W2_ERR_BAD_ARG;
+    }
+    if (par->nPpeSolver < 1 || par->nPpeSolver > 6) {
+        w2_set_error("Wrong nPpeSolver flag passed to Ppe: %d", par->nPpeSolver);  // pressure.f:238-239
+        return W2_ERR_BAD_ARG;
+    }
+    c->par = *par;
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_create(wolfd2_ctx **out, const wolfd2_params *par, const wolfd2_regions *reg,
+                                  const wolfd2_metrics *met) {
+    if (!out || !par || !reg || !met) return W2_ERR_BAD_ARG;
+    wolfd2_ctx *c = nullptr;
+    W2_TRY(w2_ctx_create_raw(&c, par->nx, par->ny));
+    int rc = wolfd2_b200_set_params(c, par);
+    if (rc == W2_OK) {
+        W2Regions r;
+        rc = w2_fill_regions(&r, par->nx, par->ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp,
+                             reg->dBCVal, reg->dPRporos, reg->dPRporc1, reg->dPRporc2);
+        if (rc == W2_OK) rc = w2_ctx_set_regions(c, &r);
+    }
+    if (rc == W2_OK) {
+        const double *const *hp = &met->rau;
+        double **dp = &c->met.rau;
+        for (int k = 0; k < 30 && rc == W2_OK; ++k)
+            if (hp[k]) rc = w2_upload2d(c, dp[k], hp[k]);
+        if (rc == W2_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = W2_ERR_CUDA;
+    }
+    if (rc != W2_OK) { wolfd2_b200_destroy(c); return rc; }
+    *out = c;
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const double *host) {
+    if (!c || !host || which < 0 || which >= W2_F_COUNT) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(c->device));
+    W2_TRY(w2_upload2d(c, c->fld[which], host));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    return W2_OK;
+}
+extern "C" int wolfd2_b200_download_field(wolfd2_ctx *c, int32_t which, double *host) {
+    if (!c || !host || which < 0 || which >= W2_F_COUNT) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(c->device));
+    W2_TRY(w2_download2d(c, host, c->fld[which]));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    return W2_OK;
+}
+extern "C" int wolfd2_b200_sync(wolfd2_ctx *c) {
+    if (!c) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    return W2_OK;
+}

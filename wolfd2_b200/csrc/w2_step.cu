@@ -1,0 +1,397 @@
+// w2_step.cu -- the time-step body of program wolfd2 (src/main.f:690-981, cold flow) and the
+// cold-start projection (src/main.f:606-641) on the device, plus the literal gfortran-ABI shims.
+#include <stdlib.h>
+#include <string.h>
+
+#include "w2.cuh"
+
+// ------------------------------------------------------------------------------ residency API
+
+extern "C" int wolfd2_b200_coldstart(wolfd2_ctx *c, int32_t *nSorConv) {
+    if (!c) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(c->device));
+    double *u = c->fld[W2_F_U], *v = c->fld[W2_F_V], *p = c->fld[W2_F_P];
+    int nconv = 0, conv = 0;
+    W2_TRY(w2_vel_bc(c, u, v));                    // :608
+    W2_TRY(w2_ppe(c, u, v, p, &nconv, &conv));     // :613
+    W2_TRY(w2_pres_bc(c, p));                      // :623
+    W2_TRY(w2_project(c, p, u, v));                // :629
+    W2_TRY(w2_vel_bc(c, u, v));                    // :637
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    if (nSorConv) *nSorConv = nconv;
+    return W2_OK;
+}
+
+static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
+    double *u = c->fld[W2_F_U], *v = c->fld[W2_F_V], *p = c->fld[W2_F_P];
+    double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS];
+    double *un = c->fld[W2_F_UN], *vn = c->fld[W2_F_VN], *pn = c->fld[W2_F_PN];
+    cudaStream_t s = c->stream;
+    cudaEventRecord(c->ev[0], s);
+    // :696-704  time-level n copies (t is identically zero on this path; d never changes, so
+    // dn == d and both stay as uploaded)
+    W2_TRY(w2_copy_field(c, pn, p));
+    W2_TRY(w2_copy_field(c, un, u));
+    W2_TRY(w2_copy_field(c, vn, v));
+    W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D]));
+    // :741-747  starred quantities (nmeiter is forced to 1 without thermal energy, :736)
+    W2_TRY(w2_copy_field(c, us, u));
+    W2_TRY(w2_copy_field(c, vs, v));
+    int nQL = -1, nSor = 0, conv = 0;
+    // us == un here, so the initialisation loop of nAuxMomentum (:114-119) is a no-op
+    W2_TRY(w2_nauxmomentum(c, /*init_star=*/0, &nQL));   // :753
+    cudaEventRecord(c->ev[1], s);
+    if (c->par.nfiltu == 1) W2_TRY(w2_filter(c, W2_U, c->par.fpu, us));   // :783
+    if (c->par.nfiltv == 1) W2_TRY(w2_filter(c, W2_V, c->par.fpv, vs));   // :788
+    W2_TRY(w2_vel_bc(c, us, vs));                   // :793
+    W2_TRY(w2_pres_bc(c, p));                       // :797
+    cudaEventRecord(c->ev[2], s);
+    W2_TRY(w2_ppe(c, us, vs, p, &nSor, &conv));     // :803
+    cudaEventRecord(c->ev[3], s);
+    W2_TRY(w2_pres_bc(c, p));                       // :813
+    W2_TRY(w2_project(c, p, us, vs));               // :820
+    W2_TRY(w2_vel_bc(c, us, vs));                   // :829
+    W2_TRY(w2_pres_bc(c, p));                       // :833
+    W2_TRY(w2_copy_field(c, u, us));                // :864-870
+    W2_TRY(w2_copy_field(c, v, vs));
+    W2_TRY(w2_vel_bc(c, u, v));                     // :946
+    W2_TRY(w2_pres_bc(c, p));                       // :950
+    W2_TRY(w2_norm_reset(c));
+    W2_TRY(w2_diffmaxnorm_async(c, pn, p, 0));      // :962-964
+    W2_TRY(w2_diffmaxnorm_async(c, un, u, 1));
+    W2_TRY(w2_diffmaxnorm_async(c, vn, v, 2));
+    cudaEventRecord(c->ev[6], s);
+    double dif[4] = {0, 0, 0, 0};
+    W2_TRY(w2_norm_fetch(c, 3, dif));               // syncs the stream
+    float t_tot = 0, t_mom = 0, t_bc1 = 0, t_ppe = 0, t_tail = 0;
+    cudaEventElapsedTime(&t_tot, c->ev[0], c->ev[6]);
+    cudaEventElapsedTime(&t_mom, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&t_bc1, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&t_ppe, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&t_tail, c->ev[3], c->ev[6]);
+    c->last_ms[0] += t_tot; c->last_ms[1] += t_mom; c->last_ms[2] += t_ppe; c->last_ms[3] += t_bc1 + t_tail;
+    double difmax = dif[0];
+    for (int q = 1; q < 4; ++q) difmax = difmax > dif[q] ? difmax : dif[q];
+    const int diverged = difmax > 1.0e12;          // :969
+    if (log) {
+        log->nQLiter = nQL; log->nSorConv = nSor; log->sor_converged = conv; log->diverged = diverged;
+        for (int q = 0; q < 4; ++q) log->dif[q] = dif[q];
+    }
+    if (diverged) {
+        w2_set_error("* Solution diverged. Please reduce CFL number.");   // :970
+        return W2_ERR_DIVERGED;
+    }
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_step(wolfd2_ctx *c, int32_t nsteps, wolfd2_step_log *logs) {
+    if (!c || nsteps < 0) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(c->device));
+    for (int q = 0; q < 4; ++q) c->last_ms[q] = 0.0;
+    c->sor_ms = 0.0; c->sor_iters = 0;
+    for (int k = 0; k < nsteps; ++k) W2_TRY(one_step(c, logs ? &logs[k] : nullptr));
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_step_host(wolfd2_ctx *c, int32_t nsteps, double *u, double *v, double *p,
+                                     wolfd2_step_log *logs) {
+    if (!c || !u || !v || !p) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(c->device));
+    W2_TRY(w2_upload2d(c, c->fld[W2_F_U], u));
+    W2_TRY(w2_upload2d(c, c->fld[W2_F_V], v));
+    W2_TRY(w2_upload2d(c, c->fld[W2_F_P], p));
+    int rc = wolfd2_b200_step(c, nsteps, logs);
+    if (rc != W2_OK && rc != W2_ERR_DIVERGED) return rc;
+    W2_TRY(w2_download2d(c, u, c->fld[W2_F_U]));
+    W2_TRY(w2_download2d(c, v, c->fld[W2_F_V]));
+    W2_TRY(w2_download2d(c, p, c->fld[W2_F_P]));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+extern "C" int wolfd2_b200_last_timing(wolfd2_ctx *c, double ms[4], int64_t launches[4]) {
+    if (!c) return W2_ERR_BAD_ARG;
+    for (int q = 0; q < 4; ++q) { if (ms) ms[q] = c->last_ms[q]; if (launches) launches[q] = c->launches[q]; }
+    return W2_OK;
+}
+extern "C" int wolfd2_b200_last_sor_timing(wolfd2_ctx *c, double *ms_total, int64_t *iterations) {
+    if (!c) return W2_ERR_BAD_ARG;
+    if (ms_total) *ms_total = c->sor_ms;
+    if (iterations) *iterations = c->sor_iters;
+    return W2_OK;
+}
+
+// ------------------------------------------------------------------------------ literal shims
+// The reference has no error channel on these routines (it prints and `stop`s, e.g.
+// src/momentum.f:472-474); the shims do the same: message on stderr, then abort().
+
+static wolfd2_ctx *g_shim = nullptr;
+
+static void die(const char *who) {
+    fprintf(stderr, "wolfd2_b200: %s failed: %s\n", who, wolfd2_b200_last_error());
+    abort();
+}
+#define SHIM_TRY(call, who) do { if ((call) != W2_OK) die(who); } while (0)
+
+static wolfd2_ctx *shim_ctx(int nx, int ny, const char *who) {
+    if (g_shim && (g_shim->nx != nx || g_shim->ny != ny || g_shim->mnx != g_mnx || g_shim->mny != g_mny)) {
+        wolfd2_b200_destroy(g_shim);
+        g_shim = nullptr;
+    }
+    if (!g_shim) {
+        SHIM_TRY(w2_ctx_create_raw(&g_shim, nx, ny), who);
+        memset(&g_shim->par, 0, sizeof(g_shim->par));
+        g_shim->par.nx = nx; g_shim->par.ny = ny;
+    }
+    if (cudaSetDevice(g_shim->device) != cudaSuccess) die(who);
+    return g_shim;
+}
+
+static void shim_regions(wolfd2_ctx *c, const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+                         const int32_t *nMomBdTp, const double *dBCVal, const double *po, const double *c1,
+                         const double *c2, const char *who) {
+    W2Regions r;
+    SHIM_TRY(w2_fill_regions(&r, c->nx, c->ny, nReg, nRegBrd, nRegType, nMomBdTp, dBCVal, po, c1, c2), who);
+    SHIM_TRY(w2_ctx_set_regions(c, &r), who);
+}
+static void up(wolfd2_ctx *c, double *dev, const double *host, const char *who) { SHIM_TRY(w2_upload2d(c, dev, host), who); }
+static void down(wolfd2_ctx *c, double *host, const double *dev, const char *who) { SHIM_TRY(w2_download2d(c, host, dev), who); }
+static void sync(wolfd2_ctx *c, const char *who) { if (cudaStreamSynchronize(c->stream) != cudaSuccess) { w2_set_error("stream sync: %s", cudaGetErrorString(cudaGetLastError())); die(who); } }
+
+extern "C" void velboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                              const int32_t *nMomBdTp, const double *dBCVal, double *u, double *v) {
+    const char *who = "velboundcond_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nullptr, nMomBdTp, dBCVal, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who);
+    SHIM_TRY(w2_vel_bc(c, c->fld[W2_F_U], c->fld[W2_F_V]), who);
+    down(c, u, c->fld[W2_F_U], who); down(c, v, c->fld[W2_F_V], who);
+    sync(c, who);
+}
+
+extern "C" void veloutflowbcs_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                               const int32_t *nMomBdTp, const double *dBCVal, double *u, double *v) {
+    const char *who = "veloutflowbcs_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nullptr, nMomBdTp, dBCVal, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who);
+    SHIM_TRY(w2_outflow_bc(c, c->fld[W2_F_U], c->fld[W2_F_V]), who);
+    down(c, u, c->fld[W2_F_U], who); down(c, v, c->fld[W2_F_V], who);
+    sync(c, who);
+}
+
+extern "C" void presboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                               const int32_t *nRegType, const int32_t *nMomBdTp, const double *dBCVal, double *p) {
+    const char *who = "presboundcond_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, dBCVal, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_P], p, who);
+    SHIM_TRY(w2_pres_bc(c, c->fld[W2_F_P]), who);
+    down(c, p, c->fld[W2_F_P], who);
+    sync(c, who);
+}
+
+extern "C" void divergence_(const int32_t *nx, const int32_t *ny, const int32_t *nloc, const double *xet,
+                            const double *yet, const double *xzi, const double *yzi, const double *u, const double *v,
+                            double *div) {
+    const char *who = "divergence_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    up(c, c->met.xeu, xet, who); up(c, c->met.yeu, yet, who); up(c, c->met.xzv, xzi, who); up(c, c->met.yzv, yzi, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who);
+    up(c, c->div, div, who);  // cells outside 1..nx,1..ny keep the caller's values
+    SHIM_TRY(w2_divergence(c, c->fld[W2_F_U], c->fld[W2_F_V], c->div, *nloc, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv), who);
+    down(c, div, c->div, who);
+    sync(c, who);
+}
+
+extern "C" void ppe_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                     const int32_t *nRegType, const int32_t *lCartesGrid, const int32_t *nPpeSolver,
+                     const int32_t *msorit, int32_t *nSorConv, const double *dk, const double *sortol,
+                     const double *sorrel, const double *rau, const double *rbu, const double *rbv, const double *rgv,
+                     const double *xeu, const double *yeu, const double *xzv, const double *yzv, const double *u,
+                     const double *v, double *p) {
+    const char *who = "ppe_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nullptr, nullptr, nullptr, nullptr, nullptr, who);
+    if (*nPpeSolver < 1 || *nPpeSolver > 6) {   // pressure.f:238-246: message, then "not converged"
+        fprintf(stderr, " Wrong nPpeSolver flag passed to Ppe\n");
+        *nSorConv = *msorit;
+        return;
+    }
+    c->par.lCartesGrid = *lCartesGrid; c->par.nPpeSolver = *nPpeSolver; c->par.msorit = *msorit;
+    c->par.dk = *dk; c->par.sortol = *sortol; c->par.sorrel = *sorrel;
+    up(c, c->met.rau, rau, who); up(c, c->met.rbu, rbu, who); up(c, c->met.rbv, rbv, who); up(c, c->met.rgv, rgv, who);
+    up(c, c->met.xeu, xeu, who); up(c, c->met.yeu, yeu, who); up(c, c->met.xzv, xzv, who); up(c, c->met.yzv, yzv, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who); up(c, c->fld[W2_F_P], p, who);
+    int n = 0, conv = 0;
+    SHIM_TRY(w2_ppe(c, c->fld[W2_F_U], c->fld[W2_F_V], c->fld[W2_F_P], &n, &conv), who);
+    if (!conv) printf(" Warning: SOR iterations did not converge after %d iterations.\n", *msorit);  // :243
+    *nSorConv = n;
+    down(c, p, c->fld[W2_F_P], who);
+    sync(c, who);
+}
+
+extern "C" void project_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                         const int32_t *nRegType, const int32_t *nMomBdTp, const double *dk, const double *dju,
+                         const double *djv, const double *yeu, const double *xzv, const double *yzu, const double *xev,
+                         const double *p, double *u, double *v) {
+    const char *who = "project_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, nullptr, nullptr, nullptr, nullptr, who);
+    c->par.dk = *dk;
+    up(c, c->met.dju, dju, who); up(c, c->met.djv, djv, who); up(c, c->met.yeu, yeu, who);
+    up(c, c->met.xzv, xzv, who); up(c, c->met.yzu, yzu, who); up(c, c->met.xev, xev, who);
+    up(c, c->fld[W2_F_P], p, who); up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who);
+    SHIM_TRY(w2_project(c, c->fld[W2_F_P], c->fld[W2_F_U], c->fld[W2_F_V]), who);
+    down(c, u, c->fld[W2_F_U], who); down(c, v, c->fld[W2_F_V], who);
+    sync(c, who);
+}
+
+extern "C" void filter_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *nReg,
+                        const int32_t *nRegBrd, const int32_t *nRegType, const int32_t *nMomBdTp,
+                        const int32_t *nTRgType, const double *fp, double *qu) {
+    (void)nTRgType;
+    const char *who = "filter_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, nullptr, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_US], qu, who);
+    SHIM_TRY(w2_filter(c, *ncomp, *fp, c->fld[W2_F_US]), who);
+    down(c, qu, c->fld[W2_F_US], who);
+    sync(c, who);
+}
+
+extern "C" double diffmaxnorm_(const int32_t *nx, const int32_t *ny, const double *un, const double *u) {
+    const char *who = "diffmaxnorm_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_U], u, who);
+    SHIM_TRY(w2_norm_reset(c), who);
+    SHIM_TRY(w2_diffmaxnorm_async(c, c->fld[W2_F_UN], c->fld[W2_F_U], 0), who);
+    double r = 0.0;
+    SHIM_TRY(w2_norm_fetch(c, 1, &r), who);
+    return r;
+}
+extern "C" double dmaxnorm_(const int32_t *nx, const int32_t *ny, const double *u) {
+    const char *who = "dmaxnorm_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    up(c, c->fld[W2_F_U], u, who);
+    SHIM_TRY(w2_norm_reset(c), who);
+    SHIM_TRY(w2_dmaxnorm_async(c, c->fld[W2_F_U], 0), who);
+    double r = 0.0;
+    SHIM_TRY(w2_norm_fetch(c, 1, &r), who);
+    return r;
+}
+
+// a(3,n) AoS in, solution in b (momentum.f:1307-1339)
+__global__ void aos_to_soa_kernel(long long n, const double *__restrict__ a3, double *__restrict__ a, double *__restrict__ d,
+                                  double *__restrict__ c) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = a3[3 * i]; d[i] = a3[3 * i + 1]; c[i] = a3[3 * i + 2]; }
+}
+extern "C" void alttridlu_(const int32_t *n_, double *a, double *b) {
+    const char *who = "alttridlu_";
+    const long long n = *n_;
+    // a context sized for the chain: nx*ny >= n
+    int side = 8;
+    while ((long long)side * side < n + 8) side += 8;
+    if (g_mnx < side + 1 || g_mny < side + 1) { w2_set_error("alttridlu_: n=%lld needs mnx,mny >= %d (wolfd2_b200_config)", n, side + 1); die(who); }
+    wolfd2_ctx *c = shim_ctx(side, side, who);
+    double *tmp = nullptr;  // AoS staging
+    if (cudaMalloc((void **)&tmp, 3 * n * sizeof(double)) != cudaSuccess) { w2_set_error("alttridlu_: out of device memory"); die(who); }
+    cudaMemcpyAsync(tmp, a, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, tmp, c->ta, c->td, c->tc);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    cudaMemcpyAsync(c->tb, b, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    SHIM_TRY(w2_tri_solve(c, n, c->ta, c->td, c->tc, c->tb, c->tx, 1), who);
+    cudaMemcpyAsync(b, c->tx, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    sync(c, who);
+}
+
+static void up_xmom(wolfd2_ctx *c, const double *rbn, const double *rgn, const double *rac, const double *rbc,
+                    const double *dju, const double *xec, const double *yec, const double *xzn, const double *yzn,
+                    const double *xeu, const double *yeu, const double *xzu, const double *yzu, const char *who) {
+    W2Metrics &t = c->met;
+    up(c, t.rbn, rbn, who); up(c, t.rgn, rgn, who); up(c, t.rac, rac, who); up(c, t.rbc, rbc, who); up(c, t.dju, dju, who);
+    up(c, t.xec, xec, who); up(c, t.yec, yec, who); up(c, t.xzn, xzn, who); up(c, t.yzn, yzn, who);
+    up(c, t.xeu, xeu, who); up(c, t.yeu, yeu, who); up(c, t.xzu, xzu, who); up(c, t.yzu, yzu, who);
+}
+static void up_ymom(wolfd2_ctx *c, const double *ran, const double *rbn, const double *rbc, const double *rgc,
+                    const double *djv, const double *xen, const double *yen, const double *xzc, const double *yzc,
+                    const double *xev, const double *yev, const double *xzv, const double *yzv, const char *who) {
+    W2Metrics &t = c->met;
+    up(c, t.ran, ran, who); up(c, t.rbn, rbn, who); up(c, t.rbc, rbc, who); up(c, t.rgc, rgc, who); up(c, t.djv, djv, who);
+    up(c, t.xen, xen, who); up(c, t.yen, yen, who); up(c, t.xzc, xzc, who); up(c, t.yzc, yzc, who);
+    up(c, t.xev, xev, who); up(c, t.yev, yev, who); up(c, t.xzv, xzv, who); up(c, t.yzv, yzv, who);
+}
+
+extern "C" void xmomentum_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                           const int32_t *nRegType, const int32_t *nMomBdTp, const double *dk, const double *re,
+                           const double *dPRporos, const double *dPRporc1, const double *dPRporc2, const double *rbn,
+                           const double *rgn, const double *rac, const double *rbc, const double *dju, const double *xec,
+                           const double *yec, const double *xzn, const double *yzn, const double *xeu, const double *yeu,
+                           const double *xzu, const double *yzu, const double *us, const double *vs, const double *un,
+                           const double *vn, double *dus) {
+    const char *who = "xmomentum_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, nullptr, dPRporos, dPRporc1, dPRporc2, who);
+    c->par.dk = *dk; c->par.re = *re;
+    up_xmom(c, rbn, rgn, rac, rbc, dju, xec, yec, xzn, yzn, xeu, yeu, xzu, yzu, who);
+    up(c, c->fld[W2_F_US], us, who); up(c, c->fld[W2_F_VS], vs, who);
+    up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
+    up(c, c->dus, dus, who);
+    SHIM_TRY(w2_xmomentum(c, c->dus), who);
+    down(c, dus, c->dus, who);
+    sync(c, who);
+}
+
+extern "C" void ymomentum_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                           const int32_t *nRegType, const int32_t *nMomBdTp, const double *dk, const double *re,
+                           const double *fr, const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+                           const double *ran, const double *rbn, const double *rbc, const double *rgc, const double *djv,
+                           const double *xen, const double *yen, const double *xzc, const double *yzc, const double *xev,
+                           const double *yev, const double *xzv, const double *yzv, const double *d, const double *dn,
+                           const double *us, const double *vs, const double *un, const double *vn, double *dvs) {
+    const char *who = "ymomentum_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, nullptr, dPRporos, dPRporc1, dPRporc2, who);
+    c->par.dk = *dk; c->par.re = *re; c->par.fr = *fr;
+    up_ymom(c, ran, rbn, rbc, rgc, djv, xen, yen, xzc, yzc, xev, yev, xzv, yzv, who);
+    up(c, c->fld[W2_F_D], d, who); up(c, c->fld[W2_F_DN], dn, who);
+    up(c, c->fld[W2_F_US], us, who); up(c, c->fld[W2_F_VS], vs, who);
+    up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
+    up(c, c->dvs, dvs, who);
+    SHIM_TRY(w2_ymomentum(c, c->dvs), who);
+    down(c, dvs, c->dvs, who);
+    sync(c, who);
+}
+
+extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int32_t *mqiter, const int32_t *nReg,
+                                 const int32_t *nRegBrd, const int32_t *nRegType, const int32_t *nMomBdTp,
+                                 const double *dk, const double *re, const double *fr, const double *qtol,
+                                 const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+                                 const double *dBCVal, const double *ran, const double *rbn, const double *rgn,
+                                 const double *rac, const double *rbc, const double *rgc, const double *dju,
+                                 const double *djv, const double *xec, const double *yec, const double *xzn,
+                                 const double *yzn, const double *xen, const double *yen, const double *xzc,
+                                 const double *yzc, const double *xeu, const double *yeu, const double *xzu,
+                                 const double *yzu, const double *xev, const double *yev, const double *xzv,
+                                 const double *yzv, const double *d, const double *dn, const double *un, const double *vn,
+                                 double *us, double *vs) {
+    const char *who = "nauxmomentum_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, dBCVal, dPRporos, dPRporc1, dPRporc2, who);
+    c->par.mqiter = *mqiter; c->par.dk = *dk; c->par.re = *re; c->par.fr = *fr; c->par.qtol = *qtol;
+    up_xmom(c, rbn, rgn, rac, rbc, dju, xec, yec, xzn, yzn, xeu, yeu, xzu, yzu, who);
+    up_ymom(c, ran, rbn, rbc, rgc, djv, xen, yen, xzc, yzc, xev, yev, xzv, yzv, who);
+    up(c, c->fld[W2_F_D], d, who); up(c, c->fld[W2_F_DN], dn, who);
+    up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
+    up(c, c->fld[W2_F_US], us, who); up(c, c->fld[W2_F_VS], vs, who);
+    // dus/dvs are local to nAuxMomentum and zeroed there (:139-144)
+    cudaMemsetAsync(c->dus, 0, c->nelem * sizeof(double), c->stream);
+    cudaMemsetAsync(c->dvs, 0, c->nelem * sizeof(double), c->stream);
+    int nql = -1;
+    SHIM_TRY(w2_nauxmomentum(c, /*init_star=*/1, &nql), who);
+    down(c, us, c->fld[W2_F_US], who); down(c, vs, c->fld[W2_F_VS], who);
+    sync(c, who);
+    return nql;
+}
