@@ -150,6 +150,9 @@ int wolfd2_b200_last_timing(wolfd2_ctx *ctx, double ms[4], int64_t launches[4]);
  * and the number of SOR iterations they covered. */
 int wolfd2_b200_last_sor_timing(wolfd2_ctx *ctx, double *ms_total, int64_t *iterations);
 int wolfd2_b200_sync(wolfd2_ctx *ctx);
+/* Page-locked host buffers for the e2e path (cudaMallocHost / cudaFreeHost). */
+void *wolfd2_b200_host_alloc(uint64_t bytes);
+void wolfd2_b200_host_free(void *p);
 
 /* ---- (1) literal shims: gfortran ABI of the reference subroutines --------------- */
 

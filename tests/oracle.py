@@ -8,6 +8,25 @@ import numpy as np
 
 from wolfd2_b200 import _abi
 
+# Routines only the oracle exposes individually (internal to the reference's call tree).
+ORACLE_ONLY = {
+    # src/momentum.f:864
+    "convcoef_": (None, "iiii" "DDDD" "DD" "DD"),
+    "dconvu_": (None, "ii" "DDD" "D"),
+    "ddiffu_": (None, "ii" "DDDD" "D" "D"),
+    "dconvv_": (None, "ii" "DDD" "D"),
+    "ddiffv_": (None, "ii" "DDDD" "D" "D"),
+    # src/pressure.f:329, 384, 457, 548, 673, 819, 976
+    "rhsppe_": (None, "ii" "i" "d" "DD" "D" "D" "D"),
+    "sor_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
+    "sorrb_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
+    "sorrbp_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
+    "slor_": (None, "ii" "i" "i" "io" "ddd" "DD" "DD" "D" "D"),
+    "slorrb_": (None, "ii" "i" "i" "io" "ddd" "DD" "DD" "D" "D"),
+    "slorrbp_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
+}
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ODIR = os.path.join(ROOT, "oracle")
 
@@ -24,7 +43,7 @@ class Oracle:
     def __init__(self, target="liboracle.so"):
         self.lib = C.CDLL(_build(target))
         table = dict(_abi.SIGNATURES)
-        table.update(_abi.ORACLE_ONLY)
+        table.update(ORACLE_ONLY)
         self.f = _abi.bind(self.lib, prefix="orc_", table=table)
         self.lib.orc_config.argtypes = [C.c_int32] * 4
         self.lib.orc_get_errflag.restype = C.c_int32

@@ -1,0 +1,233 @@
+"""GPU parity tests: every routine of SURVEY.md §8a through the C ABI (libwolfd2_b200.so) against the
+CPU oracle on the same seeded inputs.  Bit-exact for the streaming stencils, ghost fills, SOR and
+norms (the library is built with -fmad=false and keeps the reference's operation order); the
+momentum solves use a parallel elimination order and are held to rel-L2 <= 1e-12 per call and
+<= 1e-10 per step (north-star tolerance)."""
+import numpy as np
+import pytest
+
+from oracle import get_oracle
+from util import rand_field, region_args, rel_l2, test_decks
+
+pytestmark = pytest.mark.gpu
+
+TOL_SOLVE = 1e-12   # one momentum component solve, relative L2
+TOL_STEP = 1e-10    # u, v, p after each time step, relative L2 (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from wolfd2_b200 import api as a
+    a.lib()
+    return a
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return get_oracle()
+
+
+DECKS = test_decks() + test_decks(64, 64)[:2]
+IDS = [f"{d.name}-{d.nx}x{d.ny}" for d in DECKS]
+
+
+def _cfg(api, orc, d):
+    api.config(d.mnx, d.mny)
+    orc.config(d.mnx, d.mny)
+
+
+@pytest.mark.parametrize("d", DECKS, ids=IDS)
+def test_ghost_fills_bitwise(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(12345)
+    r = d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    for gf, of in ((api.VelBoundCond, orc.velboundcond), (api.VelOutflowBCs, orc.veloutflowbcs)):
+        ug, vg, uo, vo = u.copy(), v.copy(), u.copy(), v.copy()
+        gf(d.nx, d.ny, r.nReg, r.nRegBrd, r.nMomBdTp, r.dBCVal, ug, vg)
+        of(d.nx, d.ny, r.nReg, r.nRegBrd, r.nMomBdTp, r.dBCVal, uo, vo)
+        assert np.array_equal(ug, uo) and np.array_equal(vg, vo)
+    pg, po = p.copy(), p.copy()
+    api.PresBoundCond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.dBCVal, pg)
+    orc.presboundcond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.dBCVal, po)
+    assert np.array_equal(pg, po)
+
+
+@pytest.mark.parametrize("d", DECKS, ids=IDS)
+def test_divergence_project_filter_norms_bitwise(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(777)
+    r, m = d.regions, d.metrics
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    for nloc, names in ((1, "xeu yeu xzv yzv"), (2, "xev yev xzu yzu")):
+        ms = [m[n] for n in names.split()]
+        dg, do = d.new_field(), d.new_field()
+        api.Divergence(d.nx, d.ny, nloc, *ms, u, v, dg)
+        orc.divergence(d.nx, d.ny, nloc, *ms, u, v, do)
+        assert np.array_equal(dg, do)
+    pm = [m[n] for n in "dju djv yeu xzv yzu xev".split()]
+    ug, vg, uo, vo = u.copy(), v.copy(), u.copy(), v.copy()
+    api.Project(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, *pm, p, ug, vg)
+    orc.project(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, *pm, p, uo, vo)
+    assert np.array_equal(ug, uo) and np.array_equal(vg, vo)
+    ntr = np.zeros(200, np.int32)
+    for comp in (1, 2):
+        qg, qo = u.copy(), u.copy()
+        api.Filter(d.nx, d.ny, comp, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, ntr, 5.0, qg)
+        orc.filter(d.nx, d.ny, comp, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, ntr, 5.0, qo)
+        assert np.array_equal(qg, qo)
+    assert api.DiffMaxNorm(d.nx, d.ny, u, v) == orc.diffmaxnorm(d.nx, d.ny, u, v)
+    assert api.DMaxNorm(d.nx, d.ny, u) == orc.dmaxnorm(d.nx, d.ny, u)
+    # DMaxNorm's odd seed (utility.f:493): a spike at (5,5) must be seen, one at (1,1) must not
+    w = d.new_field(); w[5, 5] = -7.0; w[1, 1] = 9.0
+    assert api.DMaxNorm(d.nx, d.ny, w) == 7.0 == orc.dmaxnorm(d.nx, d.ny, w)
+
+
+@pytest.mark.parametrize("d", DECKS, ids=IDS)
+def test_momentum_components(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(4242)
+    r, m = d.regions, d.metrics
+    us, vs, un, vn = (rand_field(d, rng, -0.5, 0.5) for _ in range(4))
+    xm = [m[n] for n in "rbn rgn rac rbc dju xec yec xzn yzn xeu yeu xzu yzu".split()]
+    dg, do = d.new_field(), d.new_field()
+    api.XMomentum(d.nx, d.ny, *region_args(d), d.dk, d.re, r.dPRporos, r.dPRporc1, r.dPRporc2, *xm, us, vs, un, vn, dg)
+    orc.xmomentum(d.nx, d.ny, *region_args(d), d.dk, d.re, r.dPRporos, r.dPRporc1, r.dPRporc2, *xm, us, vs, un, vn, do)
+    assert rel_l2(dg, do) <= TOL_SOLVE
+    assert np.array_equal(dg == 0.0, do == 0.0)        # same sparsity: identity rows, untouched ghosts
+    ym = [m[n] for n in "ran rbn rbc rgc djv xen yen xzc yzc xev yev xzv yzv".split()]
+    dd, dn = rand_field(d, rng, 0.0, 0.01), rand_field(d, rng, 0.0, 0.01)   # exercise the buoyancy term
+    dg, do = d.new_field(), d.new_field()
+    api.YMomentum(d.nx, d.ny, *region_args(d), d.dk, d.re, d.fr, r.dPRporos, r.dPRporc1, r.dPRporc2, *ym, dd, dn, us, vs, un, vn, dg)
+    orc.ymomentum(d.nx, d.ny, *region_args(d), d.dk, d.re, d.fr, r.dPRporos, r.dPRporc1, r.dPRporc2, *ym, dd, dn, us, vs, un, vn, do)
+    assert rel_l2(dg, do) <= TOL_SOLVE
+    assert np.array_equal(dg == 0.0, do == 0.0)
+
+
+@pytest.mark.parametrize("d", DECKS[:4], ids=IDS[:4])
+def test_nauxmomentum(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(99)
+    r, m = d.regions, d.metrics
+    un, vn = rand_field(d, rng, -0.3, 0.3), rand_field(d, rng, -0.3, 0.3)
+    names = ("ran rbn rgn rac rbc rgc dju djv xec yec xzn yzn xen yen xzc yzc "
+             "xeu yeu xzu yzu xev yev xzv yzv").split()
+    mm = [m[n] for n in names]
+    z = d.new_field()
+    out = []
+    for f in (api.nAuxMomentum, orc.nauxmomentum):
+        us, vs = rand_field(d, np.random.default_rng(5)), rand_field(d, np.random.default_rng(6))
+        n = f(d.nx, d.ny, 6, *region_args(d), d.dk, d.re, d.fr, 1e-4, r.dPRporos, r.dPRporc1, r.dPRporc2,
+              r.dBCVal, *mm, z, z, un, vn, us, vs)
+        out.append((n, us, vs))
+    (ng, ug, vg), (no, uo, vo) = out
+    assert ng == no
+    assert rel_l2(ug, uo) <= 1e-11 and rel_l2(vg, vo) <= 1e-11
+
+
+@pytest.mark.parametrize("n", [7, 64, 4095, 4096, 4097, 70001, 1000003])
+def test_alttridlu(api, orc, n):
+    """AltTridLU incl. the first-row quirk (momentum.f:1319), one chain of n unknowns; sizes straddle
+    the 4096-unknown segment and exercise 1, 2 and 3 levels of the partitioned solver."""
+    api.config(1200, 1200); orc.config(1200, 1200)
+    rng = np.random.default_rng(n)
+    a = np.zeros((n, 3))
+    a[:, 0] = rng.uniform(-1, 1, n); a[:, 2] = rng.uniform(-1, 1, n)
+    a[:, 1] = 2.2 + rng.uniform(0, 1, n)
+    b = rng.uniform(-1, 1, n)
+    ag, bg, ao, bo = a.copy().reshape(-1), b.copy(), a.copy().reshape(-1), b.copy()
+    api.AltTridLU(n, ag, bg)
+    orc.alttridlu(n, ao, bo)
+    assert rel_l2(bg, bo) <= 1e-13
+    # slowly decaying coupling (|off-diagonals| close to the diagonal): spikes reach far
+    a[:, 0] = -1.0; a[:, 2] = -1.0; a[:, 1] = 2.0 + 1e-4
+    ag, bg, ao, bo = a.copy().reshape(-1), b.copy(), a.copy().reshape(-1), b.copy()
+    api.AltTridLU(n, ag, bg)
+    orc.alttridlu(n, ao, bo)
+    assert rel_l2(bg, bo) <= 1e-9   # condition number ~ 4e4: both solves carry ~1e-12 relative error
+
+
+@pytest.mark.parametrize("d", DECKS, ids=IDS)
+@pytest.mark.parametrize("cart", [1, 0])
+@pytest.mark.parametrize("solver", [5, 6])
+def test_ppe_bitwise(api, orc, d, cart, solver):
+    """Ppe with the red/black point SOR: identical iterate path => identical iteration count and p."""
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(31337)
+    r, m = d.regions, d.metrics
+    u, v, p = rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01)
+    pm8 = [m[n] for n in "rau rbu rbv rgv xeu yeu xzv yzv".split()]
+    for msorit, tol in ((3000, 1e-8), (25, 1e-8), (60, 0.0)):
+        pg, po = p.copy(), p.copy()
+        ng = api.Ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, cart, solver, msorit, d.dk, tol, 1.4, *pm8, u, v, pg)
+        no = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, cart, solver, msorit, d.dk, tol, 1.4, *pm8, u, v, po)
+        assert ng == no
+        assert np.array_equal(pg, po)
+    assert ng == 60  # tolerance 0 never converges: nSorConv = msorit (pressure.f:242-246)
+
+
+STEP_DECKS = None
+
+
+def _step_decks():
+    from wolfd2_b200 import deck as dk
+    ds = [dk.cavity(64, re=100.0, dt=0.01), dk.cavity(37, re=400.0, dt=0.02, ny=29),
+          dk.channel(48, re=100.0, dt=0.005, ny=40), dk.channel(48, re=100.0, dt=0.005, ny=40, fully_dev=False),
+          dk.backward_step(64, re=100.0, dt=0.005, ny=48), dk.cavity(130, re=1000.0, dt=0.004, ny=66)]
+    for d in ds:
+        d.msorit = 300
+    return ds
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_time_steps(api, orc, k):
+    """Cold start + 8 time steps: per-step rel-L2 of u, v, p, identical QL / SOR iteration counts and
+    identical PrintDiff tuple to 1e-9; drift over the run reported."""
+    d = _step_decks()[k]
+    orc.config(d.mnx, d.mny)
+    uo, vo, po = d.new_field(), d.new_field(), d.new_field()
+    nso = orc.coldstart(d, uo, vo, po)
+    worst = 0.0
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        assert ctx.coldstart() == nso
+        for step in range(8):
+            lg = ctx.step(1)[0]
+            rc, lo = orc.step(d, uo, vo, po, 1)
+            assert rc == 0
+            assert lg["nQLiter"] == lo[0]["nQLiter"] and lg["nSorConv"] == lo[0]["nSorConv"]
+            ug, vg, pg = ctx.download(api.F_U), ctx.download(api.F_V), ctx.download(api.F_P)
+            errs = [rel_l2(ug, uo), rel_l2(vg, vo), rel_l2(pg, po)]
+            worst = max(worst, *errs)
+            assert max(errs) <= TOL_STEP, f"{d.name} step {step}: rel-L2 (u,v,p) = {errs}"
+            np.testing.assert_allclose(lg["dif"][:3], lo[0]["dif"][:3], rtol=1e-9, atol=1e-14)
+    print(f"{d.name}: worst rel-L2 over 8 steps = {worst:.2e}")
+
+
+def test_step_host_equals_resident(api):
+    """The host-buffer entry point (e2e path) gives the same fields as the resident one."""
+    from wolfd2_b200 import deck as dk
+    d = dk.channel(48, re=100.0, dt=0.005, ny=40)
+    d.msorit = 100
+    with api.Context(d) as c1, api.Context(d) as c2:
+        z = d.new_field()
+        for c in (c1, c2):
+            for w in (api.F_U, api.F_V, api.F_P):
+                c.upload(w, z)
+            c.coldstart()
+        c1.step(3)
+        u, v, p = c2.download(api.F_U), c2.download(api.F_V), c2.download(api.F_P)
+        for _ in range(3):
+            c2.step_host(u, v, p, 1)
+        assert np.array_equal(u, c1.download(api.F_U)) and np.array_equal(p, c1.download(api.F_P))
+
+
+def test_unsupported_is_loud(api):
+    from wolfd2_b200 import deck as dk
+    d = dk.cavity(32, re=100.0, dt=0.01)
+    d.ppe_solver = "sor"
+    with api.Context(d) as ctx:
+        with pytest.raises(api.Wolfd2Error):
+            ctx.coldstart()

@@ -1,8 +1,8 @@
 """ctypes signature table of the reference's hot-path subroutines (gfortran ABI).
 
-One table binds two libraries: the product's literal shims in libwolfd2_b200.so
-(include/wolfd2_b200.h, section (1)) and -- in tests only -- the CPU oracle, whose
-functions carry the same argument lists behind an ``orc_`` prefix.
+The table binds the literal shims of libwolfd2_b200.so (include/wolfd2_b200.h, section (1)).
+`bind` accepts a symbol prefix so that the test suite can bind a second library exposing the same
+argument lists (the CPU checker under tests/); nothing in this package loads such a library.
 
 Argument kinds:  i = INTEGER scalar by reference (in),  o = INTEGER scalar (out),
 d = REAL*8 scalar by reference,  I = INTEGER array,  D = REAL*8 array.
@@ -45,24 +45,6 @@ SIGNATURES = {
     "dmaxnorm_": (C.c_double, "ii" "D"),
 }
 
-# Routines only the oracle exposes individually (internal to the reference's call tree).
-ORACLE_ONLY = {
-    # src/momentum.f:864
-    "convcoef_": (None, "iiii" "DDDD" "DD" "DD"),
-    "dconvu_": (None, "ii" "DDD" "D"),
-    "ddiffu_": (None, "ii" "DDDD" "D" "D"),
-    "dconvv_": (None, "ii" "DDD" "D"),
-    "ddiffv_": (None, "ii" "DDDD" "D" "D"),
-    # src/pressure.f:329, 384, 457, 548, 673, 819, 976
-    "rhsppe_": (None, "ii" "i" "d" "DD" "D" "D" "D"),
-    "sor_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
-    "sorrb_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
-    "sorrbp_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
-    "slor_": (None, "ii" "i" "i" "io" "ddd" "DD" "DD" "D" "D"),
-    "slorrb_": (None, "ii" "i" "i" "io" "ddd" "DD" "DD" "D" "D"),
-    "slorrbp_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
-}
-
 _KIND = {"i": c_i32p, "o": c_i32p, "d": c_f64p, "I": c_i32p, "D": c_f64p}
 
 
@@ -88,7 +70,7 @@ def bind(lib, prefix="", table=None):
         fn.restype = restype
         fn.argtypes = [_KIND[k] for k in kinds]
 
-        def call(*args, _fn=fn, _kinds=kinds, _name=name):
+        def call(*args, _fn=fn, _kinds=kinds, _name=name, _restype=restype):
             n_in = sum(1 for k in _kinds if k != "o")
             if len(args) != n_in:
                 raise TypeError(f"{_name}: expected {n_in} arguments, got {len(args)}")
@@ -114,7 +96,7 @@ def bind(lib, prefix="", table=None):
             r = _fn(*cargs)
             if outs:
                 vals = tuple(o.value for o in outs)
-                return (r,) + vals if restype is not None else (vals[0] if len(vals) == 1 else vals)
+                return (r,) + vals if _restype is not None else (vals[0] if len(vals) == 1 else vals)
             return r
 
         out[name.rstrip("_")] = call

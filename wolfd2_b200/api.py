@@ -59,6 +59,10 @@ def lib():
     L.wolfd2_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.wolfd2_b200_last_sor_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.wolfd2_b200_sync.argtypes = [C.c_void_p]
+    L.wolfd2_b200_host_alloc.argtypes = [C.c_uint64]
+    L.wolfd2_b200_host_alloc.restype = C.c_void_p
+    L.wolfd2_b200_host_free.argtypes = [C.c_void_p]
+    L.wolfd2_b200_host_free.restype = None
     _lib = L
     _fn = _abi.bind(L)
     return L
@@ -176,3 +180,18 @@ class Context:
 
     def sync(self):
         _check(lib().wolfd2_b200_sync(self._h), "sync")
+
+
+def pinned_field(deck):
+    """A zeroed REAL*8 f(0:mnx,0:mny) in page-locked host memory (for the e2e path)."""
+    n = (deck.mny + 1) * (deck.mnx + 1)
+    ptr = lib().wolfd2_b200_host_alloc(n * 8)
+    if not ptr:
+        raise Wolfd2Error("pinned allocation failed: " + lib().wolfd2_b200_last_error().decode())
+    buf = (C.c_double * n).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64).reshape(deck.mny + 1, deck.mnx + 1)
+    return arr, ptr
+
+
+def pinned_free(ptr):
+    lib().wolfd2_b200_host_free(ptr)

@@ -267,3 +267,14 @@ extern "C" int wolfd2_b200_sync(wolfd2_ctx *c) {
     W2_CUDA(cudaStreamSynchronize(c->stream));
     return W2_OK;
 }
+
+extern "C" void *wolfd2_b200_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaSetDevice(g_device) != cudaSuccess || cudaMallocHost(&p, bytes) != cudaSuccess) {
+        w2_set_error("host_alloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    memset(p, 0, bytes);
+    return p;
+}
+extern "C" void wolfd2_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
