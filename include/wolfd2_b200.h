@@ -113,6 +113,9 @@ enum { W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_US = 3, W2_F_VS = 4, W2_F_UN = 5
 int wolfd2_b200_config(int32_t mnx, int32_t mny, int32_t mgri, int32_t mgrj);
 /* Select the CUDA device (default 0). */
 int wolfd2_b200_set_device(int32_t device);
+/* Tuning knobs that do not change results: "sor_fused_T" = 0 (one kernel per colour half-sweep),
+ * 1 or 2 (red+black and T iterations fused into one pass; default 2). */
+int wolfd2_b200_set_option(const char *name, int32_t value);
 const char *wolfd2_b200_last_error(void);
 const char *wolfd2_b200_version(void);
 

@@ -231,3 +231,36 @@ def test_unsupported_is_loud(api):
     with api.Context(d) as ctx:
         with pytest.raises(api.Wolfd2Error):
             ctx.coldstart()
+
+
+def _fused_decks():
+    from wolfd2_b200 import deck as dk
+    return [dk.cavity(300, re=100.0, dt=0.001, ny=40), dk.channel(600, re=100.0, dt=0.001, ny=90),
+            dk.backward_step(520, re=100.0, dt=0.001, ny=64), dk.cavity(254, re=100.0, dt=0.001, ny=8),
+            dk.cavity(1030, re=100.0, dt=0.001, ny=37)]
+
+
+@pytest.mark.parametrize("k", range(5))
+@pytest.mark.parametrize("T", [0, 1, 2])
+def test_ppe_fused_pipeline_bitwise(api, orc, k, T):
+    """The fused red/black pipeline (several strips, several bands, blockage sentinel, T iterations per
+    pass incl. convergence in the middle of a pass) must reproduce SorRB bit for bit."""
+    d = _fused_decks()[k]
+    _cfg(api, orc, d)
+    api.set_option("sor_fused_T", T)
+    try:
+        rng = np.random.default_rng(2024 + k)
+        r, m = d.regions, d.metrics
+        u, v, p = rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01)
+        pm8 = [m[n] for n in "rau rbu rbv rgv xeu yeu xzv yzv".split()]
+        seen = set()
+        for msorit, tol in ((40, 1e-3), (41, 2e-3), (400, 3e-4), (401, 1e-4), (7, 0.0), (8, 0.0), (1, 1.0), (2, 1.0), (3, 1.0)):
+            pg, po = p.copy(), p.copy()
+            ng = api.Ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 5, msorit, d.dk, tol, 1.7, *pm8, u, v, pg)
+            no = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 5, msorit, d.dk, tol, 1.7, *pm8, u, v, po)
+            assert ng == no, (msorit, tol)
+            assert np.array_equal(pg, po), (msorit, tol)
+            seen.add(no % 2)
+        assert seen == {0, 1}   # both odd and even convergence points were exercised
+    finally:
+        api.set_option("sor_fused_T", -1)

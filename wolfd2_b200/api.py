@@ -47,6 +47,7 @@ def lib():
     L.wolfd2_b200_version.restype = C.c_char_p
     L.wolfd2_b200_config.argtypes = [C.c_int32] * 4
     L.wolfd2_b200_set_device.argtypes = [C.c_int32]
+    L.wolfd2_b200_set_option.argtypes = [C.c_char_p, C.c_int32]
     L.wolfd2_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.POINTER(Regions), C.POINTER(Metrics)]
     L.wolfd2_b200_destroy.argtypes = [C.c_void_p]
     L.wolfd2_b200_destroy.restype = None
@@ -80,6 +81,10 @@ def config(mnx, mny, mgri=20, mgrj=10):
 
 def set_device(dev):
     _check(lib().wolfd2_b200_set_device(dev), "wolfd2_b200_set_device")
+
+
+def set_option(name, value):
+    _check(lib().wolfd2_b200_set_option(name.encode(), int(value)), "wolfd2_b200_set_option")
 
 
 def _routine(name):

@@ -137,7 +137,7 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
     c->nx = nx; c->ny = ny; c->mnx = g_mnx; c->mny = g_mny;
     c->pitch = ((nx + 2 + 15) / 16) * 16;
     c->rows = ny + 2;
-    c->nelem = (size_t)c->pitch * (size_t)(c->rows + 1);
+    c->nelem = (size_t)c->pitch * (size_t)(c->rows + 1) + 512;  // guard: strip loads may overrun a row
     cudaDeviceProp prop;
     W2_CUDA(cudaGetDeviceProperties(&prop, c->device));
     c->num_sms = prop.multiProcessorCount;
@@ -278,3 +278,14 @@ extern "C" void *wolfd2_b200_host_alloc(uint64_t bytes) {
     return p;
 }
 extern "C" void wolfd2_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern int g_sor_T;
+extern "C" int wolfd2_b200_set_option(const char *name, int32_t value) {
+    if (name && !strcmp(name, "sor_fused_T")) {
+        if (value < -1 || value > 2) { w2_set_error("sor_fused_T must be -1 (default), 0, 1 or 2"); return W2_ERR_BAD_ARG; }
+        g_sor_T = value;
+        return W2_OK;
+    }
+    w2_set_error("unknown option %s", name ? name : "(null)");
+    return W2_ERR_BAD_ARG;
+}

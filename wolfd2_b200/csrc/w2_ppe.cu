@@ -14,6 +14,8 @@
 // a `done` word; the last CTA of each red sweep closes the iteration, tests
 // `m > 1 .and. dif < sortol` (:534-537) and publishes the result for the launches already queued
 // behind it, which then return immediately.
+#include <stdlib.h>
+
 #include "w2.cuh"
 
 #define P(i, j) p[IDX(i, j)]
@@ -114,14 +116,17 @@ __global__ void __launch_bounds__(256) div_rhs_kernel(int nx, int ny, int pitch,
                                                       const double *__restrict__ xzv, const double *__restrict__ yzv,
                                                       const double *__restrict__ u, const double *__restrict__ v,
                                                       const unsigned char *__restrict__ mask, int has_mask,
-                                                      double *__restrict__ b, double *__restrict__ div_out) {
+                                                      int sentinel, double *__restrict__ b,
+                                                      double *__restrict__ div_out) {
     const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
     for (int j = 2 + blockIdx.y; j <= ny; j += gridDim.y) {
         if (i > nx) continue;
         double d = div_point<1>(i, j, pitch, xeu, yeu, xzv, yzv, u, v);
-        if (has_mask && mask[IDX(i, j)]) d = 0.0;
+        const bool masked = has_mask && mask[IDX(i, j)];
+        if (masked) d = 0.0;
         if (div_out) div_out[IDX(i, j)] = d;
-        b[IDX(i, j)] = d / dk;
+        // the fused SOR kernel recognises identity rows by a NaN in b (it then uses b = 0, a = identity)
+        b[IDX(i, j)] = (masked && sentinel) ? __longlong_as_double(0x7ff8000000000000LL) : d / dk;
     }
 }
 
@@ -216,6 +221,18 @@ static int sor_chunk(const wolfd2_ctx *c) {
 }
 
 // Ppe (:30-249) with nPpeSolver 5 or 6 (SorRB / SorRBP: same update, same max-norm).
+int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
+                 int *iters_done);
+
+int g_sor_T = -1;   // set by wolfd2_b200_set_option("sor_fused_T", t); -1: take W2_SOR_T or the default
+static int fused_T() {   // 0 selects the plain half-sweep kernels, 1 or 2 the fused pipeline
+    if (g_sor_T >= 0) return g_sor_T;
+    const char *e = getenv("W2_SOR_T");
+    int t = e ? atoi(e) : 2;
+    if (t < 0 || t > 2) t = 2;
+    return t;
+}
+
 int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSorConv, int *converged) {
     const wolfd2_params &par = c->par;
     if (par.nPpeSolver != W2_PPE_RB_SOR && par.nPpeSolver != W2_PPE_PAR_RB_SOR) {
@@ -230,10 +247,27 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
     SorCtl *ctl = (SorCtl *)c->d_flags;
     static_assert(sizeof(SorCtl) <= 64 * sizeof(int), "ctl block too large");
 
+    const int T = (cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
     dim3 g2((nx - 1 + 255) / 256, (ny - 1) < 2048 ? (ny - 1) : 2048);
     div_rhs_kernel<<<g2, 256, 0, c->stream>>>(nx, ny, pitch, par.dk, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv, u, v,
-                                              c->pmask, has_mask, b, cart ? nullptr : c->div);
+                                              c->pmask, has_mask, T > 0, b, cart ? nullptr : c->div);
     c->launches[2]++;
+    if (T > 0) {
+        // fused red/black pipeline (w2_sor_fused.cu); c->div is free on Cartesian grids and serves as
+        // the second pressure buffer
+        double *pf = nullptr;
+        int iters = 0;
+        cudaEventRecord(c->ev[4], c->stream);
+        W2_TRY(w2_sor_fused(c, p, c->div, T, nSorConv, converged, &pf, &iters));
+        if (pf != p) W2_CUDA(cudaMemcpyAsync(p, pf, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        cudaEventRecord(c->ev[5], c->stream);
+        W2_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+        c->sor_ms += ms;
+        c->sor_iters += iters;
+        return W2_OK;
+    }
     sor_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
     W2_CUDA(cudaGetLastError());
 

@@ -1,0 +1,320 @@
+// w2_sor_fused.cu -- red/black point SOR (SorRB / SorRBP, src/pressure.f:457-656) with both colours
+// and T whole iterations fused into ONE pass over HBM.
+//
+// The plain half-sweep kernel (w2_ppe.cu) is already at the DRAM limit for what it moves
+// (ncu: 652 MB per half-sweep at 4096^2 against 537 MB algorithmic), so the only way up is to move
+// fewer bytes.  This kernel reads p, b, rau, rgv once and writes p once per T iterations
+// (40/T B/cell/iteration instead of 80), out of place (p_src -> p_dst, ping-pong).
+//
+// Structure: each CTA owns a strip of 256 columns (256-4T of them "owned", the rest halo that is
+// recomputed redundantly -- bit-identical, since every cell's arithmetic is the same wherever it
+// runs) and streams down a band of rows.  Rows of the four arrays are staged in a shared-memory ring
+// by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), several rows ahead of use.  A software
+// pipeline of 2T half-sweep stages runs on the ring: when row r has landed, stage s (s odd = black
+// of iteration (s+1)/2, s even = red) relaxes row r-2s+1 in place.  With that two-row lag every
+// stage of a time step reads only data written in earlier time steps, so all 2T stages (4 warps
+// each) run concurrently with ONE block barrier per streamed row.  After stage 2T a row is final
+// and goes back to HBM.
+//
+// Arithmetic per point is literally that of the reference (:509-513), FMA contraction off, so the
+// iterate path and max-norm are bit-identical to SorRB; the per-iteration max|sum| is accumulated
+// separately for each of the T fused iterations.  If the convergence test (:534) fires for an
+// iteration in the middle of a pass, the next launch redoes the pass from the untouched source
+// with exactly that many iterations -- the returned p and iteration count are those of the
+// reference.  Blockage (identity) rows arrive as a NaN sentinel in b.
+#include "w2.cuh"
+
+#define SF_W 256              // strip width held in shared memory (cells)
+#define SF_PADL 2             // left pad (keeps TMA destinations 16-byte aligned)
+#define SF_STRIDE (SF_W + 4)  // shared row stride in doubles
+
+struct SorFCtl {           // device-resident loop control
+    int done;              // 1: solve finished, later launches return at once
+    int m;                 // iterations completed
+    int nconv;             // converged iteration (0: not converged)
+    int ticket;            // CTAs finished in the current pass
+    int cur;               // 0: current iterate is buffer A, 1: buffer B
+    int redo;              // >0: next pass repeats from the same source with `redo` iterations
+    int pad0, pad1;
+    unsigned long long slot[8];  // max |sum| of each fused iteration of the current pass
+    unsigned long long last_dif;
+};
+
+struct SorFArgs {
+    int nx, ny, pitch;
+    int nstrips, nbands, rows_per_band, own_w;
+    int msorit;
+    double sorrel, sortol;
+    const double *rau, *rgv, *b;
+    double *pA, *pB;
+    SorFCtl *ctl;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void sorf_ctl_reset(SorFCtl *c) {
+    c->done = 0; c->m = 0; c->nconv = 0; c->ticket = 0; c->cur = 0; c->redo = 0;
+    for (int k = 0; k < 8; ++k) c->slot[k] = 0ull;
+    c->last_dif = 0ull;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T * 256, 1) sor_rb_fused_kernel(SorFArgs a) {
+    constexpr int NS = 2 * T;                 // half-sweep stages
+    constexpr int R = (T == 1) ? 8 : 16;      // ring depth (rows), power of two
+    constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
+    constexpr int D = R - LIVE - 1;           // prefetch distance (rows)
+    constexpr int H = 2 * T;                  // halo columns/rows on a non-physical side
+    static_assert(D >= 2, "ring too shallow");
+
+    SorFCtl *ctl = a.ctl;
+    if (ctl->done) return;
+    // iterations this pass: a redo pass repeats `redo` iterations, else up to T
+    int Tp = ctl->redo > 0 ? ctl->redo : min(T, a.msorit - ctl->m);
+    const int cur = ctl->cur;
+    const double *__restrict__ psrc = cur ? a.pB : a.pA;
+    double *__restrict__ pdst = cur ? a.pA : a.pB;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sP = reinterpret_cast<double *>(smem_raw);
+    double *sB = sP + R * SF_STRIDE;
+    double *sU = sB + R * SF_STRIDE;   // rau
+    double *sV = sU + R * SF_STRIDE;   // rgv
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sV + R * SF_STRIDE);
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x;
+    const int nx = a.nx, ny = a.ny, pitch = a.pitch;
+    const int strip = blockIdx.x, band = blockIdx.y;
+    // columns: strip covers global i in [i0, i0+256); i0 even
+    const int i0 = strip * a.own_w;
+    const bool physL = (strip == 0), physR = (i0 + SF_W - 1 >= nx + 1);
+    const int own_lo = physL ? 2 : i0 + H;                             // owned columns (global i)
+    const int own_hi = physR ? nx : min(nx, i0 + H + a.own_w - 1);
+    // rows: band owns [jA, jB]; loads [jL0, jL1]
+    const int jA = 2 + band * a.rows_per_band;
+    const int jB = min(ny, jA + a.rows_per_band - 1);
+    const int jL0 = max(1, jA - H), jL1 = min(ny + 1, jB + H);
+    const bool physS = (jL0 == 1), physN = (jL1 == ny + 1);
+
+    if (tid == 0) {
+        for (int k = 0; k < R; ++k) mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero the pad cells once (read by edge threads, never used by owned cells)
+    for (int k = tid; k < R * 4; k += blockDim.x) {
+        const int row = k >> 2, q = k & 3;
+        const int off = row * SF_STRIDE + (q < 2 ? q : SF_W + q);
+        sP[off] = 0.0; sB[off] = 0.0; sU[off] = 0.0; sV[off] = 0.0;
+    }
+    __syncthreads();
+
+    auto issue_row = [&](int row) {   // one thread: 4 bulk copies of 2 KB into ring slot row%R
+        const int slot = row & (R - 1);
+        const size_t g = (size_t)pitch * row + i0;
+        mbar_expect_tx(&bars[slot], 4u * SF_W * 8u);
+        tma_load_1d(sP + slot * SF_STRIDE + SF_PADL, psrc + g, SF_W * 8, &bars[slot]);
+        tma_load_1d(sB + slot * SF_STRIDE + SF_PADL, a.b + g, SF_W * 8, &bars[slot]);
+        tma_load_1d(sU + slot * SF_STRIDE + SF_PADL, a.rau + g, SF_W * 8, &bars[slot]);
+        tma_load_1d(sV + slot * SF_STRIDE + SF_PADL, a.rgv + g, SF_W * 8, &bars[slot]);
+    };
+    if (tid == 0)
+        for (int row = jL0; row <= min(jL1, jL0 + D); ++row) issue_row(row);
+
+    const int stage = (tid >> 7) + 1;         // 1..NS, 128 threads (4 warps) per stage
+    const int k = tid & 127;                   // column pair handled by this thread
+    const int colour = (stage - 1) & 1;        // 0 = black (i+j even), 1 = red
+    const bool stage_on = stage <= 2 * Tp;
+    double lmax = 0.0;
+    const double sorrel = a.sorrel;
+
+    const int r_end = jB + 4 * T - 1;
+    for (int r = jL0; r <= r_end; ++r) {
+        if (r <= jL1) mbar_wait(&bars[r & (R - 1)], (unsigned)(((r - jL0) / R) & 1));
+        // ring slots are indexed by absolute row; parity counts how often the slot has been refilled
+        // ---- stage work: row q = r - 2*stage + 1
+        const int q = r - 2 * stage + 1;
+        if (stage_on && q >= 2 && q <= ny && q - 1 >= jL0 && q + 1 <= jL1) {
+            const int c = 2 * k + ((colour + q) & 1);     // strip-local column of the active cell (i0 even)
+            const int i = i0 + c;
+            if (i >= 2 && i <= nx) {
+                const int sq = (q & (R - 1)) * SF_STRIDE + SF_PADL + c;
+                const int ss = ((q - 1) & (R - 1)) * SF_STRIDE + SF_PADL + c;
+                const int sn = ((q + 1) & (R - 1)) * SF_STRIDE + SF_PADL + c;
+                const double bb = sB[sq];
+                const double pc = sP[sq];
+                double sum;
+                if (bb != bb) {           // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
+                    sum = 0.0 - pc;
+                } else {
+                    const double a1 = sV[ss], a2 = sU[sq - 1], a4 = sU[sq], a5 = sV[sq];
+                    const double a3 = -a4 - a2 - a5 - a1;
+                    sum = bb - a1 * sP[ss] - a2 * sP[sq - 1] - a4 * sP[sq + 1] - a5 * sP[sn];
+                    sum = sum / a3 - pc;
+                }
+                sP[sq] = pc + sorrel * sum;
+                if (i >= own_lo && i <= own_hi && q >= jA && q <= jB) lmax = fmax(lmax, fabs(sum));
+            }
+        }
+        // ---- store the row that has passed every stage: qs = r - 4T + 1 (by the last stage's threads,
+        // one time step later, i.e. after the barrier below made it final)
+        __syncthreads();
+        {
+            const int qs = r - 4 * T + 1;
+            if (stage == NS && qs >= jA && qs <= jB) {
+                const int c = 2 * k;
+                const int i = i0 + c;
+                const int sq = (qs & (R - 1)) * SF_STRIDE + SF_PADL + c;
+                const double2 v = *reinterpret_cast<const double2 *>(&sP[sq]);
+                double *g = pdst + (size_t)pitch * qs + i;
+                const bool in0 = i >= own_lo && i <= own_hi, in1 = i + 1 >= own_lo && i + 1 <= own_hi;
+                if (in0 && in1) *reinterpret_cast<double2 *>(g) = v;
+                else if (in0) g[0] = v.x;
+                else if (in1) g[1] = v.y;
+            }
+        }
+        // ---- prefetch: the slot of row r+D+1 held row r+D+1-R, whose last use (the store above at time
+        // r' = row+4T-1 <= r) is behind the barrier
+        if (tid == 0) {
+            const int row = r + D + 1;
+            if (row <= jL1) issue_row(row);
+        }
+    }
+    (void)physS; (void)physN;
+
+    // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const double v = ((stage - 1) >> 1) == t ? lmax : 0.0;
+        const double m = w2_block_max(v, red);
+        if (tid == 0 && t < Tp) atomicMax(&ctl->slot[t], w2_dbits(m));
+    }
+    // ---- the last CTA closes the pass
+    if (tid == 0) {
+        __threadfence();
+        const int total = gridDim.x * gridDim.y;
+        if (atomicAdd(&ctl->ticket, 1) == total - 1) {
+            __threadfence();
+            int m = ctl->m;
+            int conv_t = -1;
+            unsigned long long last = 0ull;
+            for (int t = 0; t < Tp; ++t) {
+                const unsigned long long bits = atomicExch(&ctl->slot[t], 0ull);
+                last = bits;
+                const double dif = __longlong_as_double((long long)bits);
+                if (conv_t < 0 && (m + t + 1) > 1 && dif < a.sortol) conv_t = t;   // :534
+            }
+            ctl->ticket = 0;
+            if (ctl->redo > 0) {                       // this was the repeat of a converged prefix
+                ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1; ctl->redo = 0;
+            } else if (conv_t == Tp - 1) {             // converged exactly at the end of the pass
+                ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1;
+            } else if (conv_t >= 0) {                  // converged mid-pass: repeat conv_t+1 iterations
+                ctl->redo = conv_t + 1;
+            } else {
+                ctl->m = m + Tp; ctl->cur = cur ^ 1;
+                if (m + Tp >= a.msorit) ctl->done = 1;
+            }
+            ctl->last_dif = last;
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+static bool g_attr_set[3] = {false, false, false};
+
+template <int T>
+static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
+    constexpr int R = (T == 1) ? 8 : 16;
+    const size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
+    if (!g_attr_set[T]) {
+        W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_attr_set[T] = true;
+    }
+    sor_rb_fused_kernel<T><<<grid, T * 256, smem, c->stream>>>(a);
+    return W2_OK;
+}
+
+// Runs the whole SOR loop of SorRB on p (Cartesian grids).  b must already hold div/dk with the NaN
+// sentinel at identity rows.  scratch is a second full-size buffer.  On return *p_final points at the
+// buffer holding the solution (p or scratch) -- the caller swaps its pointers accordingly.
+int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
+                 int *iters_done) {
+    const wolfd2_params &par = c->par;
+    const int nx = c->nx, ny = c->ny;
+    SorFCtl *ctl = (SorFCtl *)c->d_flags;
+    static_assert(sizeof(SorFCtl) <= 64 * sizeof(int), "ctl block too large");
+    SorFArgs a;
+    a.nx = nx; a.ny = ny; a.pitch = c->pitch;
+    a.own_w = SF_W - 4 * T;
+    a.nstrips = 1;
+    while ((a.nstrips - 1) * a.own_w + SF_W < nx + 2) a.nstrips++;
+    // bands: about three waves of CTAs over the machine
+    int want = (3 * c->num_sms + a.nstrips - 1) / a.nstrips;
+    if (want < 1) want = 1;
+    a.rows_per_band = (ny - 1 + want - 1) / want;
+    if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
+    a.nbands = (ny - 1 + a.rows_per_band - 1) / a.rows_per_band;
+    a.msorit = par.msorit; a.sorrel = par.sorrel; a.sortol = par.sortol;
+    a.rau = c->met.rau; a.rgv = c->met.rgv; a.b = c->fld[W2_F_B];
+    a.pA = p; a.pB = scratch; a.ctl = ctl;
+    dim3 grid(a.nstrips, a.nbands);
+
+    // the ghost ring of p is frozen during the solve (:431-446 never touches it): give the second
+    // buffer the same ghosts
+    W2_CUDA(cudaMemcpyAsync(scratch, p, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    sorf_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
+    const int passes_total = (par.msorit + T - 1) / T + 1;
+    const double cells = (double)(nx - 1) * (double)(ny - 1);
+    int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + 4.0e-6));
+    if (chunk < 4) chunk = 4;
+    if (chunk > 128) chunk = 128;
+    SorFCtl h;
+    memset(&h, 0, sizeof(h));
+    int queued = 0;
+    // an upper bound on launches: every pass may need one redo at the very end only, but a redo can
+    // follow any pass, so keep launching until the control block says done
+    while (true) {
+        int n = chunk;
+        if (queued + n > 2 * passes_total) n = 2 * passes_total - queued;
+        if (n <= 0) break;
+        for (int q = 0; q < n; ++q) {
+            if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
+            else W2_TRY(launch_fused<2>(c, a, grid));
+            c->launches[2]++;
+        }
+        queued += n;
+        W2_CUDA(cudaGetLastError());
+        W2_CUDA(cudaMemcpyAsync(c->h_flags, ctl, sizeof(SorFCtl), cudaMemcpyDeviceToHost, c->stream));
+        W2_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(&h, c->h_flags, sizeof(SorFCtl));
+        if (h.done) break;
+    }
+    if (!h.done) { w2_set_error("fused SOR did not terminate"); return W2_ERR_CUDA; }
+    if (converged) *converged = h.nconv > 0;
+    if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : par.msorit;
+    if (iters_done) *iters_done = h.m;
+    *p_final = h.cur ? scratch : p;
+    return W2_OK;
+}
