@@ -1,0 +1,109 @@
+!-----------------------------------------------------------------------
+! wolfd2_gpu_iface.f90 -- ISO_C_BINDING interface block for the residency
+! API of libwolfd2_b200.so (include/wolfd2_b200.h, section (2)).
+!
+! UNTESTED HERE: neither the build container nor the GPU box has a Fortran
+! front-end (gfortran/flang/nvfortran are all absent), so this file has not
+! been compiled.  It is the binding a wolfd2 maintainer adds to the host
+! program; see INTEGRATION.md for the two edits to src/main.f.
+!
+! The literal shims (nauxmomentum_, ppe_, project_, velboundcond_, ...) need
+! NO interface block: they carry the gfortran F77 calling convention of the
+! subroutines they replace (momentum.f:33, pressure.f:30, utility.f:253,
+! bound_cond.f:511/853/1656), so main.f links against them unchanged once the
+! original objects' symbols are removed from the link line.
+!-----------------------------------------------------------------------
+module wolfd2_gpu
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  ! struct wolfd2_params  (include/wolfd2_b200.h)
+  type, bind(C) :: w2_params
+    integer(c_int32_t) :: nx, ny
+    integer(c_int32_t) :: mqiter, nmeiter, nPpeSolver, msorit
+    integer(c_int32_t) :: lCartesGrid, nfiltu, nfiltv, reserved
+    real(c_double)     :: dk, re, fr, qtol, sortol, sorrel, fpu, fpv
+  end type w2_params
+
+  ! struct wolfd2_regions: addresses of the tables SetUpBCs built
+  type, bind(C) :: w2_regions
+    type(c_ptr) :: nReg, nRegBrd, nRegType, nMomBdTp
+    type(c_ptr) :: dBCVal, dPRporos, dPRporc1, dPRporc2
+  end type w2_regions
+
+  ! struct wolfd2_metrics: addresses of the 30 metric arrays Grid built
+  type, bind(C) :: w2_metrics
+    type(c_ptr) :: rau, rbu, rbv, rgv, ran, rbn, rgn, rac, rbc, rgc
+    type(c_ptr) :: dju, djv, djc, djn
+    type(c_ptr) :: xen, yen, xzn, yzn, xec, yec, xzc, yzc
+    type(c_ptr) :: xeu, yeu, xzv, yzv, xzu, yzu, xev, yev
+  end type w2_metrics
+
+  ! struct wolfd2_step_log: the PrintDiff tuple (string.f:547-559)
+  type, bind(C) :: w2_step_log
+    integer(c_int32_t) :: nQLiter, nSorConv, sor_converged, diverged
+    real(c_double)     :: dif(4)
+  end type w2_step_log
+
+  integer(c_int32_t), parameter :: W2_F_U = 0, W2_F_V = 1, W2_F_P = 2
+
+  interface
+    ! replaces the compile-time include/config.f:19-26
+    integer(c_int) function wolfd2_b200_config(mnx, mny, mgri, mgrj) bind(C, name='wolfd2_b200_config')
+      import :: c_int, c_int32_t
+      integer(c_int32_t), value :: mnx, mny, mgri, mgrj
+    end function
+
+    ! after Grid / SetUpBCs (main.f:434-448): upload metrics and region tables
+    integer(c_int) function wolfd2_b200_create(ctx, par, reg, met) bind(C, name='wolfd2_b200_create')
+      import :: c_int, c_ptr, w2_params, w2_regions, w2_metrics
+      type(c_ptr), intent(out) :: ctx
+      type(w2_params),  intent(in) :: par
+      type(w2_regions), intent(in) :: reg
+      type(w2_metrics), intent(in) :: met
+    end function
+
+    subroutine wolfd2_b200_destroy(ctx) bind(C, name='wolfd2_b200_destroy')
+      import :: c_ptr
+      type(c_ptr), value :: ctx
+    end subroutine
+
+    ! host (0:mnx,0:mny) array -> device field, and back (dumps, restart, ATD, trajectories)
+    integer(c_int) function wolfd2_b200_upload_field(ctx, which, host) bind(C, name='wolfd2_b200_upload_field')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: which
+      real(c_double), intent(in) :: host(*)
+    end function
+    integer(c_int) function wolfd2_b200_download_field(ctx, which, host) bind(C, name='wolfd2_b200_download_field')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: which
+      real(c_double), intent(out) :: host(*)
+    end function
+
+    ! main.f:606-641
+    integer(c_int) function wolfd2_b200_coldstart(ctx, nSorConv) bind(C, name='wolfd2_b200_coldstart')
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), intent(out) :: nSorConv
+    end function
+
+    ! main.f:690-981, nsteps times, fields resident on the device
+    integer(c_int) function wolfd2_b200_step(ctx, nsteps, logs) bind(C, name='wolfd2_b200_step')
+      import :: c_int, c_int32_t, c_ptr, w2_step_log
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: nsteps
+      type(w2_step_log), intent(out) :: logs(*)
+    end function
+
+    ! same with u,v,p crossing the boundary in host arrays every call
+    integer(c_int) function wolfd2_b200_step_host(ctx, nsteps, u, v, p, logs) bind(C, name='wolfd2_b200_step_host')
+      import :: c_int, c_int32_t, c_ptr, c_double, w2_step_log
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: nsteps
+      real(c_double), intent(inout) :: u(*), v(*), p(*)
+      type(w2_step_log), intent(out) :: logs(*)
+    end function
+  end interface
+end module wolfd2_gpu

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) sor_rb_sweep(int nx, int ny, int pitch, i
             if (HAS_MASK && mask[c0]) { a1 = 0.0; a2 = 0.0; a3 = 1.0; a4 = 0.0; a5 = 0.0; }
             const double pc = p[c0];
             double sum = b[c0] - a1 * p[c0 - pitch] - a2 * p[c0 - 1] - a4 * p[c0 + 1] - a5 * p[c0 + pitch];
-            sum = sum / a3 - pc;
+            sum = w2_div_exact(sum, a3) - pc;
             p[c0] = pc + sorrel * sum;
             lmax = fmax(lmax, fabs(sum));
         }

@@ -78,29 +78,35 @@ __global__ void sorf_ctl_reset(SorFCtl *c) {
     c->last_dif = 0ull;
 }
 
+template <int T> struct SorFCfg {
+    static constexpr int R = (T == 1) ? 8 : 13;      // ring depth in rows (T=2: 108 KB -> two CTAs per SM)
+    static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
+};
+
 template <int T>
-__global__ void __launch_bounds__(T * 256, 1) sor_rb_fused_kernel(SorFArgs a) {
+__global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel(SorFArgs a) {
     constexpr int NS = 2 * T;                 // half-sweep stages
-    constexpr int R = (T == 1) ? 8 : 16;      // ring depth (rows), power of two
+    constexpr int R = SorFCfg<T>::R;
     constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
     constexpr int D = R - LIVE - 1;           // prefetch distance (rows)
     constexpr int H = 2 * T;                  // halo columns/rows on a non-physical side
+    constexpr int RS = R * SF_STRIDE;
     static_assert(D >= 2, "ring too shallow");
 
     SorFCtl *ctl = a.ctl;
     if (ctl->done) return;
     // iterations this pass: a redo pass repeats `redo` iterations, else up to T
-    int Tp = ctl->redo > 0 ? ctl->redo : min(T, a.msorit - ctl->m);
+    const int Tp = ctl->redo > 0 ? ctl->redo : min(T, a.msorit - ctl->m);
     const int cur = ctl->cur;
     const double *__restrict__ psrc = cur ? a.pB : a.pA;
     double *__restrict__ pdst = cur ? a.pA : a.pB;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sP = reinterpret_cast<double *>(smem_raw);
-    double *sB = sP + R * SF_STRIDE;
-    double *sU = sB + R * SF_STRIDE;   // rau
-    double *sV = sU + R * SF_STRIDE;   // rgv
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sV + R * SF_STRIDE);
+    double *sB = sP + RS;
+    double *sU = sB + RS;   // rau
+    double *sV = sU + RS;   // rgv
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sV + RS);
     __shared__ double red[32];
 
     const int tid = threadIdx.x;
@@ -111,11 +117,10 @@ __global__ void __launch_bounds__(T * 256, 1) sor_rb_fused_kernel(SorFArgs a) {
     const bool physL = (strip == 0), physR = (i0 + SF_W - 1 >= nx + 1);
     const int own_lo = physL ? 2 : i0 + H;                             // owned columns (global i)
     const int own_hi = physR ? nx : min(nx, i0 + H + a.own_w - 1);
-    // rows: band owns [jA, jB]; loads [jL0, jL1]
+    // rows: band owns [jA, jB]; loads [jL0, jL1]; ring slot of a row = (row - jL0) mod R
     const int jA = 2 + band * a.rows_per_band;
     const int jB = min(ny, jA + a.rows_per_band - 1);
     const int jL0 = max(1, jA - H), jL1 = min(ny + 1, jB + H);
-    const bool physS = (jL0 == 1), physN = (jL1 == ny + 1);
 
     if (tid == 0) {
         for (int k = 0; k < R; ++k) mbar_init(&bars[k], 1);
@@ -129,78 +134,82 @@ __global__ void __launch_bounds__(T * 256, 1) sor_rb_fused_kernel(SorFArgs a) {
     }
     __syncthreads();
 
-    auto issue_row = [&](int row) {   // one thread: 4 bulk copies of 2 KB into ring slot row%R
-        const int slot = row & (R - 1);
-        const size_t g = (size_t)pitch * row + i0;
-        mbar_expect_tx(&bars[slot], 4u * SF_W * 8u);
-        tma_load_1d(sP + slot * SF_STRIDE + SF_PADL, psrc + g, SF_W * 8, &bars[slot]);
-        tma_load_1d(sB + slot * SF_STRIDE + SF_PADL, a.b + g, SF_W * 8, &bars[slot]);
-        tma_load_1d(sU + slot * SF_STRIDE + SF_PADL, a.rau + g, SF_W * 8, &bars[slot]);
-        tma_load_1d(sV + slot * SF_STRIDE + SF_PADL, a.rgv + g, SF_W * 8, &bars[slot]);
+    // ---- producer state (thread 0): next row to request and its ring slot
+    int ld_row = jL0, ld_off = 0, ld_slot = 0;
+    size_t ld_g = (size_t)pitch * jL0 + i0;
+    auto issue_row = [&]() {   // 4 bulk copies of 2 KB into the next ring slot
+        mbar_expect_tx(&bars[ld_slot], 4u * SF_W * 8u);
+        tma_load_1d(sP + ld_off + SF_PADL, psrc + ld_g, SF_W * 8, &bars[ld_slot]);
+        tma_load_1d(sB + ld_off + SF_PADL, a.b + ld_g, SF_W * 8, &bars[ld_slot]);
+        tma_load_1d(sU + ld_off + SF_PADL, a.rau + ld_g, SF_W * 8, &bars[ld_slot]);
+        tma_load_1d(sV + ld_off + SF_PADL, a.rgv + ld_g, SF_W * 8, &bars[ld_slot]);
+        ++ld_row; ld_g += pitch;
+        ld_off += SF_STRIDE; ++ld_slot;
+        if (ld_slot == R) { ld_slot = 0; ld_off = 0; }
     };
     if (tid == 0)
-        for (int row = jL0; row <= min(jL1, jL0 + D); ++row) issue_row(row);
+        for (int n = 0; n <= D && ld_row <= jL1; ++n) issue_row();
 
+    // ---- consumer state
     const int stage = (tid >> 7) + 1;         // 1..NS, 128 threads (4 warps) per stage
-    const int k = tid & 127;                   // column pair handled by this thread
-    const int colour = (stage - 1) & 1;        // 0 = black (i+j even), 1 = red
+    const int k2 = 2 * (tid & 127);           // even column of this thread's pair (strip-local)
+    const int colour = (stage - 1) & 1;       // 0 = black (i+j even), 1 = red; i0 is even
     const bool stage_on = stage <= 2 * Tp;
-    double lmax = 0.0;
+    const int ig = i0 + k2;
+    const bool val0 = ig >= 2 && ig <= nx, val1 = ig + 1 >= 2 && ig + 1 <= nx;
+    const bool own0 = ig >= own_lo && ig <= own_hi, own1 = ig + 1 >= own_lo && ig + 1 <= own_hi;
+    const int qlo = max(2, jL0 + 1), qhi = min(ny, jL1 - 1);
+    const int base = SF_PADL + k2;
     const double sorrel = a.sorrel;
+    double lmax = 0.0;
 
+    int q = jL0 - 2 * stage + 1;              // row relaxed by this stage at time step r = jL0
+    auto ring_off = [&](int row) { int m = (row - jL0) % R; if (m < 0) m += R; return m * SF_STRIDE; };
+    int off_s = ring_off(q - 1), off_q = ring_off(q), off_n = ring_off(q + 1);
+    int par = (colour + q) & 1;               // column parity of the active cell in row q
+    int w_slot = 0;
+    unsigned w_par = 0;
+    double *gst = pdst + (size_t)pitch * q + ig;   // store address of (ig, q)
     const int r_end = jB + 4 * T - 1;
+#pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
-        if (r <= jL1) mbar_wait(&bars[r & (R - 1)], (unsigned)(((r - jL0) / R) & 1));
-        // ring slots are indexed by absolute row; parity counts how often the slot has been refilled
-        // ---- stage work: row q = r - 2*stage + 1
-        const int q = r - 2 * stage + 1;
-        if (stage_on && q >= 2 && q <= ny && q - 1 >= jL0 && q + 1 <= jL1) {
-            const int c = 2 * k + ((colour + q) & 1);     // strip-local column of the active cell (i0 even)
-            const int i = i0 + c;
-            if (i >= 2 && i <= nx) {
-                const int sq = (q & (R - 1)) * SF_STRIDE + SF_PADL + c;
-                const int ss = ((q - 1) & (R - 1)) * SF_STRIDE + SF_PADL + c;
-                const int sn = ((q + 1) & (R - 1)) * SF_STRIDE + SF_PADL + c;
-                const double bb = sB[sq];
-                const double pc = sP[sq];
-                double sum;
-                if (bb != bb) {           // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
-                    sum = 0.0 - pc;
-                } else {
-                    const double a1 = sV[ss], a2 = sU[sq - 1], a4 = sU[sq], a5 = sV[sq];
-                    const double a3 = -a4 - a2 - a5 - a1;
-                    sum = bb - a1 * sP[ss] - a2 * sP[sq - 1] - a4 * sP[sq + 1] - a5 * sP[sn];
-                    sum = sum / a3 - pc;
-                }
-                sP[sq] = pc + sorrel * sum;
-                if (i >= own_lo && i <= own_hi && q >= jA && q <= jB) lmax = fmax(lmax, fabs(sum));
-            }
+        if (r <= jL1) {
+            mbar_wait(&bars[w_slot], w_par);
+            if (++w_slot == R) { w_slot = 0; w_par ^= 1u; }
         }
-        // ---- store the row that has passed every stage: qs = r - 4T + 1 (by the last stage's threads,
-        // one time step later, i.e. after the barrier below made it final)
+        if (stage_on && q >= qlo && q <= qhi && (par ? val1 : val0)) {
+            const int iq = off_q + base + par, is = off_s + base + par, in = off_n + base + par;
+            const double bb = sB[iq];
+            const double pc = sP[iq];
+            double sum;
+            if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
+                sum = 0.0 - pc;
+            } else {
+                const double a1 = sV[is], a2 = sU[iq - 1], a4 = sU[iq], a5 = sV[iq];
+                const double a3 = -a4 - a2 - a5 - a1;
+                sum = bb - a1 * sP[is] - a2 * sP[iq - 1] - a4 * sP[iq + 1] - a5 * sP[in];
+                sum = w2_div_exact(sum, a3) - pc;
+            }
+            sP[iq] = pc + sorrel * sum;
+            if ((par ? own1 : own0) && q >= jA && q <= jB) lmax = fmax(lmax, fabs(sum));
+        }
         __syncthreads();
-        {
-            const int qs = r - 4 * T + 1;
-            if (stage == NS && qs >= jA && qs <= jB) {
-                const int c = 2 * k;
-                const int i = i0 + c;
-                const int sq = (qs & (R - 1)) * SF_STRIDE + SF_PADL + c;
-                const double2 v = *reinterpret_cast<const double2 *>(&sP[sq]);
-                double *g = pdst + (size_t)pitch * qs + i;
-                const bool in0 = i >= own_lo && i <= own_hi, in1 = i + 1 >= own_lo && i + 1 <= own_hi;
-                if (in0 && in1) *reinterpret_cast<double2 *>(g) = v;
-                else if (in0) g[0] = v.x;
-                else if (in1) g[1] = v.y;
-            }
+        // the row that has just passed the last stage is final: back to HBM
+        if (stage == NS && q >= jA && q <= jB) {
+            const double2 v = *reinterpret_cast<const double2 *>(&sP[off_q + base]);
+            if (own0 && own1) *reinterpret_cast<double2 *>(gst) = v;
+            else if (own0) gst[0] = v.x;
+            else if (own1) gst[1] = v.y;
         }
-        // ---- prefetch: the slot of row r+D+1 held row r+D+1-R, whose last use (the store above at time
-        // r' = row+4T-1 <= r) is behind the barrier
-        if (tid == 0) {
-            const int row = r + D + 1;
-            if (row <= jL1) issue_row(row);
-        }
+        // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
+        if (tid == 0 && ld_row <= jL1) issue_row();
+        off_s = off_q; off_q = off_n;
+        off_n += SF_STRIDE;
+        if (off_n == RS) off_n = 0;
+        par ^= 1;
+        ++q;
+        gst += pitch;
     }
-    (void)physS; (void)physN;
 
     // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
 #pragma unroll
@@ -246,8 +255,7 @@ static bool g_attr_set[3] = {false, false, false};
 
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
-    constexpr int R = (T == 1) ? 8 : 16;
-    const size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
+    const size_t smem = SorFCfg<T>::smem;
     if (!g_attr_set[T]) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_attr_set[T] = true;
@@ -270,8 +278,20 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     a.own_w = SF_W - 4 * T;
     a.nstrips = 1;
     while ((a.nstrips - 1) * a.own_w + SF_W < nx + 2) a.nstrips++;
-    // bands: about three waves of CTAs over the machine
-    int want = (3 * c->num_sms + a.nstrips - 1) / a.nstrips;
+    // bands: exactly one resident wave of CTAs (a partial second wave would double the pass time)
+    int per_sm = 1;
+    {
+        const size_t smem1 = SorFCfg<1>::smem, smem2 = SorFCfg<2>::smem;
+        if (T == 1) {
+            cudaFuncSetAttribute(sor_rb_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<1>, 256, smem1);
+        } else {
+            cudaFuncSetAttribute(sor_rb_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<2>, 512, smem2);
+        }
+        if (per_sm < 1) per_sm = 1;
+    }
+    int want = (per_sm * c->num_sms) / a.nstrips;
     if (want < 1) want = 1;
     a.rows_per_band = (ny - 1 + want - 1) / want;
     if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
