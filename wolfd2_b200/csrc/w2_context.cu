@@ -166,7 +166,7 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
     W2_TRY(dalloc(&c->td, (size_t)nmax));
     W2_TRY(dalloc(&c->tc, (size_t)nmax));
     W2_TRY(dalloc(&c->tb, (size_t)nmax));
-    W2_TRY(dalloc(&c->tx, (size_t)nmax));
+    W2_TRY(dalloc(&c->tx, (size_t)nmax > c->nelem ? (size_t)nmax : c->nelem));  // also used in field layout
     W2_TRY(w2_tri_prepare(c, nmax));
     W2_CUDA(cudaMalloc((void **)&c->d_norm, 64 * sizeof(unsigned long long)));
     W2_CUDA(cudaMemset(c->d_norm, 0, 64 * sizeof(unsigned long long)));

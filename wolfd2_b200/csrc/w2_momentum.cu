@@ -10,7 +10,7 @@
 //
 // Cells the reference never writes are zeros there (static storage): cj1(nx+1,j),
 // cj2(i,ny+1) below are the load-bearing cases and are written out as literal 0.0.
-#include "w2.cuh"
+#include "w2_tri.cuh"
 
 #define F(a, i, j) a[IDX(i, j)]
 
@@ -23,8 +23,7 @@ struct MomArgs {
     // y-momentum metrics
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
     const unsigned char *xmask, *ymask;
-    double *ta, *td, *tc, *tb;
-    const double *x1;  // step-1 solution (chain order)
+    const double *x1;  // first-step solution, field layout
 };
 
 // ---- ConvCoef pieces ------------------------------------------------------------------------
@@ -116,19 +115,18 @@ __device__ __forceinline__ double y_diff(const MomArgs &m, const double *v, int 
     return s1 + s2;
 }
 
-// ---- assembly kernels -------------------------------------------------------------------------
-// X, first split step (:350-384): unknown ind = (j-2)*nx + i, i=1..nx, j=2..ny
-__global__ void __launch_bounds__(256) xmom_step1_kernel(MomArgs m) {
-    const int pitch = m.pitch, nx = m.nx;
-    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
+// ---- one row of each split-step system ---------------------------------------------------------------
+// COMP 0 = x-momentum (unknown (i,j), i=1..nx, j=2..ny), COMP 1 = y-momentum (i=2..nx, j=1..ny);
+// STEP 1: LHS + rhs of the first split step (:350-384 / :675-711);
+// STEP 2: LHS of the second step, identity rows, rhs = first-step solution (:396-496 / :723-821).
+template <int COMP, int STEP>
+__device__ __forceinline__ void mom_row(const MomArgs &m, int i, int j, double &a1, double &a2, double &a3, double &b) {
+    const int pitch = m.pitch;
     const double re1 = 1.0 / m.re, dk2 = m.dk * 0.5;
-    for (int j = 2 + blockIdx.y; j <= m.ny; j += gridDim.y) {
-        const size_t ind = (size_t)(j - 2) * nx + (i - 1);
+    if (COMP == 0 && STEP == 1) {
         const double rkj = dk2 * F(m.dju, i, j);
         const double cj = x_cj1(m, i, j);
         const double rac0 = F(m.rac, i, j), rac1 = F(m.rac, i + 1, j);
-        double a1, a2, a3;
         if (cj >= 0.0) {
             a1 = rkj * (-x_cj1(m, i - 1, j) - re1 * rac0);
             a2 = 1.0 + rkj * (cj + re1 * (rac1 + rac0));
@@ -140,50 +138,26 @@ __global__ void __launch_bounds__(256) xmom_step1_kernel(MomArgs m) {
         }
         const double cnvs = x_conv(m, m.us, m.vs, i, j), cnvn = x_conv(m, m.un, m.vn, i, j);
         const double difs = x_diff(m, m.us, i, j), difn = x_diff(m, m.un, i, j);
-        const double b = F(m.un, i, j) - F(m.us, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
-        m.ta[ind] = a1; m.td[ind] = a2; m.tc[ind] = a3; m.tb[ind] = b;
-    }
-}
-// X, second split step LHS (:396-428) + identity rows (:434-496); rhs = first-step solution
-__global__ void __launch_bounds__(256) xmom_step2_kernel(MomArgs m) {
-    const int pitch = m.pitch, nx = m.nx;
-    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
-    const double re1 = 1.0 / m.re, dk2 = m.dk * 0.5;
-    for (int j = 2 + blockIdx.y; j <= m.ny; j += gridDim.y) {
-        const size_t ind = (size_t)(j - 2) * nx + (i - 1);
-        double a1, a2, a3, b;
-        if (m.xmask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; }
-        else {
-            const double rkj = dk2 * F(m.dju, i, j);
-            const double cj = x_cj2(m, i, j);
-            const double g0 = F(m.rgn, i, j), gm = F(m.rgn, i, j - 1);
-            if (cj >= 0.0) {
-                a1 = rkj * (-x_cj2(m, i, j - 1) - re1 * gm);
-                a2 = 1.0 + rkj * (cj + re1 * (g0 + gm));
-                a3 = rkj * (-re1 * g0);
-            } else {
-                a1 = rkj * (-re1 * gm);
-                a2 = 1.0 + rkj * (-cj + re1 * (g0 + gm));
-                a3 = rkj * (x_cj2(m, i, j + 1) - re1 * g0);
-            }
-            b = m.x1[ind];
+        b = F(m.un, i, j) - F(m.us, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
+    } else if (COMP == 0 && STEP == 2) {
+        if (m.xmask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
+        const double rkj = dk2 * F(m.dju, i, j);
+        const double cj = x_cj2(m, i, j);
+        const double g0 = F(m.rgn, i, j), gm = F(m.rgn, i, j - 1);
+        if (cj >= 0.0) {
+            a1 = rkj * (-x_cj2(m, i, j - 1) - re1 * gm);
+            a2 = 1.0 + rkj * (cj + re1 * (g0 + gm));
+            a3 = rkj * (-re1 * g0);
+        } else {
+            a1 = rkj * (-re1 * gm);
+            a2 = 1.0 + rkj * (-cj + re1 * (g0 + gm));
+            a3 = rkj * (x_cj2(m, i, j + 1) - re1 * g0);
         }
-        m.ta[ind] = a1; m.td[ind] = a2; m.tc[ind] = a3; m.tb[ind] = b;
-    }
-}
-// Y, first split step (:675-711): unknown ind = (j-1)*(nx-1) + i-1, i=2..nx, j=1..ny
-__global__ void __launch_bounds__(256) ymom_step1_kernel(MomArgs m) {
-    const int pitch = m.pitch, nx = m.nx;
-    const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
-    const double re1 = 1.0 / m.re, dk2 = m.dk * 0.5;
-    for (int j = 1 + blockIdx.y; j <= m.ny; j += gridDim.y) {
-        const size_t ind = (size_t)(j - 1) * (nx - 1) + (i - 2);
+        b = m.x1[IDX(i, j)];
+    } else if (COMP == 1 && STEP == 1) {
         const double rkj = dk2 * F(m.djv, i, j);
         const double cj = y_cj1(m, i, j);
         const double an0 = F(m.ran, i, j), anm = F(m.ran, i - 1, j);
-        double a1, a2, a3;
         if (cj >= 0.0) {
             a1 = rkj * (-y_cj1(m, i - 1, j) - re1 * anm);
             a2 = rkj * (cj + re1 * (an0 + anm)) + 1.0;
@@ -196,36 +170,162 @@ __global__ void __launch_bounds__(256) ymom_step1_kernel(MomArgs m) {
         const double buoy = m.dk * (F(m.d, i, j + 1) + F(m.d, i, j) + F(m.dn, i, j + 1) + F(m.dn, i, j)) / (4.0 * m.fr);
         const double cnvs = y_conv(m, m.us, m.vs, i, j), cnvn = y_conv(m, m.un, m.vn, i, j);
         const double difs = y_diff(m, m.vs, i, j), difn = y_diff(m, m.vn, i, j);
-        const double b = F(m.vn, i, j) - F(m.vs, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn) - buoy;
-        m.ta[ind] = a1; m.td[ind] = a2; m.tc[ind] = a3; m.tb[ind] = b;
+        b = F(m.vn, i, j) - F(m.vs, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn) - buoy;
+    } else {
+        if (m.ymask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
+        const double rkj = dk2 * F(m.djv, i, j);
+        const double cj = y_cj2(m, i, j);
+        const double g0 = F(m.rgc, i, j), gp = F(m.rgc, i, j + 1);
+        if (cj >= 0.0) {
+            a1 = rkj * (-y_cj2(m, i, j - 1) - re1 * g0);
+            a2 = rkj * (cj + re1 * (gp + g0)) + 1.0;
+            a3 = rkj * (-re1 * gp);
+        } else {
+            a1 = rkj * (-re1 * g0);
+            a2 = rkj * (-cj + re1 * (gp + g0)) + 1.0;
+            a3 = rkj * (y_cj2(m, i, j + 1) - re1 * gp);
+        }
+        b = m.x1[IDX(i, j)];
     }
 }
-// Y, second split step LHS (:723-754) + identity rows (:760-821)
-__global__ void __launch_bounds__(256) ymom_step2_kernel(MomArgs m) {
-    const int pitch = m.pitch, nx = m.nx;
-    const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
-    const double re1 = 1.0 / m.re, dk2 = m.dk * 0.5;
-    for (int j = 1 + blockIdx.y; j <= m.ny; j += gridDim.y) {
-        const size_t ind = (size_t)(j - 1) * (nx - 1) + (i - 2);
-        double a1, a2, a3, b;
-        if (m.ymask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; }
-        else {
-            const double rkj = dk2 * F(m.djv, i, j);
-            const double cj = y_cj2(m, i, j);
-            const double g0 = F(m.rgc, i, j), gp = F(m.rgc, i, j + 1);
-            if (cj >= 0.0) {
-                a1 = rkj * (-y_cj2(m, i, j - 1) - re1 * g0);
-                a2 = rkj * (cj + re1 * (gp + g0)) + 1.0;
-                a3 = rkj * (-re1 * gp);
-            } else {
-                a1 = rkj * (-re1 * g0);
-                a2 = rkj * (-cj + re1 * (gp + g0)) + 1.0;
-                a3 = rkj * (y_cj2(m, i, j + 1) - re1 * gp);
+
+// chain index e (0-based, reference ordering momentum.f:353 / :677) -> grid point
+template <int COMP>
+__device__ __forceinline__ void chain_ij(const MomArgs &m, long long e, int &i, int &j) {
+    if (COMP == 0) { const int jj = (int)(e / m.nx); j = 2 + jj; i = 1 + (int)(e - (long long)jj * m.nx); }
+    else { const int w = m.nx - 1; const int jj = (int)(e / w); j = 1 + jj; i = 2 + (int)(e - (long long)jj * w); }
+}
+
+// ---- fused assembly + level-0 reduce --------------------------------------------------------------------
+// One CTA per segment of TRI_S chain unknowns.  Rows are assembled in a coalesced mapping (thread <->
+// consecutive i), transposed through shared memory to the solver's chunk mapping (thread <-> 8
+// consecutive unknowns; padded stride 9 is conflict-free), reduced by tri_cta_core, and the result is
+// transposed back: Y goes straight into the FIELD layout of `out` (no chain->field scatter pass), the
+// spikes V/W go to chain-layout arrays only over the prefix/suffix where they are not exactly zero.
+#define MR_PAD(x) ((x) + ((x) >> 3))
+#define MR_LEN (TRI_S + TRI_S / 8)
+
+template <int COMP, int STEP>
+__global__ void __launch_bounds__(TRI_T, 1) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
+                                                              double *__restrict__ Vg, double *__restrict__ Wg,
+                                                              double *__restrict__ seg, int *__restrict__ ext,
+                                                              long long nseg, int direct) {
+    extern __shared__ __align__(16) double sm[];
+    double *s0 = sm, *s1 = sm + MR_LEN, *s2 = sm + 2 * MR_LEN, *s3 = sm + 3 * MR_LEN;
+    __shared__ int s_ext[2];
+    __shared__ double sSig;
+    const int t = threadIdx.x;
+    const long long g = blockIdx.x;
+    const long long ebase = g * (long long)TRI_S;
+    const int pitch = m.pitch;
+    constexpr int L = TRI_M - 2;
+    if (t == 0) { s_ext[0] = 0; s_ext[1] = 0; }
+
+    // ---- phase A: assemble rows, coalesced
+#pragma unroll 1
+    for (int q = 0; q < TRI_M; ++q) {
+        const int el = t + TRI_T * q;
+        const long long e = ebase + el;
+        double a1 = 0.0, a2 = 1.0, a3 = 0.0, b = 0.0;
+        if (e < n) {
+            int i, j;
+            chain_ij<COMP>(m, e, i, j);
+            mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
+            if (e == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
+                a1 = 0.0;
+                int i2, j2; double b1, b2, b3, bb;
+                chain_ij<COMP>(m, 1, i2, j2);
+                mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+                a3 = a3 * a2 / b2;
             }
-            b = m.x1[ind];
+            if (e == n - 1) a3 = 0.0;
         }
-        m.ta[ind] = a1; m.td[ind] = a2; m.tc[ind] = a3; m.tb[ind] = b;
+        const int p = MR_PAD(el);
+        s0[p] = a1; s1[p] = a2; s2[p] = a3; s3[p] = b;
+    }
+    __syncthreads();
+    // ---- phase B: chunk mapping
+    double A[TRI_M], D[TRI_M], C[TRI_M], B[TRI_M];
+#pragma unroll
+    for (int k = 0; k < TRI_M; ++k) {
+        const int p = 9 * t + k;
+        A[k] = s0[p]; D[k] = s1[p]; C[k] = s2[p]; B[k] = s3[p];
+    }
+    __syncthreads();
+    double Ye[TRI_M], Ve[TRI_M], We[TRI_M];
+    double ar, dr, cr, br;
+    // the six TRI_T-long work arrays of the core alias the (now free) staging area
+    tri_cta_core(A, D, C, B, Ye, Ve, We, sm, sm + TRI_T, sm + 2 * TRI_T, sm + 3 * TRI_T, sm + 4 * TRI_T, sm + 5 * TRI_T,
+                 ar, dr, cr, br);
+    if (direct) {
+        if (t == TRI_T - 1) sSig = (br - ar * Ye[L]) / (dr - ar * We[L]);
+        __syncthreads();
+        const double sig = sSig;
+#pragma unroll
+        for (int k = 0; k < TRI_M; ++k) Ye[k] = Ye[k] - sig * We[k];
+    } else {
+        // extent of the exactly-non-zero part of the spikes (prefix for V, suffix for W)
+        bool nzv = false, nzw = false;
+#pragma unroll
+        for (int k = 0; k < TRI_M; ++k) { nzv |= (Ve[k] != 0.0); nzw |= (We[k] != 0.0); }
+        if (nzv) atomicMax(&s_ext[0], TRI_M * (t + 1));
+        if (nzw) atomicMax(&s_ext[1], TRI_S - TRI_M * t);
+    }
+    __syncthreads();   // core's shared arrays are dead; s_ext final
+    // ---- phase C: transpose back and write coalesced
+#pragma unroll
+    for (int k = 0; k < TRI_M; ++k) {
+        const int p = 9 * t + k;
+        s0[p] = Ye[k];
+        if (!direct) { s1[p] = Ve[k]; s2[p] = We[k]; }
+    }
+    __syncthreads();
+    const int extV = s_ext[0], extW = s_ext[1];
+#pragma unroll 1
+    for (int q = 0; q < TRI_M; ++q) {
+        const int el = t + TRI_T * q;
+        const long long e = ebase + el;
+        if (e >= n) break;
+        int i, j;
+        chain_ij<COMP>(m, e, i, j);
+        const int p = MR_PAD(el);
+        out[IDX(i, j)] = s0[p];
+        if (!direct) {
+            if (el < extV) Vg[e] = s1[p];
+            if (el >= TRI_S - extW) Wg[e] = s2[p];
+        }
+    }
+    if (direct) return;
+    if (t == 0) {
+        seg[g] = Ye[0]; seg[nseg + g] = Ve[0]; seg[2 * nseg + g] = We[0];
+        ext[2 * g] = extV; ext[2 * g + 1] = extW;
+    }
+    if (t == TRI_T - 1) {
+        seg[3 * nseg + g] = Ye[L]; seg[4 * nseg + g] = Ve[L]; seg[5 * nseg + g] = We[L];
+        seg[6 * nseg + g] = ar; seg[7 * nseg + g] = dr; seg[8 * nseg + g] = cr; seg[9 * nseg + g] = br;
+    }
+}
+
+// x = Y - Sg[g-1]*V - Sg[g]*W in field layout, touching only the unknowns whose spike entries are non-zero
+template <int COMP>
+__global__ void __launch_bounds__(256) mom_finalize_kernel(MomArgs m, long long n, double *__restrict__ out,
+                                                           const double *__restrict__ Vg, const double *__restrict__ Wg,
+                                                           const double *__restrict__ sig, const int *__restrict__ ext) {
+    const long long g = blockIdx.x;
+    const int pitch = m.pitch;
+    const int extV = ext[2 * g], extW = ext[2 * g + 1];
+    const double sl = g > 0 ? sig[g - 1] : 0.0, sr = sig[g];
+    const int lo2 = max(extV, TRI_S - extW);   // start of the W-only part
+    const int cnt = extV + (TRI_S - lo2);
+    for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+        const int el = q < extV ? q : lo2 + (q - extV);
+        const long long e = g * (long long)TRI_S + el;
+        if (e >= n) continue;
+        int i, j;
+        chain_ij<COMP>(m, e, i, j);
+        const double v = el < extV ? Vg[e] : 0.0;
+        const double w = el >= TRI_S - extW ? Wg[e] : 0.0;
+        out[IDX(i, j)] = out[IDX(i, j)] - sl * v - sr * w;
     }
 }
 
@@ -257,20 +357,6 @@ __global__ void mom_mask_kernel(const W2Regions *__restrict__ R, int nx, int ny,
     }
     xmask[IDX(i, j)] = mx;
     ymask[IDX(i, j)] = my;
-}
-
-// chain -> field scatter (:505-510, :829-834)
-__global__ void __launch_bounds__(256) scatter_x_kernel(int nx, int ny, int pitch, const double *__restrict__ x,
-                                                        double *__restrict__ dus) {
-    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
-    for (int j = 2 + blockIdx.y; j <= ny; j += gridDim.y) dus[IDX(i, j)] = x[(size_t)(j - 2) * nx + (i - 1)];
-}
-__global__ void __launch_bounds__(256) scatter_y_kernel(int nx, int ny, int pitch, const double *__restrict__ x,
-                                                        double *__restrict__ dvs) {
-    const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nx) return;
-    for (int j = 1 + blockIdx.y; j <= ny; j += gridDim.y) dvs[IDX(i, j)] = x[(size_t)(j - 1) * (nx - 1) + (i - 2)];
 }
 
 // us,vs <- un,vn on 1..nx+1, 1..ny+1 (:114-119)
@@ -329,7 +415,7 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xen = t.xen; m.yen = t.yen; m.xzc = t.xzc; m.yzc = t.yzc;
     m.xev = t.xev; m.yev = t.yev; m.xzv = t.xzv; m.yzv = t.yzv;
     m.xmask = c->xmask; m.ymask = c->ymask;
-    m.ta = c->ta; m.td = c->td; m.tc = c->tc; m.tb = c->tb; m.x1 = c->tx;
+    m.x1 = c->tx;
 }
 
 static int check_porous(wolfd2_ctx *c) {
@@ -340,22 +426,36 @@ static int check_porous(wolfd2_ctx *c) {
     return W2_OK;
 }
 
+template <int COMP, int STEP>
+static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
+    static bool attr = false;
+    const size_t smem = (size_t)4 * MR_LEN * sizeof(double);
+    if (!attr) {
+        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    W2TriWork &w = c->tri;
+    const long long nseg = (n + TRI_S - 1) / TRI_S;
+    const int direct = nseg == 1;
+    mom_reduce_kernel<COMP, STEP><<<(unsigned)nseg, TRI_T, smem, c->stream>>>(m, n, out, w.V0, w.W0, w.lv[0].seg, w.ext, nseg, direct);
+    c->launches[1]++;
+    if (!direct) {
+        const double *sigma = nullptr;
+        W2_TRY(w2_tri_upper(c, nseg, &sigma));
+        mom_finalize_kernel<COMP><<<(unsigned)nseg, 256, 0, c->stream>>>(m, n, out, w.V0, w.W0, sigma, w.ext);
+        c->launches[1]++;
+    }
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+
 int w2_xmomentum(wolfd2_ctx *c, double *dus) {
     W2_TRY(check_porous(c));
     MomArgs m;
     fill_args(c, m);
-    const int nx = c->nx, ny = c->ny;
-    const long long n = (long long)nx * (ny - 1);
-    dim3 grid((nx + 255) / 256, (ny - 1) < 2048 ? (ny - 1) : 2048);
-    xmom_step1_kernel<<<grid, 256, 0, c->stream>>>(m);
-    c->launches[1]++;
-    W2_TRY(w2_tri_solve(c, n, c->ta, c->td, c->tc, c->tb, c->tx, 1));  // :389
-    xmom_step2_kernel<<<grid, 256, 0, c->stream>>>(m);
-    c->launches[1]++;
-    W2_TRY(w2_tri_solve(c, n, c->ta, c->td, c->tc, c->tb, c->tx, 1));  // :501
-    scatter_x_kernel<<<grid, 256, 0, c->stream>>>(nx, ny, c->pitch, c->tx, dus);
-    c->launches[1]++;
-    W2_CUDA(cudaGetLastError());
+    const long long n = (long long)c->nx * (c->ny - 1);
+    W2_TRY((mom_solve<0, 1>(c, m, n, c->tx)));   // :350-389, result in field layout
+    W2_TRY((mom_solve<0, 2>(c, m, n, dus)));     // :396-510
     return W2_OK;
 }
 
@@ -363,18 +463,9 @@ int w2_ymomentum(wolfd2_ctx *c, double *dvs) {
     W2_TRY(check_porous(c));
     MomArgs m;
     fill_args(c, m);
-    const int nx = c->nx, ny = c->ny;
-    const long long n = (long long)(nx - 1) * ny;
-    dim3 grid((nx - 1 + 255) / 256, ny < 2048 ? ny : 2048);
-    ymom_step1_kernel<<<grid, 256, 0, c->stream>>>(m);
-    c->launches[1]++;
-    W2_TRY(w2_tri_solve(c, n, c->ta, c->td, c->tc, c->tb, c->tx, 1));  // :716
-    ymom_step2_kernel<<<grid, 256, 0, c->stream>>>(m);
-    c->launches[1]++;
-    W2_TRY(w2_tri_solve(c, n, c->ta, c->td, c->tc, c->tb, c->tx, 1));  // :826
-    scatter_y_kernel<<<grid, 256, 0, c->stream>>>(nx, ny, c->pitch, c->tx, dvs);
-    c->launches[1]++;
-    W2_CUDA(cudaGetLastError());
+    const long long n = (long long)(c->nx - 1) * c->ny;
+    W2_TRY((mom_solve<1, 1>(c, m, n, c->tx)));   // :675-716
+    W2_TRY((mom_solve<1, 2>(c, m, n, dvs)));     // :723-834
     return W2_OK;
 }
 

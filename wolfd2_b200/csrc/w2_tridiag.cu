@@ -24,11 +24,7 @@
 // AltTridLU's first-row quirk (momentum.f:1319: a(3,1) = a(3,1)/a(2,2)) is algebraically the
 // plain Thomas algorithm applied to a system whose first super-diagonal is c1*d1/d2; the row
 // provider applies exactly that substitution.
-#include "w2.cuh"
-
-#define TRI_T 512
-#define TRI_M 8
-#define TRI_S (TRI_T * TRI_M)
+#include "w2_tri.cuh"
 
 // ---------------------------------------------------------------------- row providers
 struct ProvSoA {  // rows stored as four arrays in HBM
@@ -103,83 +99,9 @@ __global__ void __launch_bounds__(TRI_T, 1) tri_reduce_kernel(Prov prov, long lo
 
     double A[TRI_M], D[TRI_M], C[TRI_M], B[TRI_M];
     prov.load(e0, A, D, C, B);
-
-    // --- thread-level elimination of the M-1 interior unknowns, 3 right-hand sides
-    double y[TRI_M - 1], v[TRI_M - 1], w[TRI_M - 1], cp[TRI_M - 1];
-    {
-        double inv = 1.0 / D[0];
-        cp[0] = C[0] * inv; y[0] = B[0] * inv; v[0] = A[0] * inv;
-#pragma unroll
-        for (int k = 1; k <= L; ++k) {
-            inv = 1.0 / (D[k] - A[k] * cp[k - 1]);
-            cp[k] = C[k] * inv;
-            y[k] = (B[k] - A[k] * y[k - 1]) * inv;
-            v[k] = (-A[k] * v[k - 1]) * inv;
-        }
-        w[L] = cp[L];
-#pragma unroll
-        for (int k = L - 1; k >= 0; --k) {
-            y[k] = y[k] - cp[k] * y[k + 1];
-            v[k] = v[k] - cp[k] * v[k + 1];
-            w[k] = -cp[k] * w[k + 1];
-        }
-    }
-    // --- exchange first-interior values with the left neighbour thread
-    sY[t] = y[0]; sV[t] = v[0]; sW[t] = w[0];
-    __syncthreads();
-    const double ar = A[TRI_M - 1], dr = D[TRI_M - 1], cr = C[TRI_M - 1], br = B[TRI_M - 1];
-    double rA, rD, rC, rY, rV, rW;  // this thread's separator row, 3 rhs
-    if (t < TRI_T - 1) {
-        const double yF = sY[t + 1], vF = sV[t + 1], wF = sW[t + 1];
-        rA = -ar * v[L];
-        rD = dr - ar * w[L] - cr * vF;
-        rC = -cr * wF;
-        rY = br - ar * y[L];
-        rY = rY - cr * yF;
-        rV = 0.0; rW = 0.0;
-        if (t == 0) { rV = rA; rA = 0.0; }
-        if (t == TRI_T - 2) { rW = rC; rC = 0.0; }
-    } else {  // the CTA's own separator is not part of the in-CTA system
-        rA = 0.0; rD = 1.0; rC = 0.0; rY = 0.0; rV = 0.0; rW = 0.0;
-    }
-    __syncthreads();
-    // --- parallel cyclic reduction over the T thread separators
-#pragma unroll 1
-    for (int s = 1; s < TRI_T; s <<= 1) {
-        sA[t] = rA; sD[t] = rD; sC[t] = rC; sY[t] = rY; sV[t] = rV; sW[t] = rW;
-        __syncthreads();
-        const int lo = t - s, hi = t + s;
-        double aL = 0.0, dL = 1.0, cL = 0.0, yL = 0.0, vL = 0.0, wL = 0.0;
-        double aH = 0.0, dH = 1.0, cH = 0.0, yH = 0.0, vH = 0.0, wH = 0.0;
-        if (lo >= 0) { aL = sA[lo]; dL = sD[lo]; cL = sC[lo]; yL = sY[lo]; vL = sV[lo]; wL = sW[lo]; }
-        if (hi < TRI_T) { aH = sA[hi]; dH = sD[hi]; cH = sC[hi]; yH = sY[hi]; vH = sV[hi]; wH = sW[hi]; }
-        const double al = -rA / dL, ga = -rC / dH;
-        rD = rD + al * cL + ga * aH;
-        rY = rY + al * yL + ga * yH;
-        rV = rV + al * vL + ga * vH;
-        rW = rW + al * wL + ga * wH;
-        rA = al * aL;
-        rC = ga * cH;
-        __syncthreads();
-    }
-    // separator solution, as coefficients of (1, Sg[g-1], Sg[g])
-    double sy, sv, sw;
-    if (t < TRI_T - 1) { const double inv = 1.0 / rD; sy = rY * inv; sv = rV * inv; sw = rW * inv; }
-    else { sy = 0.0; sv = 0.0; sw = -1.0; }
-    sY[t] = sy; sV[t] = sv; sW[t] = sw;
-    __syncthreads();
-    double py = 0.0, pv = -1.0, pw = 0.0;  // the separator to the left of this chunk
-    if (t > 0) { py = sY[t - 1]; pv = sV[t - 1]; pw = sW[t - 1]; }
-
-    // --- per-element coefficients of the segment-level representation
     double Ye[TRI_M], Ve[TRI_M], We[TRI_M];
-#pragma unroll
-    for (int k = 0; k <= L; ++k) {
-        Ye[k] = y[k] - py * v[k] - sy * w[k];
-        Ve[k] = -(pv * v[k] + sv * w[k]);
-        We[k] = -(pw * v[k] + sw * w[k]);
-    }
-    Ye[TRI_M - 1] = sy; Ve[TRI_M - 1] = sv; We[TRI_M - 1] = sw;
+    double ar, dr, cr, br;
+    tri_cta_core(A, D, C, B, Ye, Ve, We, sA, sD, sC, sY, sV, sW, ar, dr, cr, br);
 
     if (direct) {
         // single segment: Sg[-1] = 0 and the separator row has no right neighbour
@@ -247,6 +169,7 @@ int w2_tri_prepare(wolfd2_ctx *c, long long nmax) {
             W2_CUDA(cudaMalloc((void **)&lv.x, pad * sizeof(double)));
         }
         W2_CUDA(cudaMalloc((void **)&lv.seg, 10 * (lv.nseg + 1) * sizeof(double)));
+        if (l == 0) W2_CUDA(cudaMalloc((void **)&w.ext, 2 * (lv.nseg + 1) * sizeof(int)));
         ++l;
         if (lv.nseg == 1) break;
         n = lv.nseg;
@@ -258,7 +181,7 @@ int w2_tri_prepare(wolfd2_ctx *c, long long nmax) {
 
 void w2_tri_release(wolfd2_ctx *c) {
     W2TriWork &w = c->tri;
-    cudaFree(w.Y0); cudaFree(w.V0); cudaFree(w.W0);
+    cudaFree(w.Y0); cudaFree(w.V0); cudaFree(w.W0); cudaFree(w.ext);
     for (int l = 0; l < w.nlevels; ++l) {
         if (l > 0) { cudaFree(w.lv[l].Y); cudaFree(w.lv[l].V); cudaFree(w.lv[l].W); cudaFree(w.lv[l].x); }
         cudaFree(w.lv[l].seg);
@@ -266,38 +189,53 @@ void w2_tri_release(wolfd2_ctx *c) {
     memset(&w, 0, sizeof(w));
 }
 
+// Levels >= 1: solve the separator system whose rows are formed from the level-0 segment records in
+// tri.lv[0].seg (nseg0 of them).  On return *sigma points at the nseg0 separator values.
+int w2_tri_upper(wolfd2_ctx *c, long long nseg0, const double **sigma) {
+    W2TriWork &w = c->tri;
+    long long ns[6], segs[6];
+    int nl = 1;
+    ns[0] = 0; segs[0] = nseg0;
+    for (long long n = nseg0;;) {
+        ns[nl] = n; segs[nl] = (n + TRI_S - 1) / TRI_S; ++nl;
+        if (segs[nl - 1] == 1) break;
+        n = segs[nl - 1];
+        if (nl >= 6) { w2_set_error("tridiagonal hierarchy too deep"); return W2_ERR_BAD_ARG; }
+    }
+    for (int l = 1; l < nl; ++l) {
+        W2TriLevel &lv = w.lv[l];
+        const int direct = (l == nl - 1);
+        ProvSeg ps{w.lv[l - 1].seg, ns[l]};
+        tri_reduce_kernel<ProvSeg><<<(unsigned)segs[l], TRI_T, 0, c->stream>>>(ps, ns[l], lv.Y, lv.V, lv.W, lv.seg, segs[l], direct,
+                                                                               direct ? lv.x : nullptr);
+        c->launches[1]++;
+    }
+    for (int l = nl - 2; l >= 1; --l) {
+        W2TriLevel &lv = w.lv[l];
+        const unsigned blocks = (unsigned)((ns[l] + 255) / 256);
+        tri_finalize_kernel<<<blocks, 256, 0, c->stream>>>(ns[l], lv.Y, lv.V, lv.W, w.lv[l + 1].x, lv.x);
+        c->launches[1]++;
+    }
+    W2_CUDA(cudaGetLastError());
+    *sigma = w.lv[1].x;
+    return W2_OK;
+}
+
 static int tri_solve_impl(wolfd2_ctx *c, const ProvSoA &p0, double *x) {
     W2TriWork &w = c->tri;
     const long long n0 = p0.n;
     if (n0 < 2) { w2_set_error("tridiagonal system too small"); return W2_ERR_BAD_ARG; }
     if (round_up(n0, TRI_S) > w.cap) { w2_set_error("tridiagonal system of %lld exceeds prepared capacity", n0); return W2_ERR_BAD_ARG; }
-    // sizes of the hierarchy for this n
-    long long ns[6], segs[6];
-    int nl = 0;
-    for (long long n = n0;; ) {
-        ns[nl] = n; segs[nl] = (n + TRI_S - 1) / TRI_S; ++nl;
-        if (segs[nl - 1] == 1) break;
-        n = segs[nl - 1];
-    }
-    // upward sweep
-    for (int l = 0; l < nl; ++l) {
-        W2TriLevel &lv = w.lv[l];
-        const int direct = (l == nl - 1);
-        double *xo = direct ? (l == 0 ? x : lv.x) : nullptr;
-        if (l == 0)
-            tri_reduce_kernel<ProvSoA><<<(unsigned)segs[l], TRI_T, 0, c->stream>>>(p0, ns[l], lv.Y, lv.V, lv.W, lv.seg, segs[l], direct, xo);
-        else {
-            ProvSeg ps{w.lv[l - 1].seg, ns[l]};
-            tri_reduce_kernel<ProvSeg><<<(unsigned)segs[l], TRI_T, 0, c->stream>>>(ps, ns[l], lv.Y, lv.V, lv.W, lv.seg, segs[l], direct, xo);
-        }
-        c->launches[1]++;
-    }
-    // downward sweep
-    for (int l = nl - 2; l >= 0; --l) {
-        W2TriLevel &lv = w.lv[l];
-        double *xo = (l == 0) ? x : lv.x;
-        const unsigned blocks = (unsigned)((ns[l] + 255) / 256);
-        tri_finalize_kernel<<<blocks, 256, 0, c->stream>>>(ns[l], lv.Y, lv.V, lv.W, w.lv[l + 1].x, xo);
+    const long long nseg0 = (n0 + TRI_S - 1) / TRI_S;
+    W2TriLevel &lv = w.lv[0];
+    const int direct = nseg0 == 1;
+    tri_reduce_kernel<ProvSoA><<<(unsigned)nseg0, TRI_T, 0, c->stream>>>(p0, n0, lv.Y, lv.V, lv.W, lv.seg, nseg0, direct,
+                                                                         direct ? x : nullptr);
+    c->launches[1]++;
+    if (!direct) {
+        const double *sigma = nullptr;
+        W2_TRY(w2_tri_upper(c, nseg0, &sigma));
+        tri_finalize_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, c->stream>>>(n0, lv.Y, lv.V, lv.W, sigma, x);
         c->launches[1]++;
     }
     W2_CUDA(cudaGetLastError());
