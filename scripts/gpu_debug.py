@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from wolfd2_b200 import api, deck as dk
 from oracle import get_oracle
-from util import rel_l2, rand_field, test_decks, region_args
+from util import rel_l2, rand_field, make_test_decks, region_args
 
 o = get_oracle()
 rng = np.random.default_rng(12345)
@@ -14,7 +14,7 @@ print(api.lib().wolfd2_b200_version().decode())
 def cmp(tag, a, b):
     print(f"  {tag:28s} bitwise={np.array_equal(a, b)}  maxabs={np.max(np.abs(a-b)):.3e} rel_l2={rel_l2(a,b):.3e}")
 
-for d in test_decks():
+for d in make_test_decks():
     print("==", d.name, d.nx, d.ny)
     api.config(d.mnx, d.mny); o.config(d.mnx, d.mny)
     r = d.regions

@@ -1,0 +1,53 @@
+"""Regenerates tests/golden/*.npz from the CPU oracle.
+
+The reference ships no golden vectors and cannot be built here (no Fortran compiler), so these fixtures
+are REGRESSION PINS of the oracle (oracle/wolfd2_oracle.c at -O2 -ffp-contract=off), not outputs of the
+reference.  They let the GPU tests check the CUDA path against committed numbers and catch any later
+drift of the oracle itself.   Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import get_oracle  # noqa: E402
+from wolfd2_b200 import deck as dk  # noqa: E402
+
+
+def cases():
+    c = {}
+    d = dk.cavity(24, re=100.0, dt=0.02, ny=20); d.msorit = 150; d.sorrel = 1.5
+    c["cavity24x20"] = d
+    d = dk.channel(22, re=100.0, dt=0.01, ny=18, fully_dev=True); d.msorit = 400; d.sorrel = 1.6
+    c["channel22x18_fd"] = d
+    d = dk.channel(22, re=100.0, dt=0.01, ny=18, fully_dev=False); d.msorit = 400; d.sorrel = 1.6
+    c["channel22x18_mc"] = d
+    d = dk.backward_step(26, re=100.0, dt=0.01, ny=20); d.msorit = 400; d.sorrel = 1.6
+    c["bstep26x20"] = d
+    return c
+
+
+def run(d, nsteps=4):
+    o = get_oracle()
+    u, v, p = d.new_field(), d.new_field(), d.new_field()
+    ncold = o.coldstart(d, u, v, p)
+    out = {"ncold": np.array(ncold)}
+    nql, nsor, dif = [], [], []
+    for k in range(nsteps):
+        rc, lg = o.step(d, u, v, p, 1)
+        assert rc == 0
+        nql.append(lg[0]["nQLiter"]); nsor.append(lg[0]["nSorConv"]); dif.append(lg[0]["dif"][:3])
+        out[f"u{k}"], out[f"v{k}"], out[f"p{k}"] = u.copy(), v.copy(), p.copy()
+    out["nql"], out["nsor"], out["dif"] = np.array(nql), np.array(nsor), np.array(dif)
+    return out
+
+
+if __name__ == "__main__":
+    for name, d in cases().items():
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run(d))
+        print("wrote", name)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import get_oracle
-from util import rand_field, region_args, rel_l2, test_decks
+from util import rand_field, region_args, rel_l2, make_test_decks
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,7 @@ def orc():
     return get_oracle()
 
 
-DECKS = test_decks() + test_decks(64, 64)[:2]
+DECKS = make_test_decks() + make_test_decks(64, 64)[:2]
 IDS = [f"{d.name}-{d.nx}x{d.ny}" for d in DECKS]
 
 
@@ -264,3 +264,27 @@ def test_ppe_fused_pipeline_bitwise(api, orc, k, T):
         assert seen == {0, 1}   # both odd and even convergence points were exercised
     finally:
         api.set_option("sor_fused_T", -1)
+
+
+@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20"])
+def test_time_steps_against_committed_golden(api, name):
+    """CUDA path vs the committed fixtures (tests/golden/*.npz, made by make_golden.py) -- no oracle
+    involved at run time."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    d = make_golden.cases()[name]
+    ref = np.load(os.path.join(here, "golden", name + ".npz"))
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        assert ctx.coldstart() == int(ref["ncold"])
+        for k in range(4):
+            lg = ctx.step(1)[0]
+            assert lg["nQLiter"] == int(ref["nql"][k]) and lg["nSorConv"] == int(ref["nsor"][k])
+            for f, w in (("u", api.F_U), ("v", api.F_V), ("p", api.F_P)):
+                assert rel_l2(ctx.download(w), ref[f"{f}{k}"]) <= TOL_STEP, (name, f, k)
+            np.testing.assert_allclose(lg["dif"][:3], ref["dif"][k], rtol=1e-9, atol=1e-14)

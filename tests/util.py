@@ -24,7 +24,7 @@ def region_args(deck):
     return r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp
 
 
-def test_decks(nx=37, ny=29, **kw):
+def make_test_decks(nx=37, ny=29, **kw):
     """Small decks covering every boundary type and a blockage."""
     out = []
     out.append(dk.cavity(nx, re=100.0, dt=0.01, ny=ny, **kw))

@@ -316,7 +316,10 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     // an upper bound on launches: every pass may need one redo at the very end only, but a redo can
     // follow any pass, so keep launching until the control block says done
     while (true) {
-        int n = chunk;
+        // passes still needed if no convergence intervenes (+1 for a possible repeat pass)
+        const int need = (par.msorit - h.m + T - 1) / T + (h.redo > 0 ? 1 : 0);
+        int n = chunk < need ? chunk : need;
+        if (n < 1) n = 1;
         if (queued + n > 2 * passes_total) n = 2 * passes_total - queued;
         if (n <= 0) break;
         for (int q = 0; q < n; ++q) {
