@@ -224,13 +224,60 @@ def test_step_host_equals_resident(api):
         assert np.array_equal(u, c1.download(api.F_U)) and np.array_equal(p, c1.download(api.F_P))
 
 
-def test_unsupported_is_loud(api):
+@pytest.mark.parametrize("d", DECKS[:5], ids=IDS[:5])
+@pytest.mark.parametrize("cart", [1, 0])
+@pytest.mark.parametrize("solver", [1, 2, 3, 4])
+def test_ppe_other_solvers(api, orc, d, cart, solver):
+    """ids 1-4.  Lexicographic point SOR (1) is bit-exact (same data dependences, same arithmetic); the
+    line solvers (2-4) differ from the oracle only by the elimination order of each line solve."""
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(555)
+    r, m = d.regions, d.metrics
+    u, v, p = rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01)
+    pm8 = [m[n] for n in "rau rbu rbv rgv xeu yeu xzv yzv".split()]
+    for msorit, tol in ((400, 1e-8), (9, 0.0)):
+        pg, po = p.copy(), p.copy()
+        ng = api.Ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, cart, solver, msorit, d.dk, tol, 1.3, *pm8, u, v, pg)
+        no = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, cart, solver, msorit, d.dk, tol, 1.3, *pm8, u, v, po)
+        if solver == 1:
+            assert ng == no and np.array_equal(pg, po)
+        else:
+            assert abs(ng - no) <= 1          # a near-threshold exit may move by one iteration
+            if ng == no:
+                assert rel_l2(pg, po) <= 1e-11
+
+
+def test_default_solver_runs_whole_steps(api, orc):
+    """The reference's default deck (ppe_solver sor, id 1) through the step driver."""
     from wolfd2_b200 import deck as dk
-    d = dk.cavity(32, re=100.0, dt=0.01)
-    d.ppe_solver = "sor"
+    d = dk.cavity(40, re=100.0, dt=0.01, ny=36)
+    d.ppe_solver, d.msorit, d.sorrel = "sor", 500, 1.5
+    orc.config(d.mnx, d.mny)
+    uo, vo, po = d.new_field(), d.new_field(), d.new_field()
+    orc.coldstart(d, uo, vo, po)
+    rc, lo = orc.step(d, uo, vo, po, 3)
     with api.Context(d) as ctx:
-        with pytest.raises(api.Wolfd2Error):
-            ctx.coldstart()
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        ctx.coldstart()
+        lg = ctx.step(3)
+        for g, o_ in zip(lg, lo):
+            assert g["nQLiter"] == o_["nQLiter"] and g["nSorConv"] == o_["nSorConv"]
+        assert rel_l2(ctx.download(api.F_P), po) <= TOL_STEP and rel_l2(ctx.download(api.F_U), uo) <= TOL_STEP
+
+
+def test_porous_is_refused_loudly(api):
+    from wolfd2_b200 import deck as dk
+    reg = dk.RegionTables(32, 32, 2, 1, (16,), ()).porous(2, 1, 0.6, 10.0, 1.0)
+    d = dk._mk("porous", 32, 32, reg, 100.0, 0.01)
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        ctx.coldstart()
+        with pytest.raises(api.Wolfd2Error, match="porous"):
+            ctx.step(1)
 
 
 def _fused_decks():

@@ -221,6 +221,17 @@ static int sor_chunk(const wolfd2_ctx *c) {
 }
 
 // Ppe (:30-249) with nPpeSolver 5 or 6 (SorRB / SorRBP: same update, same max-norm).
+int w2_ppe_line_sor(wolfd2_ctx *c, double *p, int *nSorConv, int *converged, int *iters_done);
+int w2_ppe_lex_sor(wolfd2_ctx *c, double *p, int *nSorConv, int *converged, int *iters_done);
+
+// RhsPpe on a non-Cartesian grid, for the solvers in w2_ppe_other.cu
+void rhs_cross_launch(wolfd2_ctx *c, double *p) {
+    dim3 g2((c->nx - 1 + 255) / 256, (c->ny - 1) < 2048 ? (c->ny - 1) : 2048);
+    rhs_cross_kernel<<<g2, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, c->par.dk, c->met.rbu, c->met.rbv, c->div, p,
+                                                c->fld[W2_F_B], nullptr);
+    c->launches[2]++;
+}
+
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done);
 
@@ -235,11 +246,11 @@ static int fused_T() {   // 0 selects the plain half-sweep kernels, 1 or 2 the f
 
 int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSorConv, int *converged) {
     const wolfd2_params &par = c->par;
-    if (par.nPpeSolver != W2_PPE_RB_SOR && par.nPpeSolver != W2_PPE_PAR_RB_SOR) {
-        w2_set_error("ppe_solver id %d is not implemented on the device yet (supported: rb_sor=5, par_rb_sor=6)",
-                     par.nPpeSolver);
-        return W2_ERR_UNSUPPORTED;
+    if (par.nPpeSolver < 1 || par.nPpeSolver > 6) {
+        w2_set_error("Wrong nPpeSolver flag passed to Ppe: %d", par.nPpeSolver);   // :238-239
+        return W2_ERR_BAD_ARG;
     }
+    const bool rb_point = par.nPpeSolver == W2_PPE_RB_SOR || par.nPpeSolver == W2_PPE_PAR_RB_SOR;
     const int nx = c->nx, ny = c->ny, pitch = c->pitch;
     const int cart = par.lCartesGrid != 0;
     const int has_mask = c->hreg.has_blockage;
@@ -247,7 +258,7 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
     SorCtl *ctl = (SorCtl *)c->d_flags;
     static_assert(sizeof(SorCtl) <= 64 * sizeof(int), "ctl block too large");
 
-    const int T = (cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
+    const int T = (rb_point && cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
     dim3 g2((nx - 1 + 255) / 256, (ny - 1) < 2048 ? (ny - 1) : 2048);
     div_rhs_kernel<<<g2, 256, 0, c->stream>>>(nx, ny, pitch, par.dk, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv, u, v,
                                               c->pmask, has_mask, T > 0, b, cart ? nullptr : c->div);
@@ -266,6 +277,21 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
         cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
         c->sor_ms += ms;
         c->sor_iters += iters;
+        return W2_OK;
+    }
+    if (!rb_point) {   // ids 1-4: w2_ppe_other.cu
+        int iters = 0, conv = 0, nconv = par.msorit;
+        cudaEventRecord(c->ev[4], c->stream);
+        if (par.nPpeSolver == W2_PPE_SOR) W2_TRY(w2_ppe_lex_sor(c, p, &nconv, &conv, &iters));
+        else W2_TRY(w2_ppe_line_sor(c, p, &nconv, &conv, &iters));
+        cudaEventRecord(c->ev[5], c->stream);
+        W2_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+        c->sor_ms += ms;
+        c->sor_iters += iters;
+        if (converged) *converged = conv;
+        if (nSorConv) *nSorConv = nconv;
         return W2_OK;
     }
     sor_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
