@@ -14,6 +14,8 @@
 
 #define F(a, i, j) a[IDX(i, j)]
 
+__device__ __forceinline__ double a_sum4_sic(double a, double b, double c, double d) { return a + b + c + d / 4.0; }
+
 struct MomArgs {
     int nx, ny, pitch;
     double dk, re, fr;
@@ -24,27 +26,69 @@ struct MomArgs {
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
     const unsigned char *xmask, *ymask;
     const double *x1;  // first-step solution, field layout
+    // porous regions (RM_POROUS): per-cell region maps, see por_map_kernel
+    int porous;
+    const W2Regions *R;
+    const unsigned char *xd1, *xd2, *yd1, *yd2, *xcp, *ycp;
 };
+
+// "divide convective terms by porosity" (:296-324 for u, :621-649 for v): the loops visit regions in
+// order and their index ranges overlap on shared borders, so a point can be divided twice -- the two
+// maps hold the (1-based) porous regions whose range contains the point, in visiting order.
+__device__ __forceinline__ double por_div(const MomArgs &m, const unsigned char *d1, const unsigned char *d2, int i,
+                                          int j, double val) {
+    if (!m.porous) return val;
+    const int pitch = m.pitch;
+    const int q1 = d1[IDX(i, j)];
+    if (q1) val = val / m.R->poros[q1 - 1];
+    const int q2 = d2[IDX(i, j)];
+    if (q2) val = val / m.R->poros[q2 - 1];
+    return val;
+}
+// PorosCoef (:1115-1226): Dupuit-Forchheimer coefficient at (i,j); the region whose assignment reaches
+// the cell last wins (non-porous regions assign 0 on jS..jN x iW..iE, :1166-1172).
+template <int COMP>
+__device__ __forceinline__ double por_coef(const MomArgs &m, const double *u, const double *v, int njacob, int i, int j) {
+    if (!m.porous) return 0.0;
+    const int pitch = m.pitch;
+    const int q = (COMP == 0 ? m.xcp : m.ycp)[IDX(i, j)];
+    if (!q || m.R->type[q - 1] != W2_RM_POROUS) return 0.0;
+    const double porc1 = m.R->porc1[q - 1], porc2 = m.R->porc2[q - 1];
+    double unorm, own;
+    if (COMP == 0) {   // :1193-1194 (sic: /dFour binds to the last v only)
+        const double t = a_sum4_sic(v[IDX(i, j)], v[IDX(i + 1, j)], v[IDX(i, j - 1)], v[IDX(i + 1, j - 1)]);
+        own = u[IDX(i, j)];
+        unorm = sqrt(own * own + t * t);
+    } else {           // :1207-1208
+        const double t = (u[IDX(i - 1, j + 1)] + u[IDX(i, j + 1)] + u[IDX(i - 1, j)] + u[IDX(i, j)]) / 4.0;
+        own = v[IDX(i, j)];
+        unorm = sqrt(t * t + own * own);
+    }
+    double unrm1 = 0.0;
+    if (unorm > 1.e-8) unrm1 = (own * own) / unorm;
+    if (njacob == 1) unorm = unrm1 + unorm;
+    return porc1 + porc2 * unorm;
+}
 
 // ---- ConvCoef pieces ------------------------------------------------------------------------
 // case 1 (x-momentum rhs, djac = 1): cc1 on 1..nx+1,1..ny+1 ; cc2 on 1..nx,1..ny   (:901-913)
-__device__ __forceinline__ double x_c1(const MomArgs &m, const double *u, const double *v, int i, int j) {
+__device__ __forceinline__ double x_c1_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
     const int pitch = m.pitch;
     return (F(m.yec, i, j) * (F(u, i, j) + F(u, i - 1, j)) - F(m.xec, i, j) * (F(v, i, j) + F(v, i, j - 1))) * 0.5;
 }
-__device__ __forceinline__ double x_c2(const MomArgs &m, const double *u, const double *v, int i, int j) {
+__device__ __forceinline__ double x_c2_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
     const int pitch = m.pitch;
     return (F(m.xzn, i, j) * (F(v, i + 1, j) + F(v, i, j)) - F(m.yzn, i, j) * (F(u, i, j + 1) + F(u, i, j))) * 0.5;
 }
 // case 4 (x-momentum upwind Jacobian, djac = 2): written on i=0..nx, j=1..ny   (:942-950)
-__device__ __forceinline__ double x_cj1(const MomArgs &m, int i, int j) {
+__device__ __forceinline__ double x_cj1_raw(const MomArgs &m, int i, int j) {
     const int pitch = m.pitch;
     if (i > m.nx) return 0.0;  // never written by the reference -> static zero
     const double *u = m.us, *v = m.vs;
     return 2.0 * F(m.yeu, i, j) * F(u, i, j)
            - F(m.xeu, i, j) * (F(v, i + 1, j) + F(v, i, j) + F(v, i + 1, j - 1) + F(v, i, j - 1)) / 4.0;
 }
-__device__ __forceinline__ double x_cj2(const MomArgs &m, int i, int j) {
+__device__ __forceinline__ double x_cj2_raw(const MomArgs &m, int i, int j) {
     const int pitch = m.pitch;
     if (j > m.ny) return 0.0;  // cj2(i,ny+1): never written
     const double *u = m.us, *v = m.vs;
@@ -52,29 +96,39 @@ __device__ __forceinline__ double x_cj2(const MomArgs &m, int i, int j) {
            - 2.0 * F(m.yzu, i, j) * F(u, i, j);
 }
 // case 2 (y-momentum rhs): cc1 on 1..nx,1..ny ; cc2 on 1..nx+1,1..ny+1   (:916-928)
-__device__ __forceinline__ double y_c1(const MomArgs &m, const double *u, const double *v, int i, int j) {
+__device__ __forceinline__ double y_c1_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
     const int pitch = m.pitch;
     return (F(m.yen, i, j) * (F(u, i, j + 1) + F(u, i, j)) - F(m.xen, i, j) * (F(v, i + 1, j) + F(v, i, j))) * 0.5;
 }
-__device__ __forceinline__ double y_c2(const MomArgs &m, const double *u, const double *v, int i, int j) {
+__device__ __forceinline__ double y_c2_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
     const int pitch = m.pitch;
     return (F(m.xzc, i, j) * (F(v, i, j) + F(v, i, j - 1)) - F(m.yzc, i, j) * (F(u, i, j) + F(u, i - 1, j))) * 0.5;
 }
 // case 5 (y-momentum upwind Jacobian, djac = 2): written on i=1..nx, j=0..ny   (:953-961)
-__device__ __forceinline__ double y_cj1(const MomArgs &m, int i, int j) {
+__device__ __forceinline__ double y_cj1_raw(const MomArgs &m, int i, int j) {
     const int pitch = m.pitch;
     if (i > m.nx) return 0.0;  // cj1(nx+1,j): never written
     const double *u = m.us, *v = m.vs;
     return F(m.yev, i, j) * (F(u, i, j + 1) + F(u, i - 1, j + 1) + F(u, i, j) + F(u, i - 1, j)) / 4.0
            - 2.0 * F(m.xev, i, j) * F(v, i, j);
 }
-__device__ __forceinline__ double y_cj2(const MomArgs &m, int i, int j) {
+__device__ __forceinline__ double y_cj2_raw(const MomArgs &m, int i, int j) {
     const int pitch = m.pitch;
     if (j > m.ny) return 0.0;  // cj2(i,ny+1): never written
     const double *u = m.us, *v = m.vs;
     return 2.0 * F(m.xzv, i, j) * F(v, i, j)
            - F(m.yzv, i, j) * (F(u, i, j + 1) + F(u, i - 1, j + 1) + F(u, i, j) + F(u, i - 1, j)) / 4.0;
 }
+
+// porosity-scaled versions (identity when the deck has no porous region)
+__device__ __forceinline__ double x_c1(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_c1_raw(m, u, v, i, j)); }
+__device__ __forceinline__ double x_c2(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_c2_raw(m, u, v, i, j)); }
+__device__ __forceinline__ double y_c1(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_c1_raw(m, u, v, i, j)); }
+__device__ __forceinline__ double y_c2(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_c2_raw(m, u, v, i, j)); }
+__device__ __forceinline__ double x_cj1(const MomArgs &m, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_cj1_raw(m, i, j)); }
+__device__ __forceinline__ double x_cj2(const MomArgs &m, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_cj2_raw(m, i, j)); }
+__device__ __forceinline__ double y_cj1(const MomArgs &m, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_cj1_raw(m, i, j)); }
+__device__ __forceinline__ double y_cj2(const MomArgs &m, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_cj2_raw(m, i, j)); }
 
 // DConvU (:1000-1006) and DDiffU (:1030-1042) at one point
 __device__ __forceinline__ double x_conv(const MomArgs &m, const double *u, const double *v, int i, int j) {
@@ -139,6 +193,10 @@ __device__ __forceinline__ void mom_row(const MomArgs &m, int i, int j, double &
         const double cnvs = x_conv(m, m.us, m.vs, i, j), cnvn = x_conv(m, m.un, m.vn, i, j);
         const double difs = x_diff(m, m.us, i, j), difn = x_diff(m, m.un, i, j);
         b = F(m.un, i, j) - F(m.us, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
+        if (m.porous) {   // + dk2*cpj on the diagonal, - dk2*(cps*us + cpn*un) on the rhs (:367-381)
+            a2 = a2 + dk2 * por_coef<0>(m, m.us, m.vs, 1, i, j);
+            b = b - dk2 * (por_coef<0>(m, m.us, m.vs, 0, i, j) * F(m.us, i, j) + por_coef<0>(m, m.un, m.vn, 0, i, j) * F(m.un, i, j));
+        }
     } else if (COMP == 0 && STEP == 2) {
         if (m.xmask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
         const double rkj = dk2 * F(m.dju, i, j);
@@ -153,36 +211,42 @@ __device__ __forceinline__ void mom_row(const MomArgs &m, int i, int j, double &
             a2 = 1.0 + rkj * (-cj + re1 * (g0 + gm));
             a3 = rkj * (x_cj2(m, i, j + 1) - re1 * g0);
         }
+        if (m.porous) a2 = a2 + dk2 * por_coef<0>(m, m.us, m.vs, 1, i, j);   // :413-419
         b = m.x1[IDX(i, j)];
     } else if (COMP == 1 && STEP == 1) {
         const double rkj = dk2 * F(m.djv, i, j);
         const double cj = y_cj1(m, i, j);
         const double an0 = F(m.ran, i, j), anm = F(m.ran, i - 1, j);
+        const double cpj = m.porous ? dk2 * por_coef<1>(m, m.us, m.vs, 1, i, j) : 0.0;   // x + 0.0 == x
         if (cj >= 0.0) {
             a1 = rkj * (-y_cj1(m, i - 1, j) - re1 * anm);
-            a2 = rkj * (cj + re1 * (an0 + anm)) + 1.0;
+            a2 = rkj * (cj + re1 * (an0 + anm)) + cpj + 1.0;
             a3 = rkj * (-re1 * an0);
         } else {
             a1 = rkj * (-re1 * anm);
-            a2 = rkj * (-cj + re1 * (an0 + anm)) + 1.0;
+            a2 = rkj * (-cj + re1 * (an0 + anm)) + cpj + 1.0;
             a3 = rkj * (y_cj1(m, i + 1, j) - re1 * an0);
         }
         const double buoy = m.dk * (F(m.d, i, j + 1) + F(m.d, i, j) + F(m.dn, i, j + 1) + F(m.dn, i, j)) / (4.0 * m.fr);
         const double cnvs = y_conv(m, m.us, m.vs, i, j), cnvn = y_conv(m, m.un, m.vn, i, j);
         const double difs = y_diff(m, m.vs, i, j), difn = y_diff(m, m.vn, i, j);
-        b = F(m.vn, i, j) - F(m.vs, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn) - buoy;
+        b = F(m.vn, i, j) - F(m.vs, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
+        if (m.porous)     // :705-708
+            b = b - dk2 * (por_coef<1>(m, m.us, m.vs, 0, i, j) * F(m.vs, i, j) + por_coef<1>(m, m.un, m.vn, 0, i, j) * F(m.vn, i, j));
+        b = b - buoy;
     } else {
         if (m.ymask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
         const double rkj = dk2 * F(m.djv, i, j);
         const double cj = y_cj2(m, i, j);
         const double g0 = F(m.rgc, i, j), gp = F(m.rgc, i, j + 1);
+        const double cpj = m.porous ? dk2 * por_coef<1>(m, m.us, m.vs, 1, i, j) : 0.0;
         if (cj >= 0.0) {
             a1 = rkj * (-y_cj2(m, i, j - 1) - re1 * g0);
-            a2 = rkj * (cj + re1 * (gp + g0)) + 1.0;
+            a2 = rkj * (cj + re1 * (gp + g0)) + cpj + 1.0;
             a3 = rkj * (-re1 * gp);
         } else {
             a1 = rkj * (-re1 * g0);
-            a2 = rkj * (-cj + re1 * (gp + g0)) + 1.0;
+            a2 = rkj * (-cj + re1 * (gp + g0)) + cpj + 1.0;
             a3 = rkj * (y_cj2(m, i, j + 1) - re1 * gp);
         }
         b = m.x1[IDX(i, j)];
@@ -395,7 +459,37 @@ __global__ void __launch_bounds__(256) ql_update_kernel(int nx, int ny, int pitc
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+// per-cell porous-region maps (6 planes): xd1,xd2 / yd1,yd2 = porous regions whose division range holds
+// the cell (momentum.f:310-319 / :635-644); xcp / ycp = last region whose PorosCoef assignment reaches it
+__global__ void por_map_kernel(const W2Regions *__restrict__ R, int nx, int ny, int pitch, size_t plane,
+                               unsigned char *__restrict__ maps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i > nx + 1 || j > ny + 1) return;
+    unsigned char xd[2] = {0, 0}, yd[2] = {0, 0}, xc = 0, yc = 0;
+    int nxd = 0, nyd = 0;
+    for (int q = 0; q < R->nreg; ++q) {
+        const int iW = R->iW[q], iE = R->iE[q], jS = R->jS[q], jN = R->jN[q];
+        const bool por = R->type[q] == W2_RM_POROUS;
+        const bool inx = i >= iW && i <= iE && j >= jS + 1 && j <= jN;
+        const bool iny = i >= iW + 1 && i <= iE && j >= jS && j <= jN;
+        const bool full = i >= iW && i <= iE && j >= jS && j <= jN;
+        if (por) {
+            if (inx) { if (nxd < 2) xd[nxd] = (unsigned char)(q + 1); ++nxd; xc = (unsigned char)(q + 1); }
+            if (iny) { if (nyd < 2) yd[nyd] = (unsigned char)(q + 1); ++nyd; yc = (unsigned char)(q + 1); }
+        } else if (full) { xc = (unsigned char)(q + 1); yc = (unsigned char)(q + 1); }
+    }
+    const size_t o = IDX(i, j);
+    maps[o] = xd[0]; maps[plane + o] = xd[1]; maps[2 * plane + o] = yd[0]; maps[3 * plane + o] = yd[1];
+    maps[4 * plane + o] = xc; maps[5 * plane + o] = yc;
+}
+
 int w2_build_mom_masks(wolfd2_ctx *c) {
+    if (c->hreg.has_porous) {
+        if (!c->pormap) W2_CUDA(cudaMalloc((void **)&c->pormap, 6 * c->nelem));
+        dim3 g((c->nx + 2 + 255) / 256, c->ny + 2);
+        por_map_kernel<<<g, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, c->nelem, c->pormap);
+    }
     dim3 grid((c->nx + 2 + 255) / 256, c->ny + 2);
     mom_mask_kernel<<<grid, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, c->xmask, c->ymask);
     W2_CUDA(cudaGetLastError());
@@ -416,14 +510,10 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xev = t.xev; m.yev = t.yev; m.xzv = t.xzv; m.yzv = t.yzv;
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->tx;
-}
-
-static int check_porous(wolfd2_ctx *c) {
-    if (c->hreg.has_porous) {
-        w2_set_error("porous regions (RM_POROUS, PorosCoef momentum.f:1115-1226) are not implemented on the device yet");
-        return W2_ERR_UNSUPPORTED;
-    }
-    return W2_OK;
+    m.porous = c->hreg.has_porous; m.R = c->dreg;
+    unsigned char *pm = c->pormap;
+    m.xd1 = pm; m.xd2 = pm + c->nelem; m.yd1 = pm + 2 * c->nelem; m.yd2 = pm + 3 * c->nelem;
+    m.xcp = pm + 4 * c->nelem; m.ycp = pm + 5 * c->nelem;
 }
 
 template <int COMP, int STEP>
@@ -450,7 +540,6 @@ static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
 }
 
 int w2_xmomentum(wolfd2_ctx *c, double *dus) {
-    W2_TRY(check_porous(c));
     MomArgs m;
     fill_args(c, m);
     const long long n = (long long)c->nx * (c->ny - 1);
@@ -460,7 +549,6 @@ int w2_xmomentum(wolfd2_ctx *c, double *dus) {
 }
 
 int w2_ymomentum(wolfd2_ctx *c, double *dvs) {
-    W2_TRY(check_porous(c));
     MomArgs m;
     fill_args(c, m);
     const long long n = (long long)(c->nx - 1) * c->ny;
