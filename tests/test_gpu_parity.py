@@ -318,3 +318,60 @@ def test_porous_regions(api, orc, k):
             assert lg["nQLiter"] == lo[0]["nQLiter"] and lg["nSorConv"] == lo[0]["nSorConv"]
             for w, ref in ((api.F_U, uo), (api.F_V, vo), (api.F_P, po)):
                 assert rel_l2(ctx.download(w), ref) <= TOL_STEP
+
+
+def _fused_decks():
+    from wolfd2_b200 import deck as dk
+    return [dk.cavity(300, re=100.0, dt=0.001, ny=40), dk.channel(600, re=100.0, dt=0.001, ny=90),
+            dk.backward_step(520, re=100.0, dt=0.001, ny=64), dk.cavity(254, re=100.0, dt=0.001, ny=8),
+            dk.cavity(1030, re=100.0, dt=0.001, ny=37)]
+
+
+@pytest.mark.parametrize("k", range(5))
+@pytest.mark.parametrize("T", [0, 1, 2])
+def test_ppe_fused_pipeline_bitwise(api, orc, k, T):
+    """The fused red/black pipeline (several strips, several bands, blockage sentinel, T iterations per
+    pass incl. convergence in the middle of a pass) must reproduce SorRB bit for bit."""
+    d = _fused_decks()[k]
+    _cfg(api, orc, d)
+    api.set_option("sor_fused_T", T)
+    try:
+        rng = np.random.default_rng(2024 + k)
+        r, m = d.regions, d.metrics
+        u, v, p = rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01), rand_field(d, rng, -0.01, 0.01)
+        pm8 = [m[n] for n in "rau rbu rbv rgv xeu yeu xzv yzv".split()]
+        seen = set()
+        for msorit, tol in ((40, 1e-3), (41, 2e-3), (400, 3e-4), (401, 1e-4), (7, 0.0), (8, 0.0), (1, 1.0), (2, 1.0), (3, 1.0)):
+            pg, po = p.copy(), p.copy()
+            ng = api.Ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 5, msorit, d.dk, tol, 1.7, *pm8, u, v, pg)
+            no = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 5, msorit, d.dk, tol, 1.7, *pm8, u, v, po)
+            assert ng == no, (msorit, tol)
+            assert np.array_equal(pg, po), (msorit, tol)
+            seen.add(no % 2)
+        assert seen == {0, 1}   # both odd and even convergence points were exercised
+    finally:
+        api.set_option("sor_fused_T", -1)
+
+
+@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20"])
+def test_time_steps_against_committed_golden(api, name):
+    """CUDA path vs the committed fixtures (tests/golden/*.npz, made by make_golden.py) -- no oracle
+    involved at run time."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    d = make_golden.cases()[name]
+    ref = np.load(os.path.join(here, "golden", name + ".npz"))
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        assert ctx.coldstart() == int(ref["ncold"])
+        for k in range(4):
+            lg = ctx.step(1)[0]
+            assert lg["nQLiter"] == int(ref["nql"][k]) and lg["nSorConv"] == int(ref["nsor"][k])
+            for f, w in (("u", api.F_U), ("v", api.F_V), ("p", api.F_P)):
+                assert rel_l2(ctx.download(w), ref[f"{f}{k}"]) <= TOL_STEP, (name, f, k)
+            np.testing.assert_allclose(lg["dif"][:3], ref["dif"][k], rtol=1e-9, atol=1e-14)

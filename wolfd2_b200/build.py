@@ -25,7 +25,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + \
         [os.path.join(HERE, "..", "include", "wolfd2_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -32,225 +32,11 @@ struct MomArgs {
     const unsigned char *xd1, *xd2, *yd1, *yd2, *xcp, *ycp;
 };
 
-// "divide convective terms by porosity" (:296-324 for u, :621-649 for v): the loops visit regions in
-// order and their index ranges overlap on shared borders, so a point can be divided twice -- the two
-// maps hold the (1-based) porous regions whose range contains the point, in visiting order.
-__device__ __forceinline__ double por_div(const MomArgs &m, const unsigned char *d1, const unsigned char *d2, int i,
-                                          int j, double val) {
-    if (!m.porous) return val;
-    const int pitch = m.pitch;
-    const int q1 = d1[IDX(i, j)];
-    if (q1) val = val / m.R->poros[q1 - 1];
-    const int q2 = d2[IDX(i, j)];
-    if (q2) val = val / m.R->poros[q2 - 1];
-    return val;
+namespace mom_np { constexpr bool kPorous = false;
+#include "w2_mom_rows.inc"
 }
-// PorosCoef (:1115-1226): Dupuit-Forchheimer coefficient at (i,j); the region whose assignment reaches
-// the cell last wins (non-porous regions assign 0 on jS..jN x iW..iE, :1166-1172).
-template <int COMP>
-__device__ __forceinline__ double por_coef(const MomArgs &m, const double *u, const double *v, int njacob, int i, int j) {
-    if (!m.porous) return 0.0;
-    const int pitch = m.pitch;
-    const int q = (COMP == 0 ? m.xcp : m.ycp)[IDX(i, j)];
-    if (!q || m.R->type[q - 1] != W2_RM_POROUS) return 0.0;
-    const double porc1 = m.R->porc1[q - 1], porc2 = m.R->porc2[q - 1];
-    double unorm, own;
-    if (COMP == 0) {   // :1193-1194 (sic: /dFour binds to the last v only)
-        const double t = a_sum4_sic(v[IDX(i, j)], v[IDX(i + 1, j)], v[IDX(i, j - 1)], v[IDX(i + 1, j - 1)]);
-        own = u[IDX(i, j)];
-        unorm = sqrt(own * own + t * t);
-    } else {           // :1207-1208
-        const double t = (u[IDX(i - 1, j + 1)] + u[IDX(i, j + 1)] + u[IDX(i - 1, j)] + u[IDX(i, j)]) / 4.0;
-        own = v[IDX(i, j)];
-        unorm = sqrt(t * t + own * own);
-    }
-    double unrm1 = 0.0;
-    if (unorm > 1.e-8) unrm1 = (own * own) / unorm;
-    if (njacob == 1) unorm = unrm1 + unorm;
-    return porc1 + porc2 * unorm;
-}
-
-// ---- ConvCoef pieces ------------------------------------------------------------------------
-// case 1 (x-momentum rhs, djac = 1): cc1 on 1..nx+1,1..ny+1 ; cc2 on 1..nx,1..ny   (:901-913)
-__device__ __forceinline__ double x_c1_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    return (F(m.yec, i, j) * (F(u, i, j) + F(u, i - 1, j)) - F(m.xec, i, j) * (F(v, i, j) + F(v, i, j - 1))) * 0.5;
-}
-__device__ __forceinline__ double x_c2_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    return (F(m.xzn, i, j) * (F(v, i + 1, j) + F(v, i, j)) - F(m.yzn, i, j) * (F(u, i, j + 1) + F(u, i, j))) * 0.5;
-}
-// case 4 (x-momentum upwind Jacobian, djac = 2): written on i=0..nx, j=1..ny   (:942-950)
-__device__ __forceinline__ double x_cj1_raw(const MomArgs &m, int i, int j) {
-    const int pitch = m.pitch;
-    if (i > m.nx) return 0.0;  // never written by the reference -> static zero
-    const double *u = m.us, *v = m.vs;
-    return 2.0 * F(m.yeu, i, j) * F(u, i, j)
-           - F(m.xeu, i, j) * (F(v, i + 1, j) + F(v, i, j) + F(v, i + 1, j - 1) + F(v, i, j - 1)) / 4.0;
-}
-__device__ __forceinline__ double x_cj2_raw(const MomArgs &m, int i, int j) {
-    const int pitch = m.pitch;
-    if (j > m.ny) return 0.0;  // cj2(i,ny+1): never written
-    const double *u = m.us, *v = m.vs;
-    return F(m.xzu, i, j) * (F(v, i + 1, j) + F(v, i, j) + F(v, i + 1, j - 1) + F(v, i, j - 1)) / 4.0
-           - 2.0 * F(m.yzu, i, j) * F(u, i, j);
-}
-// case 2 (y-momentum rhs): cc1 on 1..nx,1..ny ; cc2 on 1..nx+1,1..ny+1   (:916-928)
-__device__ __forceinline__ double y_c1_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    return (F(m.yen, i, j) * (F(u, i, j + 1) + F(u, i, j)) - F(m.xen, i, j) * (F(v, i + 1, j) + F(v, i, j))) * 0.5;
-}
-__device__ __forceinline__ double y_c2_raw(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    return (F(m.xzc, i, j) * (F(v, i, j) + F(v, i, j - 1)) - F(m.yzc, i, j) * (F(u, i, j) + F(u, i - 1, j))) * 0.5;
-}
-// case 5 (y-momentum upwind Jacobian, djac = 2): written on i=1..nx, j=0..ny   (:953-961)
-__device__ __forceinline__ double y_cj1_raw(const MomArgs &m, int i, int j) {
-    const int pitch = m.pitch;
-    if (i > m.nx) return 0.0;  // cj1(nx+1,j): never written
-    const double *u = m.us, *v = m.vs;
-    return F(m.yev, i, j) * (F(u, i, j + 1) + F(u, i - 1, j + 1) + F(u, i, j) + F(u, i - 1, j)) / 4.0
-           - 2.0 * F(m.xev, i, j) * F(v, i, j);
-}
-__device__ __forceinline__ double y_cj2_raw(const MomArgs &m, int i, int j) {
-    const int pitch = m.pitch;
-    if (j > m.ny) return 0.0;  // cj2(i,ny+1): never written
-    const double *u = m.us, *v = m.vs;
-    return 2.0 * F(m.xzv, i, j) * F(v, i, j)
-           - F(m.yzv, i, j) * (F(u, i, j + 1) + F(u, i - 1, j + 1) + F(u, i, j) + F(u, i - 1, j)) / 4.0;
-}
-
-// porosity-scaled versions (identity when the deck has no porous region)
-__device__ __forceinline__ double x_c1(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_c1_raw(m, u, v, i, j)); }
-__device__ __forceinline__ double x_c2(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_c2_raw(m, u, v, i, j)); }
-__device__ __forceinline__ double y_c1(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_c1_raw(m, u, v, i, j)); }
-__device__ __forceinline__ double y_c2(const MomArgs &m, const double *u, const double *v, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_c2_raw(m, u, v, i, j)); }
-__device__ __forceinline__ double x_cj1(const MomArgs &m, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_cj1_raw(m, i, j)); }
-__device__ __forceinline__ double x_cj2(const MomArgs &m, int i, int j) { return por_div(m, m.xd1, m.xd2, i, j, x_cj2_raw(m, i, j)); }
-__device__ __forceinline__ double y_cj1(const MomArgs &m, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_cj1_raw(m, i, j)); }
-__device__ __forceinline__ double y_cj2(const MomArgs &m, int i, int j) { return por_div(m, m.yd1, m.yd2, i, j, y_cj2_raw(m, i, j)); }
-
-// DConvU (:1000-1006) and DDiffU (:1030-1042) at one point
-__device__ __forceinline__ double x_conv(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    const double c1 = x_c1(m, u, v, i, j), c1e = x_c1(m, u, v, i + 1, j);
-    const double c2 = x_c2(m, u, v, i, j), c2s = x_c2(m, u, v, i, j - 1);
-    return -c2s * F(u, i, j - 1) - c1 * F(u, i - 1, j) + (c1e - c1 + c2 - c2s) * F(u, i, j)
-           + c1e * F(u, i + 1, j) + c2 * F(u, i, j + 1);
-}
-__device__ __forceinline__ double x_diff(const MomArgs &m, const double *u, int i, int j) {
-    const int pitch = m.pitch;
-    const double *ac = m.rac, *bc = m.rbc, *bn = m.rbn, *gn = m.rgn;
-    const double s1 = F(ac, i + 1, j) * (F(u, i + 1, j) - F(u, i, j)) - F(ac, i, j) * (F(u, i, j) - F(u, i - 1, j))
-                      + F(bc, i + 1, j) * (F(u, i + 1, j + 1) + F(u, i, j + 1) - F(u, i + 1, j - 1) - F(u, i, j - 1))
-                      - F(bc, i, j) * (F(u, i, j + 1) + F(u, i - 1, j + 1) - F(u, i, j - 1) - F(u, i - 1, j - 1));
-    const double s2 = F(bn, i, j) * (F(u, i + 1, j + 1) + F(u, i + 1, j) - F(u, i - 1, j + 1) - F(u, i - 1, j))
-                      - F(bn, i, j - 1) * (F(u, i + 1, j) + F(u, i + 1, j - 1) - F(u, i - 1, j) - F(u, i - 1, j - 1))
-                      + F(gn, i, j) * (F(u, i, j + 1) - F(u, i, j)) - F(gn, i, j - 1) * (F(u, i, j) - F(u, i, j - 1));
-    return s1 + s2;
-}
-// DConvV (:1064-1070) and DDiffV (:1094-1106)
-__device__ __forceinline__ double y_conv(const MomArgs &m, const double *u, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    const double c1 = y_c1(m, u, v, i, j), c1w = y_c1(m, u, v, i - 1, j);
-    const double c2 = y_c2(m, u, v, i, j), c2n = y_c2(m, u, v, i, j + 1);
-    return -c2 * F(v, i, j - 1) - c1w * F(v, i - 1, j) + (c1 - c1w + c2n - c2) * F(v, i, j)
-           + c1 * F(v, i + 1, j) + c2n * F(v, i, j + 1);
-}
-__device__ __forceinline__ double y_diff(const MomArgs &m, const double *v, int i, int j) {
-    const int pitch = m.pitch;
-    const double *an = m.ran, *bc = m.rbc, *bn = m.rbn, *gc = m.rgc;
-    const double s1 = F(an, i, j) * (F(v, i + 1, j) - F(v, i, j)) - F(an, i - 1, j) * (F(v, i, j) - F(v, i - 1, j))
-                      + F(bn, i, j) * (F(v, i + 1, j + 1) + F(v, i, j + 1) - F(v, i + 1, j - 1) - F(v, i, j - 1))
-                      - F(bn, i - 1, j) * (F(v, i, j + 1) + F(v, i - 1, j + 1) - F(v, i, j - 1) - F(v, i - 1, j - 1));
-    const double s2 = F(bc, i, j + 1) * (F(v, i + 1, j + 1) + F(v, i + 1, j) - F(v, i - 1, j + 1) - F(v, i - 1, j))
-                      - F(bc, i, j) * (F(v, i + 1, j) + F(v, i + 1, j - 1) - F(v, i - 1, j) - F(v, i - 1, j - 1))
-                      + F(gc, i, j + 1) * (F(v, i, j + 1) - F(v, i, j)) - F(gc, i, j) * (F(v, i, j) - F(v, i, j - 1));
-    return s1 + s2;
-}
-
-// ---- one row of each split-step system ---------------------------------------------------------------
-// COMP 0 = x-momentum (unknown (i,j), i=1..nx, j=2..ny), COMP 1 = y-momentum (i=2..nx, j=1..ny);
-// STEP 1: LHS + rhs of the first split step (:350-384 / :675-711);
-// STEP 2: LHS of the second step, identity rows, rhs = first-step solution (:396-496 / :723-821).
-template <int COMP, int STEP>
-__device__ __forceinline__ void mom_row(const MomArgs &m, int i, int j, double &a1, double &a2, double &a3, double &b) {
-    const int pitch = m.pitch;
-    const double re1 = 1.0 / m.re, dk2 = m.dk * 0.5;
-    if (COMP == 0 && STEP == 1) {
-        const double rkj = dk2 * F(m.dju, i, j);
-        const double cj = x_cj1(m, i, j);
-        const double rac0 = F(m.rac, i, j), rac1 = F(m.rac, i + 1, j);
-        if (cj >= 0.0) {
-            a1 = rkj * (-x_cj1(m, i - 1, j) - re1 * rac0);
-            a2 = 1.0 + rkj * (cj + re1 * (rac1 + rac0));
-            a3 = rkj * (-re1 * rac1);
-        } else {
-            a1 = rkj * (-re1 * rac0);
-            a2 = 1.0 + rkj * (-cj + re1 * (rac1 + rac0));
-            a3 = rkj * (x_cj1(m, i + 1, j) - re1 * rac1);
-        }
-        const double cnvs = x_conv(m, m.us, m.vs, i, j), cnvn = x_conv(m, m.un, m.vn, i, j);
-        const double difs = x_diff(m, m.us, i, j), difn = x_diff(m, m.un, i, j);
-        b = F(m.un, i, j) - F(m.us, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
-        if (m.porous) {   // + dk2*cpj on the diagonal, - dk2*(cps*us + cpn*un) on the rhs (:367-381)
-            a2 = a2 + dk2 * por_coef<0>(m, m.us, m.vs, 1, i, j);
-            b = b - dk2 * (por_coef<0>(m, m.us, m.vs, 0, i, j) * F(m.us, i, j) + por_coef<0>(m, m.un, m.vn, 0, i, j) * F(m.un, i, j));
-        }
-    } else if (COMP == 0 && STEP == 2) {
-        if (m.xmask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
-        const double rkj = dk2 * F(m.dju, i, j);
-        const double cj = x_cj2(m, i, j);
-        const double g0 = F(m.rgn, i, j), gm = F(m.rgn, i, j - 1);
-        if (cj >= 0.0) {
-            a1 = rkj * (-x_cj2(m, i, j - 1) - re1 * gm);
-            a2 = 1.0 + rkj * (cj + re1 * (g0 + gm));
-            a3 = rkj * (-re1 * g0);
-        } else {
-            a1 = rkj * (-re1 * gm);
-            a2 = 1.0 + rkj * (-cj + re1 * (g0 + gm));
-            a3 = rkj * (x_cj2(m, i, j + 1) - re1 * g0);
-        }
-        if (m.porous) a2 = a2 + dk2 * por_coef<0>(m, m.us, m.vs, 1, i, j);   // :413-419
-        b = m.x1[IDX(i, j)];
-    } else if (COMP == 1 && STEP == 1) {
-        const double rkj = dk2 * F(m.djv, i, j);
-        const double cj = y_cj1(m, i, j);
-        const double an0 = F(m.ran, i, j), anm = F(m.ran, i - 1, j);
-        const double cpj = m.porous ? dk2 * por_coef<1>(m, m.us, m.vs, 1, i, j) : 0.0;   // x + 0.0 == x
-        if (cj >= 0.0) {
-            a1 = rkj * (-y_cj1(m, i - 1, j) - re1 * anm);
-            a2 = rkj * (cj + re1 * (an0 + anm)) + cpj + 1.0;
-            a3 = rkj * (-re1 * an0);
-        } else {
-            a1 = rkj * (-re1 * anm);
-            a2 = rkj * (-cj + re1 * (an0 + anm)) + cpj + 1.0;
-            a3 = rkj * (y_cj1(m, i + 1, j) - re1 * an0);
-        }
-        const double buoy = m.dk * (F(m.d, i, j + 1) + F(m.d, i, j) + F(m.dn, i, j + 1) + F(m.dn, i, j)) / (4.0 * m.fr);
-        const double cnvs = y_conv(m, m.us, m.vs, i, j), cnvn = y_conv(m, m.un, m.vn, i, j);
-        const double difs = y_diff(m, m.vs, i, j), difn = y_diff(m, m.vn, i, j);
-        b = F(m.vn, i, j) - F(m.vs, i, j) + rkj * (-cnvs - cnvn) + rkj * re1 * (difs + difn);
-        if (m.porous)     // :705-708
-            b = b - dk2 * (por_coef<1>(m, m.us, m.vs, 0, i, j) * F(m.vs, i, j) + por_coef<1>(m, m.un, m.vn, 0, i, j) * F(m.vn, i, j));
-        b = b - buoy;
-    } else {
-        if (m.ymask[IDX(i, j)]) { a1 = 0.0; a2 = 1.0; a3 = 0.0; b = 0.0; return; }
-        const double rkj = dk2 * F(m.djv, i, j);
-        const double cj = y_cj2(m, i, j);
-        const double g0 = F(m.rgc, i, j), gp = F(m.rgc, i, j + 1);
-        const double cpj = m.porous ? dk2 * por_coef<1>(m, m.us, m.vs, 1, i, j) : 0.0;
-        if (cj >= 0.0) {
-            a1 = rkj * (-y_cj2(m, i, j - 1) - re1 * g0);
-            a2 = rkj * (cj + re1 * (gp + g0)) + cpj + 1.0;
-            a3 = rkj * (-re1 * gp);
-        } else {
-            a1 = rkj * (-re1 * g0);
-            a2 = rkj * (-cj + re1 * (gp + g0)) + cpj + 1.0;
-            a3 = rkj * (y_cj2(m, i, j + 1) - re1 * gp);
-        }
-        b = m.x1[IDX(i, j)];
-    }
+namespace mom_po { constexpr bool kPorous = true;
+#include "w2_mom_rows.inc"
 }
 
 // chain index e (0-based, reference ordering momentum.f:353 / :677) -> grid point
@@ -269,7 +55,7 @@ __device__ __forceinline__ void chain_ij(const MomArgs &m, long long e, int &i, 
 #define MR_PAD(x) ((x) + ((x) >> 3))
 #define MR_LEN (TRI_S + TRI_S / 8)
 
-template <int COMP, int STEP>
+template <int COMP, int STEP, bool POR>
 __global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
@@ -294,12 +80,14 @@ __global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long lo
         if (e < n) {
             int i, j;
             chain_ij<COMP>(m, e, i, j);
-            mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
+            if (POR) mom_po::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
+            else mom_np::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
             if (e == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
                 a1 = 0.0;
                 int i2, j2; double b1, b2, b3, bb;
                 chain_ij<COMP>(m, 1, i2, j2);
-                mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+                if (POR) mom_po::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+                else mom_np::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
                 a3 = a3 * a2 / b2;
             }
             if (e == n - 1) a3 = 0.0;
@@ -516,18 +304,26 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xcp = pm + 4 * c->nelem; m.ycp = pm + 5 * c->nelem;
 }
 
+template <int COMP, int STEP, bool POR>
+static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out);
+
 template <int COMP, int STEP>
 static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
+    return c->hreg.has_porous ? mom_solve_impl<COMP, STEP, true>(c, m, n, out) : mom_solve_impl<COMP, STEP, false>(c, m, n, out);
+}
+
+template <int COMP, int STEP, bool POR>
+static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
     static bool attr = false;
     const size_t smem = (size_t)4 * MR_LEN * sizeof(double);
     if (!attr) {
-        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, POR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     W2TriWork &w = c->tri;
     const long long nseg = (n + TRI_S - 1) / TRI_S;
     const int direct = nseg == 1;
-    mom_reduce_kernel<COMP, STEP><<<(unsigned)nseg, TRI_T, smem, c->stream>>>(m, n, out, w.V0, w.W0, w.lv[0].seg, w.ext, nseg, direct);
+    mom_reduce_kernel<COMP, STEP, POR><<<(unsigned)nseg, TRI_T, smem, c->stream>>>(m, n, out, w.V0, w.W0, w.lv[0].seg, w.ext, nseg, direct);
     c->launches[1]++;
     if (!direct) {
         const double *sigma = nullptr;
