@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long lo
     constexpr int L = TRI_M - 2;
     if (t == 0) { s_ext[0] = 0; s_ext[1] = 0; }
 
-    // ---- phase A: assemble rows, coalesced
-#pragma unroll 1
+    // ---- phase A: assemble rows, coalesced (the cheap second-step rows are unrolled for more loads in flight)
+#pragma unroll(STEP == 2 ? 4 : 2)
     for (int q = 0; q < TRI_M; ++q) {
         const int el = t + TRI_T * q;
         const long long e = ebase + el;
