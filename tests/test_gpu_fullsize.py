@@ -70,8 +70,10 @@ def test_altridlu_residual_16M(api):
 
 
 @pytest.mark.parametrize("n", [1024, 4096])
-def test_ghost_fills_idempotent_and_local(api, n):
-    """Wall / inlet / fully-developed-outlet fills applied twice equal once, and touch ghost cells only."""
+def test_ghost_fills_reach_fixed_point_and_are_local(api, n):
+    """Wall / inlet / fully-developed-outlet fills touch ghost cells only and reach a fixed point after two
+    applications (the first is not idempotent at corners: the E face reads u(iE,jS) before the S face
+    rewrites it, exactly as in bound_cond.f:657-735)."""
     from wolfd2_b200 import deck as dk
     d = dk.channel(n, re=100.0, dt=1e-5, fully_dev=True)
     api.config(d.mnx, d.mny)
@@ -86,7 +88,11 @@ def test_ghost_fills_idempotent_and_local(api, n):
     u2, v2, p2 = u1.copy(), v1.copy(), p1.copy()
     api.VelBoundCond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nMomBdTp, r.dBCVal, u2, v2)
     api.PresBoundCond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.dBCVal, p2)
-    assert np.array_equal(u1, u2) and np.array_equal(v1, v2) and np.array_equal(p1, p2)
+    u3, v3, p3 = u2.copy(), v2.copy(), p2.copy()
+    api.VelBoundCond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nMomBdTp, r.dBCVal, u3, v3)
+    api.PresBoundCond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.dBCVal, p3)
+    assert np.array_equal(u3, u2) and np.array_equal(v3, v2) and np.array_equal(p3, p2)
+    assert np.array_equal(p1, p2)                      # pressure fills never read what they write
     I = (slice(3, d.ny - 1), slice(3, d.nx - 1))
     assert np.array_equal(u1[I], u[I]) and np.array_equal(v1[I], v[I]) and np.array_equal(p1[I], p[I])
 
