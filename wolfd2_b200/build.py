@@ -44,5 +44,21 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_BIN = os.path.join(HERE, "host", "wolfd2_host")
+
+
+def build_host():
+    """The compiled host driver (g++, links the in-tree library; no CUDA headers needed)."""
+    src = os.path.join(HERE, "host", "wolfd2_host.cpp")
+    if os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return HOST_BIN
+    cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_BIN, src, "-L" + HERE, "-lwolfd2_b200", "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed for the host driver")
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
