@@ -186,6 +186,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     for (int k = 0; k < 30; ++k) cudaFree(mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) cudaFree(c->fld[k]);
     cudaFree(c->dus); cudaFree(c->dvs); cudaFree(c->div); cudaFree(c->qh); cudaFree(c->pmask); cudaFree(c->xmask); cudaFree(c->ymask); cudaFree(c->pormap);
+    for (int k = 0; k < 4; ++k) cudaFree(c->sorf_buf[k]);
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
     w2_tri_release(c);
     cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);

@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256) div_rhs_kernel(int nx, int ny, int pitch,
         if (masked) d = 0.0;
         if (div_out) div_out[IDX(i, j)] = d;
         // the fused SOR kernel recognises identity rows by a NaN in b (it then uses b = 0, a = identity)
-        b[IDX(i, j)] = (masked && sentinel) ? __longlong_as_double(0x7ff8000000000000LL) : d / dk;
+        // (sentinel mode also means: b is consumed by the fused kernel, which wants colour-split rows)
+        const size_t bo = sentinel ? (size_t)pitch * j + (size_t)(i & 1) * (pitch >> 1) + (i >> 1) : IDX(i, j);
+        b[bo] = (masked && sentinel) ? __longlong_as_double(0x7ff8000000000000LL) : d / dk;
     }
 }
 

@@ -25,8 +25,10 @@
 #include "w2.cuh"
 
 #define SF_W 256              // strip width held in shared memory (cells)
-#define SF_PADL 2             // left pad (keeps TMA destinations 16-byte aligned)
-#define SF_STRIDE (SF_W + 4)  // shared row stride in doubles
+#define SF_HALF (SF_W / 2)    // cells of one colour parity per strip row
+#define SF_PADL 2             // pad cells on each side of a half row (keeps TMA destinations 16-byte aligned)
+#define SF_HSTR (SF_HALF + 2 * SF_PADL)   // one half row in shared memory
+#define SF_STRIDE (2 * SF_HSTR)           // shared row stride in doubles: [even-i half | odd-i half]
 
 struct SorFCtl {           // device-resident loop control
     int done;              // 1: solve finished, later launches return at once
@@ -45,6 +47,10 @@ struct SorFArgs {
     int nstrips, nbands, rows_per_band, own_w;
     int msorit;
     double sorrel, sortol;
+    // all five arrays are in the COLOUR-SPLIT device layout: row j = [cells with even i | cells with odd i],
+    // each half pitch/2 doubles long (see sorf_pack_kernel).  Every cell relaxed in one half-sweep of a row
+    // has the same i-parity, so in this layout a warp's shared-memory accesses are unit-stride and free of
+    // the 2-way bank conflicts an interleaved row causes (ncu r01: 45 -> 24 wavefronts per warp-update).
     const double *rau, *rgv, *b;
     double *pA, *pB;
     SorFCtl *ctl;
@@ -127,22 +133,28 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the pad cells once (read by edge threads, never used by owned cells)
-    for (int k = tid; k < R * 4; k += blockDim.x) {
-        const int row = k >> 2, q = k & 3;
-        const int off = row * SF_STRIDE + (q < 2 ? q : SF_W + q);
+    for (int k = tid; k < R * 8; k += blockDim.x) {
+        const int row = k >> 3, q = k & 7;   // pads: 0,1 | 130,131 | 132,133 | 262,263
+        const int off = row * SF_STRIDE + (q >> 2) * SF_HSTR + ((q & 3) < 2 ? (q & 3) : SF_HALF + (q & 3));
         sP[off] = 0.0; sB[off] = 0.0; sU[off] = 0.0; sV[off] = 0.0;
     }
     __syncthreads();
 
     // ---- producer state (thread 0): next row to request and its ring slot
     int ld_row = jL0, ld_off = 0, ld_slot = 0;
-    size_t ld_g = (size_t)pitch * jL0 + i0;
-    auto issue_row = [&]() {   // 4 bulk copies of 2 KB into the next ring slot
+    const int hp = pitch >> 1;                       // half pitch: start of the odd-i half of a row
+    size_t ld_g = (size_t)pitch * jL0 + (i0 >> 1);  // even-i half; i0 is a multiple of 4 (16-byte aligned)
+    auto issue_row = [&]() {   // 8 bulk copies of 1 KB (even / odd half of 4 arrays) into the next ring slot
         mbar_expect_tx(&bars[ld_slot], 4u * SF_W * 8u);
-        tma_load_1d(sP + ld_off + SF_PADL, psrc + ld_g, SF_W * 8, &bars[ld_slot]);
-        tma_load_1d(sB + ld_off + SF_PADL, a.b + ld_g, SF_W * 8, &bars[ld_slot]);
-        tma_load_1d(sU + ld_off + SF_PADL, a.rau + ld_g, SF_W * 8, &bars[ld_slot]);
-        tma_load_1d(sV + ld_off + SF_PADL, a.rgv + ld_g, SF_W * 8, &bars[ld_slot]);
+        const int oe = ld_off + SF_PADL, oo = ld_off + SF_HSTR + SF_PADL;
+        tma_load_1d(sP + oe, psrc + ld_g, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sP + oo, psrc + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sB + oe, a.b + ld_g, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sB + oo, a.b + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sU + oe, a.rau + ld_g, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sU + oo, a.rau + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sV + oe, a.rgv + ld_g, SF_HALF * 8, &bars[ld_slot]);
+        tma_load_1d(sV + oo, a.rgv + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
         ++ld_row; ld_g += pitch;
         ld_off += SF_STRIDE; ++ld_slot;
         if (ld_slot == R) { ld_slot = 0; ld_off = 0; }
@@ -152,14 +164,15 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
 
     // ---- consumer state
     const int stage = (tid >> 7) + 1;         // 1..NS, 128 threads (4 warps) per stage
-    const int k2 = 2 * (tid & 127);           // even column of this thread's pair (strip-local)
+    const int kk = tid & 127;                 // this thread's pair of columns (strip-local 2kk, 2kk+1)
+    const int k2 = 2 * kk;
     const int colour = (stage - 1) & 1;       // 0 = black (i+j even), 1 = red; i0 is even
     const bool stage_on = stage <= 2 * Tp;
     const int ig = i0 + k2;
     const bool val0 = ig >= 2 && ig <= nx, val1 = ig + 1 >= 2 && ig + 1 <= nx;
     const bool own0 = ig >= own_lo && ig <= own_hi, own1 = ig + 1 >= own_lo && ig + 1 <= own_hi;
     const int qlo = max(2, jL0 + 1), qhi = min(ny, jL1 - 1);
-    const int base = SF_PADL + k2;
+    const int base = SF_PADL + kk;            // index of the pair inside a half row
     const double sorrel = a.sorrel;
     double lmax = 0.0;
 
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     int par = (colour + q) & 1;               // column parity of the active cell in row q
     int w_slot = 0;
     unsigned w_par = 0;
-    double *gst = pdst + (size_t)pitch * q + ig;   // store address of (ig, q)
+    double *gst = pdst + (size_t)pitch * q + (ig >> 1);   // store address of (ig, q); (ig+1, q) is hp further
     const int r_end = jB + 4 * T - 1;
 #pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
@@ -178,16 +191,20 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
             if (++w_slot == R) { w_slot = 0; w_par ^= 1u; }
         }
         if (stage_on && q >= qlo && q <= qhi && (par ? val1 : val0)) {
-            const int iq = off_q + base + par, is = off_s + base + par, in = off_n + base + par;
+            // active cell: half `par`, pair kk.  Its west / east neighbours live in the other half:
+            // par = 0 (i = i0+2kk):   west = odd[kk-1], east = odd[kk];  par = 1: west = even[kk], east = even[kk+1]
+            const int ha = par * SF_HSTR + base;
+            const int hw = (par ? base : SF_HSTR + base - 1);
+            const int iq = off_q + ha, is = off_s + ha, in = off_n + ha, iw = off_q + hw;
             const double bb = sB[iq];
             const double pc = sP[iq];
             double sum;
             if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
                 sum = 0.0 - pc;
             } else {
-                const double a1 = sV[is], a2 = sU[iq - 1], a4 = sU[iq], a5 = sV[iq];
+                const double a1 = sV[is], a2 = sU[iw], a4 = sU[iq], a5 = sV[iq];
                 const double a3 = -a4 - a2 - a5 - a1;
-                sum = bb - a1 * sP[is] - a2 * sP[iq - 1] - a4 * sP[iq + 1] - a5 * sP[in];
+                sum = bb - a1 * sP[is] - a2 * sP[iw] - a4 * sP[iw + 1] - a5 * sP[in];
                 sum = w2_div_exact(sum, a3) - pc;
             }
             sP[iq] = pc + sorrel * sum;
@@ -196,10 +213,8 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
         __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
         if (stage == NS && q >= jA && q <= jB) {
-            const double2 v = *reinterpret_cast<const double2 *>(&sP[off_q + base]);
-            if (own0 && own1) *reinterpret_cast<double2 *>(gst) = v;
-            else if (own0) gst[0] = v.x;
-            else if (own1) gst[1] = v.y;
+            if (own0) gst[0] = sP[off_q + base];
+            if (own1) gst[hp] = sP[off_q + SF_HSTR + base];
         }
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
         if (tid == 0 && ld_row <= jL1) issue_row();
@@ -250,6 +265,31 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     }
 }
 
+// interleaved (reference order, i fastest) <-> colour-split rows.  TO_SPLIT: dst[j][ (i&1)*hp + i/2 ] = src[j][i]
+template <bool TO_SPLIT>
+__global__ void __launch_bounds__(256) sorf_pack_kernel(int pitch, int rows, const double *__restrict__ src,
+                                                        double *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pitch) return;
+    const int hp = pitch >> 1;
+    const int s = (i & 1) * hp + (i >> 1);
+    for (int j = blockIdx.y; j < rows; j += gridDim.y) {
+        const size_t r = (size_t)pitch * j;
+        if (TO_SPLIT) dst[r + s] = src[r + i];
+        else dst[r + i] = src[r + s];
+    }
+}
+
+int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
+    const int rows = c->rows + 1;
+    dim3 grid((c->pitch + 255) / 256, rows < 2048 ? rows : 2048);
+    if (to_split) sorf_pack_kernel<true><<<grid, 256, 0, c->stream>>>(c->pitch, rows, src, dst);
+    else sorf_pack_kernel<false><<<grid, 256, 0, c->stream>>>(c->pitch, rows, src, dst);
+    c->launches[2]++;
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+
 // ---------------------------------------------------------------------------------------- host
 static bool g_attr_set[3] = {false, false, false};
 
@@ -264,11 +304,22 @@ static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     return W2_OK;
 }
 
-// Runs the whole SOR loop of SorRB on p (Cartesian grids).  b must already hold div/dk with the NaN
-// sentinel at identity rows.  scratch is a second full-size buffer.  On return *p_final points at the
-// buffer holding the solution (p or scratch) -- the caller swaps its pointers accordingly.
+// Runs the whole SOR loop of SorRB on p (Cartesian grids).  b (W2_F_B) must already hold div/dk in the
+// colour-split layout with the NaN sentinel at identity rows.  p is packed into the split layout, iterated
+// between two split buffers, and unpacked at the end; rau and rgv are re-packed on every call (0.1 ms at
+// 4096^2) so that shims which re-upload metrics need no invalidation logic.
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done) {
+    for (int k = 0; k < 4; ++k)
+        if (!c->sorf_buf[k]) {
+            W2_CUDA(cudaMalloc((void **)&c->sorf_buf[k], c->nelem * sizeof(double)));
+            W2_CUDA(cudaMemsetAsync(c->sorf_buf[k], 0, c->nelem * sizeof(double), c->stream));
+        }
+    double *pA = c->sorf_buf[0], *pB = c->sorf_buf[1], *rauS = c->sorf_buf[2], *rgvS = c->sorf_buf[3];
+    (void)scratch;
+    W2_TRY(w2_sorf_pack(c, p, pA, true));
+    W2_TRY(w2_sorf_pack(c, c->met.rau, rauS, true));
+    W2_TRY(w2_sorf_pack(c, c->met.rgv, rgvS, true));
     const wolfd2_params &par = c->par;
     const int nx = c->nx, ny = c->ny;
     SorFCtl *ctl = (SorFCtl *)c->d_flags;
@@ -297,13 +348,13 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
     a.nbands = (ny - 1 + a.rows_per_band - 1) / a.rows_per_band;
     a.msorit = par.msorit; a.sorrel = par.sorrel; a.sortol = par.sortol;
-    a.rau = c->met.rau; a.rgv = c->met.rgv; a.b = c->fld[W2_F_B];
-    a.pA = p; a.pB = scratch; a.ctl = ctl;
+    a.rau = rauS; a.rgv = rgvS; a.b = c->fld[W2_F_B];
+    a.pA = pA; a.pB = pB; a.ctl = ctl;
     dim3 grid(a.nstrips, a.nbands);
 
     // the ghost ring of p is frozen during the solve (:431-446 never touches it): give the second
     // buffer the same ghosts
-    W2_CUDA(cudaMemcpyAsync(scratch, p, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    W2_CUDA(cudaMemcpyAsync(pB, pA, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     sorf_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
     const int passes_total = (par.msorit + T - 1) / T + 1;
     const double cells = (double)(nx - 1) * (double)(ny - 1);
@@ -338,6 +389,7 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     if (converged) *converged = h.nconv > 0;
     if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : par.msorit;
     if (iters_done) *iters_done = h.m;
-    *p_final = h.cur ? scratch : p;
+    W2_TRY(w2_sorf_pack(c, h.cur ? pB : pA, p, false));   // back to the reference order
+    *p_final = p;
     return W2_OK;
 }
