@@ -78,6 +78,26 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  : "memory");
 }
 
+// explicit shared-space accesses with 32-bit addresses: keeps the per-update instruction stream free of the
+// generic->shared window arithmetic (S2R SR_CgaCtaId / LEA) the compiler otherwise re-emits per access
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar_addr, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+
 __global__ void sorf_ctl_reset(SorFCtl *c) {
     c->done = 0; c->m = 0; c->nconv = 0; c->ticket = 0; c->cur = 0; c->redo = 0;
     for (int k = 0; k < 8; ++k) c->slot[k] = 0ull;
@@ -162,66 +182,76 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     if (tid == 0)
         for (int n = 0; n <= D && ld_row <= jL1; ++n) issue_row();
 
-    // ---- consumer state
+    // ---- consumer state (all shared-memory addresses are 32-bit byte addresses)
     const int stage = (tid >> 7) + 1;         // 1..NS, 128 threads (4 warps) per stage
     const int kk = tid & 127;                 // this thread's pair of columns (strip-local 2kk, 2kk+1)
-    const int k2 = 2 * kk;
     const int colour = (stage - 1) & 1;       // 0 = black (i+j even), 1 = red; i0 is even
-    const bool stage_on = stage <= 2 * Tp;
-    const int ig = i0 + k2;
-    const bool val0 = ig >= 2 && ig <= nx, val1 = ig + 1 >= 2 && ig + 1 <= nx;
-    const bool own0 = ig >= own_lo && ig <= own_hi, own1 = ig + 1 >= own_lo && ig + 1 <= own_hi;
-    const int qlo = max(2, jL0 + 1), qhi = min(ny, jL1 - 1);
-    const int base = SF_PADL + kk;            // index of the pair inside a half row
+    const int ig = i0 + 2 * kk;
+    // bit 0 / bit 1: the even / odd column of the pair is an unknown (2..nx) resp. owned by this CTA
+    const unsigned vmask = (unsigned)(ig >= 2 && ig <= nx) | ((unsigned)(ig + 1 >= 2 && ig + 1 <= nx) << 1);
+    const unsigned omask = (unsigned)(ig >= own_lo && ig <= own_hi) | ((unsigned)(ig + 1 >= own_lo && ig + 1 <= own_hi) << 1);
+    // rows this stage may relax: q in [qlo, qlo+qspan] (empty when the stage is switched off for this pass)
+    const int qlo = max(2, jL0 + 1);
+    const unsigned qspan = (stage <= 2 * Tp) ? (unsigned)(min(ny, jL1 - 1) - qlo) : 0u;
+    const bool any_row = (stage <= 2 * Tp) && (min(ny, jL1 - 1) >= qlo);
+    const unsigned jspan = (unsigned)(jB - jA);
     const double sorrel = a.sorrel;
     double lmax = 0.0;
 
+    constexpr unsigned ROWB = SF_STRIDE * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8;
+    const unsigned sbase = smem_u32(smem_raw);
+    const unsigned aP = sbase, aB = sbase + RINGB, aU = sbase + 2 * RINGB, aV = sbase + 3 * RINGB, aBar = sbase + 4 * RINGB;
+    const unsigned base8 = (SF_PADL + kk) * 8;
+
     int q = jL0 - 2 * stage + 1;              // row relaxed by this stage at time step r = jL0
-    auto ring_off = [&](int row) { int m = (row - jL0) % R; if (m < 0) m += R; return m * SF_STRIDE; };
-    int off_s = ring_off(q - 1), off_q = ring_off(q), off_n = ring_off(q + 1);
-    int par = (colour + q) & 1;               // column parity of the active cell in row q
-    int w_slot = 0;
-    unsigned w_par = 0;
+    auto ring_off = [&](int row) { int m = (row - jL0) % R; if (m < 0) m += R; return (unsigned)m * ROWB; };
+    unsigned off_s = ring_off(q - 1), off_q = ring_off(q), off_n = ring_off(q + 1);
+    unsigned par = (unsigned)(colour + q) & 1u;   // column parity of the active cell in row q
+    // active cell: half `par`, pair kk; west neighbour: par=0 -> odd[kk-1], par=1 -> even[kk]; east = west + 1
+    unsigned ha8 = base8 + par * HSTRB;
+    unsigned hw8 = par ? base8 : base8 + HSTRB - 8;
+    const unsigned HA_SUM = 2 * base8 + HSTRB, HW_SUM = 2 * base8 + HSTRB - 8;
+    unsigned w_bar = aBar, w_par = 0;
     double *gst = pdst + (size_t)pitch * q + (ig >> 1);   // store address of (ig, q); (ig+1, q) is hp further
+    const bool last_stage = stage == NS;
     const int r_end = jB + 4 * T - 1;
 #pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
         if (r <= jL1) {
-            mbar_wait(&bars[w_slot], w_par);
-            if (++w_slot == R) { w_slot = 0; w_par ^= 1u; }
+            mbar_wait_a(w_bar, w_par);
+            w_bar += 8;
+            if (w_bar == aBar + 8 * R) { w_bar = aBar; w_par ^= 1u; }
         }
-        if (stage_on && q >= qlo && q <= qhi && (par ? val1 : val0)) {
-            // active cell: half `par`, pair kk.  Its west / east neighbours live in the other half:
-            // par = 0 (i = i0+2kk):   west = odd[kk-1], east = odd[kk];  par = 1: west = even[kk], east = even[kk+1]
-            const int ha = par * SF_HSTR + base;
-            const int hw = (par ? base : SF_HSTR + base - 1);
-            const int iq = off_q + ha, is = off_s + ha, in = off_n + ha, iw = off_q + hw;
-            const double bb = sB[iq];
-            const double pc = sP[iq];
+        if (any_row && (unsigned)(q - qlo) <= qspan && ((vmask >> par) & 1u)) {
+            const unsigned iq = off_q + ha8, is = off_s + ha8, in = off_n + ha8, iw = off_q + hw8;
+            const double bb = lds_f64(aB + iq);
+            const double pc = lds_f64(aP + iq);
             double sum;
             if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
                 sum = 0.0 - pc;
             } else {
-                const double a1 = sV[is], a2 = sU[iw], a4 = sU[iq], a5 = sV[iq];
+                const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
+                const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
                 const double a3 = -a4 - a2 - a5 - a1;
-                sum = bb - a1 * sP[is] - a2 * sP[iw] - a4 * sP[iw + 1] - a5 * sP[in];
+                sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
                 sum = w2_div_exact(sum, a3) - pc;
             }
-            sP[iq] = pc + sorrel * sum;
-            if ((par ? own1 : own0) && q >= jA && q <= jB) lmax = fmax(lmax, fabs(sum));
+            sts_f64(aP + iq, pc + sorrel * sum);
+            if (((omask >> par) & 1u) && (unsigned)(q - jA) <= jspan) lmax = fmax(lmax, fabs(sum));
         }
         __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
-        if (stage == NS && q >= jA && q <= jB) {
-            if (own0) gst[0] = sP[off_q + base];
-            if (own1) gst[hp] = sP[off_q + SF_HSTR + base];
+        if (last_stage && (unsigned)(q - jA) <= jspan) {
+            if (omask & 1u) gst[0] = lds_f64(aP + off_q + base8);
+            if (omask & 2u) gst[hp] = lds_f64(aP + off_q + HSTRB + base8);
         }
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
         if (tid == 0 && ld_row <= jL1) issue_row();
         off_s = off_q; off_q = off_n;
-        off_n += SF_STRIDE;
-        if (off_n == RS) off_n = 0;
-        par ^= 1;
+        off_n += ROWB;
+        if (off_n == RINGB) off_n = 0;
+        ha8 = HA_SUM - ha8; hw8 = HW_SUM - hw8;
+        par ^= 1u;
         ++q;
         gst += pitch;
     }
