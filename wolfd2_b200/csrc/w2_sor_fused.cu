@@ -26,6 +26,8 @@
 
 #define SF_W 256              // strip width held in shared memory (cells)
 #define SF_HALF (SF_W / 2)    // cells of one colour parity per strip row
+#define SF_CPT 1              // column pairs per thread (threads per stage = SF_HALF / SF_CPT)
+#define SF_TPS (SF_HALF / SF_CPT)
 #define SF_PADL 2             // pad cells on each side of a half row (keeps TMA destinations 16-byte aligned)
 #define SF_HSTR (SF_HALF + 2 * SF_PADL)   // one half row in shared memory
 #define SF_STRIDE (2 * SF_HSTR)           // shared row stride in doubles: [even-i half | odd-i half]
@@ -110,7 +112,7 @@ template <int T> struct SorFCfg {
 };
 
 template <int T>
-__global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel(SorFArgs a) {
+__global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused_kernel(SorFArgs a) {
     constexpr int NS = 2 * T;                 // half-sweep stages
     constexpr int R = SorFCfg<T>::R;
     constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
@@ -160,36 +162,41 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     }
     __syncthreads();
 
-    // ---- producer state (thread 0): next row to request and its ring slot
-    int ld_row = jL0, ld_off = 0, ld_slot = 0;
+    // ---- producer state (lanes 0..7 of warp 0, one bulk copy each): next row to request and its ring slot
     const int hp = pitch >> 1;                       // half pitch: start of the odd-i half of a row
-    size_t ld_g = (size_t)pitch * jL0 + (i0 >> 1);  // even-i half; i0 is a multiple of 4 (16-byte aligned)
-    auto issue_row = [&]() {   // 8 bulk copies of 1 KB (even / odd half of 4 arrays) into the next ring slot
-        mbar_expect_tx(&bars[ld_slot], 4u * SF_W * 8u);
-        const int oe = ld_off + SF_PADL, oo = ld_off + SF_HSTR + SF_PADL;
-        tma_load_1d(sP + oe, psrc + ld_g, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sP + oo, psrc + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sB + oe, a.b + ld_g, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sB + oo, a.b + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sU + oe, a.rau + ld_g, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sU + oo, a.rau + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sV + oe, a.rgv + ld_g, SF_HALF * 8, &bars[ld_slot]);
-        tma_load_1d(sV + oo, a.rgv + ld_g + hp, SF_HALF * 8, &bars[ld_slot]);
-        ++ld_row; ld_g += pitch;
+    int ld_row = jL0, ld_slot = 0;
+    unsigned ld_off = 0;
+    // lane l copies array (l>>1) in {p, b, rau, rgv}, half (l&1) in {even i, odd i}; 1 KB each
+    const double *ld_src = nullptr;
+    double *ld_dst = nullptr;
+    if (tid < 8) {
+        const int arr = tid >> 1, half = tid & 1;
+        const double *g = arr == 0 ? psrc : arr == 1 ? a.b : arr == 2 ? a.rau : a.rgv;
+        ld_src = g + (size_t)pitch * jL0 + (i0 >> 1) + (half ? hp : 0);   // i0 is a multiple of 4: 16-byte aligned
+        ld_dst = sP + arr * RS + half * SF_HSTR + SF_PADL;
+    }
+    auto issue_row = [&]() {   // executed by lanes 0..7 together
+        if (tid == 0) mbar_expect_tx(&bars[ld_slot], 4u * SF_W * 8u);
+        tma_load_1d(ld_dst + ld_off, ld_src, SF_HALF * 8, &bars[ld_slot]);
+        ++ld_row; ld_src += pitch;
         ld_off += SF_STRIDE; ++ld_slot;
         if (ld_slot == R) { ld_slot = 0; ld_off = 0; }
     };
-    if (tid == 0)
+    if (tid < 8)
         for (int n = 0; n <= D && ld_row <= jL1; ++n) issue_row();
 
     // ---- consumer state (all shared-memory addresses are 32-bit byte addresses)
-    const int stage = (tid >> 7) + 1;         // 1..NS, 128 threads (4 warps) per stage
-    const int kk = tid & 127;                 // this thread's pair of columns (strip-local 2kk, 2kk+1)
+    const int stage = tid / SF_TPS + 1;       // 1..NS, SF_TPS threads per stage
+    const int kk0 = tid % SF_TPS;             // this thread's column pairs: kk0 + u*SF_TPS, u = 0..SF_CPT-1
     const int colour = (stage - 1) & 1;       // 0 = black (i+j even), 1 = red; i0 is even
-    const int ig = i0 + 2 * kk;
-    // bit 0 / bit 1: the even / odd column of the pair is an unknown (2..nx) resp. owned by this CTA
-    const unsigned vmask = (unsigned)(ig >= 2 && ig <= nx) | ((unsigned)(ig + 1 >= 2 && ig + 1 <= nx) << 1);
-    const unsigned omask = (unsigned)(ig >= own_lo && ig <= own_hi) | ((unsigned)(ig + 1 >= own_lo && ig + 1 <= own_hi) << 1);
+    // per pair u, bits 2u / 2u+1: the even / odd column is an unknown (2..nx) resp. owned by this CTA
+    unsigned vmask = 0, omask = 0;
+#pragma unroll
+    for (int u = 0; u < SF_CPT; ++u) {
+        const int ig = i0 + 2 * (kk0 + u * SF_TPS);
+        vmask |= ((unsigned)(ig >= 2 && ig <= nx) | ((unsigned)(ig + 1 >= 2 && ig + 1 <= nx) << 1)) << (2 * u);
+        omask |= ((unsigned)(ig >= own_lo && ig <= own_hi) | ((unsigned)(ig + 1 >= own_lo && ig + 1 <= own_hi) << 1)) << (2 * u);
+    }
     // rows this stage may relax: q in [qlo, qlo+qspan] (empty when the stage is switched off for this pass)
     const int qlo = max(2, jL0 + 1);
     const unsigned qspan = (stage <= 2 * Tp) ? (unsigned)(min(ny, jL1 - 1) - qlo) : 0u;
@@ -198,10 +205,10 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     const double sorrel = a.sorrel;
     double lmax = 0.0;
 
-    constexpr unsigned ROWB = SF_STRIDE * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8;
+    constexpr unsigned ROWB = SF_STRIDE * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8, PAIRB = SF_TPS * 8;
     const unsigned sbase = smem_u32(smem_raw);
     const unsigned aP = sbase, aB = sbase + RINGB, aU = sbase + 2 * RINGB, aV = sbase + 3 * RINGB, aBar = sbase + 4 * RINGB;
-    const unsigned base8 = (SF_PADL + kk) * 8;
+    const unsigned base8 = (SF_PADL + kk0) * 8;
 
     int q = jL0 - 2 * stage + 1;              // row relaxed by this stage at time step r = jL0
     auto ring_off = [&](int row) { int m = (row - jL0) % R; if (m < 0) m += R; return (unsigned)m * ROWB; };
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
     unsigned hw8 = par ? base8 : base8 + HSTRB - 8;
     const unsigned HA_SUM = 2 * base8 + HSTRB, HW_SUM = 2 * base8 + HSTRB - 8;
     unsigned w_bar = aBar, w_par = 0;
-    double *gst = pdst + (size_t)pitch * q + (ig >> 1);   // store address of (ig, q); (ig+1, q) is hp further
+    double *gst = pdst + (size_t)pitch * q + (i0 >> 1) + kk0;   // store address of pair kk0's even cell in row q
     const bool last_stage = stage == NS;
     const int r_end = jB + 4 * T - 1;
 #pragma unroll 1
@@ -222,31 +229,40 @@ __global__ void __launch_bounds__(T * 256, (T == 1) ? 3 : 2) sor_rb_fused_kernel
             w_bar += 8;
             if (w_bar == aBar + 8 * R) { w_bar = aBar; w_par ^= 1u; }
         }
-        if (any_row && (unsigned)(q - qlo) <= qspan && ((vmask >> par) & 1u)) {
-            const unsigned iq = off_q + ha8, is = off_s + ha8, in = off_n + ha8, iw = off_q + hw8;
-            const double bb = lds_f64(aB + iq);
-            const double pc = lds_f64(aP + iq);
-            double sum;
-            if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
-                sum = 0.0 - pc;
-            } else {
-                const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
-                const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
-                const double a3 = -a4 - a2 - a5 - a1;
-                sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
-                sum = w2_div_exact(sum, a3) - pc;
+        if (any_row && (unsigned)(q - qlo) <= qspan) {
+            const bool row_owned = (unsigned)(q - jA) <= jspan;
+#pragma unroll
+            for (int u = 0; u < SF_CPT; ++u) {
+                if (!((vmask >> (2 * u + par)) & 1u)) continue;
+                const unsigned iq = off_q + ha8 + u * PAIRB, is = off_s + ha8 + u * PAIRB, in = off_n + ha8 + u * PAIRB,
+                               iw = off_q + hw8 + u * PAIRB;
+                const double bb = lds_f64(aB + iq);
+                const double pc = lds_f64(aP + iq);
+                double sum;
+                if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
+                    sum = 0.0 - pc;
+                } else {
+                    const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
+                    const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
+                    const double a3 = -a4 - a2 - a5 - a1;
+                    sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
+                    sum = w2_div_exact(sum, a3) - pc;
+                }
+                sts_f64(aP + iq, pc + sorrel * sum);
+                if (row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
             }
-            sts_f64(aP + iq, pc + sorrel * sum);
-            if (((omask >> par) & 1u) && (unsigned)(q - jA) <= jspan) lmax = fmax(lmax, fabs(sum));
         }
         __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
         if (last_stage && (unsigned)(q - jA) <= jspan) {
-            if (omask & 1u) gst[0] = lds_f64(aP + off_q + base8);
-            if (omask & 2u) gst[hp] = lds_f64(aP + off_q + HSTRB + base8);
+#pragma unroll
+            for (int u = 0; u < SF_CPT; ++u) {
+                if ((omask >> (2 * u)) & 1u) gst[u * SF_TPS] = lds_f64(aP + off_q + base8 + u * PAIRB);
+                if ((omask >> (2 * u + 1)) & 1u) gst[hp + u * SF_TPS] = lds_f64(aP + off_q + HSTRB + base8 + u * PAIRB);
+            }
         }
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
-        if (tid == 0 && ld_row <= jL1) issue_row();
+        if (tid < 8 && ld_row <= jL1) issue_row();
         off_s = off_q; off_q = off_n;
         off_n += ROWB;
         if (off_n == RINGB) off_n = 0;
@@ -330,7 +346,7 @@ static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_attr_set[T] = true;
     }
-    sor_rb_fused_kernel<T><<<grid, T * 256, smem, c->stream>>>(a);
+    sor_rb_fused_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
     return W2_OK;
 }
 
@@ -365,10 +381,10 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         const size_t smem1 = SorFCfg<1>::smem, smem2 = SorFCfg<2>::smem;
         if (T == 1) {
             cudaFuncSetAttribute(sor_rb_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<1>, 256, smem1);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<1>, 2 * SF_TPS, smem1);
         } else {
             cudaFuncSetAttribute(sor_rb_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<2>, 512, smem2);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<2>, 4 * SF_TPS, smem2);
         }
         if (per_sm < 1) per_sm = 1;
     }
