@@ -86,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)],
+                                          "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -259,11 +259,12 @@ def run_gpu(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing --------------------------------------------------------
-    ctx.step(args.warmup)
-    l0 = ctx.timing()["launches"]
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # samples cover warm-up + timed steps (all under the same load)
+        time.sleep(0.3)
+    ctx.step(args.warmup)
+    l0 = ctx.timing()["launches"]
     barrier()
     logs = ctx.step(args.steps)
     barrier()
