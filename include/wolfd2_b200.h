@@ -157,6 +157,24 @@ int wolfd2_b200_sync(wolfd2_ctx *ctx);
 void *wolfd2_b200_host_alloc(uint64_t bytes);
 void wolfd2_b200_host_free(void *p);
 
+/* ---- (3) several GPUs of one node: row slabs, one process per GPU ------------------
+ * The reference is serial (its only parallel constructs are OpenMP loops inside SorRBP/SlorRBP,
+ * src/pressure.f:599-649); this is the decomposition SURVEY.md section 8(e) derives from it.  The unknown
+ * pressure rows j = 2..ny are cut into `world` contiguous slabs.  Rank r holds every array on rows
+ * A0..A1 (its rows J0..J1 plus HG halo rows, clipped to 0..ny+1); the arrays it passes to create_slab /
+ * upload / download / step_host hold those rows only, host row 0 = global row A0, so mny >= A1-A0.
+ * params and region tables stay global.  Results are bit-identical to the one-GPU run.
+ * Supported: ppe_solver 5/6, Cartesian grid, nx >= 254, no OUTLT2 faces. */
+/* out = {J0, J1, A0, A1, HG} for `rank` of `world` */
+int wolfd2_b200_slab_layout(int32_t nx, int32_t ny, int32_t world, int32_t rank, int32_t out[5]);
+/* NCCL communicator over the ranks: rank 0 makes the 128-byte id, the launcher hands it to every rank
+ * (MPI_Bcast, torch.distributed, a file ...), every rank calls comm_init after wolfd2_b200_set_device. */
+int wolfd2_b200_comm_unique_id(unsigned char id[128]);
+int wolfd2_b200_comm_init(int32_t rank, int32_t world, const unsigned char id[128]);
+int wolfd2_b200_comm_finalize(void);
+int wolfd2_b200_create_slab(wolfd2_ctx **out, const wolfd2_params *par, const wolfd2_regions *reg,
+                            const wolfd2_metrics *met, int32_t rank, int32_t world);
+
 /* ---- (1) literal shims: gfortran ABI of the reference subroutines --------------- */
 
 /* src/momentum.f:33-48  INTEGER function nAuxMomentum(...) */

@@ -49,6 +49,10 @@ def lib():
     L.wolfd2_b200_set_device.argtypes = [C.c_int32]
     L.wolfd2_b200_set_option.argtypes = [C.c_char_p, C.c_int32]
     L.wolfd2_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.POINTER(Regions), C.POINTER(Metrics)]
+    L.wolfd2_b200_create_slab.argtypes = L.wolfd2_b200_create.argtypes + [C.c_int32, C.c_int32]
+    L.wolfd2_b200_slab_layout.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)]
+    L.wolfd2_b200_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
+    L.wolfd2_b200_comm_init.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_ubyte)]
     L.wolfd2_b200_destroy.argtypes = [C.c_void_p]
     L.wolfd2_b200_destroy.restype = None
     L.wolfd2_b200_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
@@ -120,8 +124,13 @@ class Context:
         config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
         self._par, self._reg, self._met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
         h = C.c_void_p()
-        _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
-               "wolfd2_b200_create")
+        if getattr(deck, "slab", None):   # one rank of a multi-GPU run: this deck holds rows A0..A1 only
+            rank, world = deck.slab[0], deck.slab[1]
+            _check(L.wolfd2_b200_create_slab(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met),
+                                             rank, world), "wolfd2_b200_create_slab")
+        else:
+            _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
+                   "wolfd2_b200_create")
         self._h = h
 
     def close(self):
@@ -185,6 +194,17 @@ class Context:
 
     def sync(self):
         _check(lib().wolfd2_b200_sync(self._h), "sync")
+
+
+def slab_layout(nx, ny, world, rank):
+    """(J0, J1, A0, A1, HG) as the library computes it (wolfd2_b200_slab_layout)."""
+    out = (C.c_int32 * 5)()
+    _check(lib().wolfd2_b200_slab_layout(nx, ny, world, rank, out), "wolfd2_b200_slab_layout")
+    return tuple(out)
+
+
+def comm_finalize():
+    lib().wolfd2_b200_comm_finalize()
 
 
 def pinned_field(deck):

@@ -13,7 +13,7 @@ NVCC_FLAGS = [
     # parity build: no FMA contraction, so stencil results are bit-identical to a non-FMA CPU
     # build of the reference (gfortran -O2 on baseline x86-64 emits no FMA); IEEE div/sqrt.
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl",
 ]
 
 

@@ -14,11 +14,15 @@
 #define V(i, j) v[IDX(i, j)]
 #define P(i, j) p[IDX(i, j)]
 #define PFOR(var, lo, hi) for (int var = (lo) + (int)threadIdx.x; var <= (hi); var += BC_THREADS)
+// row loops are clipped to the rows [jlo, jhi] this rank holds (all rows on one GPU); a south / north face
+// is applied only where both rows it touches are held (w2_dist.cu: the outermost halo row is spare)
+#define PFORJ(var, lo, hi) for (int var = max((lo), jlo) + (int)threadIdx.x; var <= min((hi), jhi); var += BC_THREADS)
+#define ROWS_HELD(a, b) ((a) >= jlo && (b) <= jhi)
 #define SEQ if (threadIdx.x == 0)
 
 template <bool kOutflowOnly>
 __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__restrict__ R, int pitch,
-                                                            double *u, double *v) {
+                                                            int jlo, int jhi, double *u, double *v) {
     const double dZero = 0.0, dTwo = 2.0, dThree = 3.0, dFour = 4.0, dFive = 5.0, dEight = 8.0;
     const int nreg = R->nreg;
     for (int q = 0; q < nreg; ++q) {
@@ -28,26 +32,26 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
             const int bt = R->bd[q][W2_WEST - 1];
             const double valU = R->val[q][W2_WEST - 1][W2_U - 1], valV = R->val[q][W2_WEST - 1][W2_V - 1];
             if (!kOutflowOnly && bt == W2_BM_WALL1) {
-                PFOR(j, jS, jN) U(iW, j) = dZero;
+                PFORJ(j, jS, jN) U(iW, j) = dZero;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
+                PFORJ(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
             } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
-                PFOR(j, jS, jN) U(iW, j) = dZero;
+                PFORJ(j, jS, jN) U(iW, j) = dZero;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iW, j) = V(iW + 1, j);
+                PFORJ(j, jS + 1, jN) V(iW, j) = V(iW + 1, j);
             } else if (!kOutflowOnly && bt == W2_BM_INLET) {
-                PFOR(j, jS, jN) U(iW, j) = valU;
+                PFORJ(j, jS, jN) U(iW, j) = valU;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
+                PFORJ(j, jS + 1, jN) V(iW, j) = dTwo * valV - V(iW + 1, j);
             } else if (bt == W2_BM_OUTLT1) {
-                PFOR(j, jS, jN) U(iW - 1, j) = valU + U(iW, j);
+                PFORJ(j, jS, jN) U(iW - 1, j) = valU + U(iW, j);
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iW, j) = -V(iW + 1, j);
+                PFORJ(j, jS + 1, jN) V(iW, j) = -V(iW + 1, j);
             } else if (bt == W2_BM_OUTLT2) {
                 if (kOutflowOnly) {  // VelOutflowBCs :1725
-                    PFOR(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) - V(iW + 1, j) + V(iW + 1, j - 1);
+                    PFORJ(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) - V(iW + 1, j) + V(iW + 1, j - 1);
                 } else {             // VelBoundCond :608
-                    PFOR(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) + V(iW + 1, j) - V(iW + 1, j - 1);
+                    PFORJ(j, jS + 1, jN) U(iW, j) = U(iW + 1, j) + V(iW + 1, j) - V(iW + 1, j - 1);
                 }
                 __syncthreads();
                 SEQ {  // carried value kept in a register; same arithmetic as :612-613
@@ -66,23 +70,23 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
             const int bt = R->bd[q][W2_EAST - 1];
             const double valU = R->val[q][W2_EAST - 1][W2_U - 1], valV = R->val[q][W2_EAST - 1][W2_V - 1];
             if (!kOutflowOnly && bt == W2_BM_WALL1) {
-                PFOR(j, jS, jN) U(iE, j) = dZero;
+                PFORJ(j, jS, jN) U(iE, j) = dZero;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
+                PFORJ(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
             } else if (!kOutflowOnly && bt == W2_BM_WALL2) {
-                PFOR(j, jS, jN) U(iE, j) = dZero;
+                PFORJ(j, jS, jN) U(iE, j) = dZero;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iE + 1, j) = V(iE, j);
+                PFORJ(j, jS + 1, jN) V(iE + 1, j) = V(iE, j);
             } else if (!kOutflowOnly && bt == W2_BM_INLET) {
-                PFOR(j, jS, jN) U(iE, j) = valU;
+                PFORJ(j, jS, jN) U(iE, j) = valU;
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
+                PFORJ(j, jS + 1, jN) V(iE + 1, j) = dTwo * valV - V(iE, j);
             } else if (bt == W2_BM_OUTLT1) {
-                PFOR(j, jS, jN) U(iE + 1, j) = valU + U(iE, j);
+                PFORJ(j, jS, jN) U(iE + 1, j) = valU + U(iE, j);
                 __syncthreads();
-                PFOR(j, jS + 1, jN) V(iE + 1, j) = -V(iE, j);
+                PFORJ(j, jS + 1, jN) V(iE + 1, j) = -V(iE, j);
             } else if (bt == W2_BM_OUTLT2) {
-                PFOR(j, jS + 1, jN) U(iE, j) = U(iE - 1, j) - (V(iE, j) - V(iE, j - 1));
+                PFORJ(j, jS + 1, jN) U(iE, j) = U(iE - 1, j) - (V(iE, j) - V(iE, j - 1));
                 __syncthreads();
                 SEQ {
                     double prev = V(iE + 1, jS);
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
         }
         // ---------------- SOUTH (:697-766 / :1784-1824)
         {
-            const int bt = R->bd[q][W2_SOUTH - 1];
+            const int bt = ROWS_HELD(jS, jS + 1) ? R->bd[q][W2_SOUTH - 1] : W2_BM_INTERN;
             const double valU = R->val[q][W2_SOUTH - 1][W2_U - 1], valV = R->val[q][W2_SOUTH - 1][W2_V - 1];
             if (!kOutflowOnly && bt == W2_BM_WALL1) {
                 PFOR(i, iW + 1, iE) U(i, jS) = dTwo * valU - U(i, jS + 1);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
         }
         // ---------------- NORTH (:770-840 / :1828-1868)
         {
-            const int bt = R->bd[q][W2_NORTH - 1];
+            const int bt = ROWS_HELD(jN - 1, jN + 1) ? R->bd[q][W2_NORTH - 1] : W2_BM_INTERN;
             const double valU = R->val[q][W2_NORTH - 1][W2_U - 1], valV = R->val[q][W2_NORTH - 1][W2_V - 1];
             if (!kOutflowOnly && bt == W2_BM_WALL1) {
                 PFOR(i, iW + 1, iE) U(i, jN + 1) = dTwo * valU - U(i, jN);
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
     }
 }
 
-__global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__restrict__ R, int pitch, double *p) {
+__global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__restrict__ R, int pitch, int jlo, int jhi, double *p) {
     const double dZero = 0.0, dTwo = 2.0;
     const int nreg = R->nreg;
     for (int q = 0; q < nreg; ++q) {
@@ -173,40 +177,43 @@ __global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__
         const double vS = R->val[q][W2_SOUTH - 1][W2_P - 1], vN = R->val[q][W2_NORTH - 1][W2_P - 1];
         if (R->type[q] == W2_RM_BLOCKG) {  // :903-936
             const int w = iE - iW, h = jN - jS;
-            for (int t = threadIdx.x; t < w * h; t += BC_THREADS) P(iW + 1 + t % w, jS + 1 + t / w) = dZero;
+            for (int t = threadIdx.x; t < w * h; t += BC_THREADS) {
+                const int j = jS + 1 + t / w;
+                if (j >= jlo && j <= jhi) P(iW + 1 + t % w, j) = dZero;
+            }
             __syncthreads();
-            PFOR(j, jS + 1, jN) P(iW + 1, j) = vW + P(iW, j);
+            PFORJ(j, jS + 1, jN) P(iW + 1, j) = vW + P(iW, j);
             __syncthreads();
-            PFOR(j, jS + 1, jN) P(iE, j) = vE + P(iE + 1, j);
+            PFORJ(j, jS + 1, jN) P(iE, j) = vE + P(iE + 1, j);
             __syncthreads();
-            PFOR(i, iW + 1, iE) P(i, jS + 1) = vS + P(i, jS);
+            if (ROWS_HELD(jS, jS + 1)) PFOR(i, iW + 1, iE) P(i, jS + 1) = vS + P(i, jS);
             __syncthreads();
-            PFOR(i, iW + 1, iE) P(i, jN) = vN + P(i, jN + 1);
+            if (ROWS_HELD(jN, jN + 1)) PFOR(i, iW + 1, iE) P(i, jN) = vN + P(i, jN + 1);
             __syncthreads();
             continue;
         }
         int bt = R->bd[q][W2_WEST - 1];
         if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
-            PFOR(j, jS + 1, jN) P(iW, j) = vW + P(iW + 1, j);
+            PFORJ(j, jS + 1, jN) P(iW, j) = vW + P(iW + 1, j);
         } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
-            PFOR(j, jS + 1, jN) P(iW, j) = dTwo * vW - P(iW + 1, j);
+            PFORJ(j, jS + 1, jN) P(iW, j) = dTwo * vW - P(iW + 1, j);
         }
         __syncthreads();
         bt = R->bd[q][W2_EAST - 1];
         if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
-            PFOR(j, jS + 1, jN) P(iE + 1, j) = vE + P(iE, j);
+            PFORJ(j, jS + 1, jN) P(iE + 1, j) = vE + P(iE, j);
         } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
-            PFOR(j, jS + 1, jN) P(iE + 1, j) = dTwo * vE - P(iE, j);
+            PFORJ(j, jS + 1, jN) P(iE + 1, j) = dTwo * vE - P(iE, j);
         }
         __syncthreads();
-        bt = R->bd[q][W2_SOUTH - 1];
+        bt = ROWS_HELD(jS, jS + 1) ? R->bd[q][W2_SOUTH - 1] : W2_BM_INTERN;
         if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
             PFOR(i, iW + 1, iE) P(i, jS) = vS + P(i, jS + 1);
         } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
             PFOR(i, iW + 1, iE) P(i, jS) = dTwo * vS - P(i, jS + 1);
         }
         __syncthreads();
-        bt = R->bd[q][W2_NORTH - 1];
+        bt = ROWS_HELD(jN, jN + 1) ? R->bd[q][W2_NORTH - 1] : W2_BM_INTERN;
         if (bt == W2_BM_WALL1 || bt == W2_BM_WALL2 || bt == W2_BM_INLET) {
             PFOR(i, iW + 1, iE) P(i, jN + 1) = vN + P(i, jN);
         } else if (bt == W2_BM_OUTLT1 || bt == W2_BM_OUTLT2) {
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__
 }
 
 int w2_vel_bc(wolfd2_ctx *c, double *u, double *v) {
-    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, u, v);
+    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
@@ -229,13 +236,13 @@ int w2_outflow_bc(wolfd2_ctx *c, double *u, double *v) {
         for (int k = 0; k < 4; ++k)
             if (c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2) any = true;
     if (!any) return W2_OK;
-    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, u, v);
+    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v);
     c->launches[1]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
 int w2_pres_bc(wolfd2_ctx *c, double *p) {
-    pres_bc_kernel<<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, p);
+    pres_bc_kernel<<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, p);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;

@@ -55,6 +55,48 @@ static int dalloc(double **p, size_t n) {
     W2_CUDA(cudaMemset(*p, 0, n * sizeof(double)));
     return W2_OK;
 }
+// field-layout array of this rank's rows; the stored pointer is shifted so that f[i + pitch*j] takes GLOBAL j
+static int falloc(wolfd2_ctx *c, double **p) {
+    W2_TRY(dalloc(p, c->nelem));
+    *p -= c->row_off;
+    return W2_OK;
+}
+static int balloc(wolfd2_ctx *c, unsigned char **p, size_t planes) {
+    W2_CUDA(cudaMalloc((void **)p, planes * c->nelem));
+    W2_CUDA(cudaMemset(*p, 0, planes * c->nelem));
+    *p -= c->row_off;
+    return W2_OK;
+}
+int w2_alloc_pormap(wolfd2_ctx *c) { return c->pormap ? W2_OK : balloc(c, &c->pormap, 6); }
+int w2_alloc_field(wolfd2_ctx *c, double **p) { return falloc(c, p); }
+static void ffree(wolfd2_ctx *c, double *p) { if (p) cudaFree(p + c->row_off); }
+static void bfree(wolfd2_ctx *c, unsigned char *p) { if (p) cudaFree(p + c->row_off); }
+
+// Row slab of `rank` (same arithmetic as wolfd2_b200/slab.py slab_rows): the unknown pressure rows 2..ny in
+// `world` contiguous blocks, earlier ranks take the remainder.  Halo depth: 2T = 4 rows for the fused SOR
+// pass and the rows a straddling 2048-unknown momentum segment reaches into, plus the stencil row.
+void w2_slab_layout(int nx, int ny, int world, int rank, int *J0, int *J1, int *A0, int *A1, int *HG) {
+    const int nrows = ny - 1, base = nrows / world, rem = nrows % world;
+    *J0 = 2 + rank * base + (rank < rem ? rank : rem);
+    *J1 = *J0 + base + (rank < rem ? 1 : 0) - 1;
+    *HG = world == 1 ? 0 : 4 + 2047 / (nx - 1);
+    if (world > 1 && *HG < 5) *HG = 5;
+    *A0 = rank == 0 ? 0 : *J0 - *HG;
+    *A1 = rank == world - 1 ? ny + 1 : *J1 + *HG;
+    if (*A0 < 0) *A0 = 0;
+    if (*A1 > ny + 1) *A1 = ny + 1;
+}
+extern "C" int wolfd2_b200_slab_layout(int32_t nx, int32_t ny, int32_t world, int32_t rank, int32_t out[5]) {
+    if (world < 1 || rank < 0 || rank >= world || nx < 6 || ny < 6) { w2_set_error("slab_layout: bad arguments"); return W2_ERR_BAD_ARG; }
+    int J0, J1, A0, A1, HG;
+    w2_slab_layout(nx, ny, world, rank, &J0, &J1, &A0, &A1, &HG);
+    if (world > 1 && (ny - 1) / world < 2 * HG) {
+        w2_set_error("%d rows cannot be split into %d slabs of >= %d rows (2 x halo depth)", ny - 1, world, 2 * HG);
+        return W2_ERR_BAD_ARG;
+    }
+    out[0] = J0; out[1] = J1; out[2] = A0; out[3] = A1; out[4] = HG;
+    return W2_OK;
+}
 
 // Translate the Fortran region tables (bound_cond.f SetUpBCs output) to the device struct.
 int w2_fill_regions(W2Regions *r, int nx, int ny, const int32_t *nReg, const int32_t *nRegBrd,
@@ -119,14 +161,16 @@ int w2_ctx_set_regions(wolfd2_ctx *c, const W2Regions *r) {
     return W2_OK;
 }
 
-int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
+int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     *out = nullptr;
     W2_TRY(check_device());
+    int32_t lay[5];
+    W2_TRY(wolfd2_b200_slab_layout(nx, ny, world, rank, lay));
     if (nx < 6 || ny < 6) {
         w2_set_error("grid %dx%d too small (need nx,ny >= 6)", nx, ny);
         return W2_ERR_BAD_ARG;
     }
-    if (nx + 1 > g_mnx || ny + 1 > g_mny) {  // CheckGridSize, src/grid.f:551
+    if (nx + 1 > g_mnx || (world == 1 ? ny + 1 : lay[3] - lay[2]) > g_mny) {  // CheckGridSize, src/grid.f:551
         w2_set_error("grid %dx%d does not fit mnx=%d mny=%d (need mnx>=nx+1, mny>=ny+1); call wolfd2_b200_config",
                      nx, ny, g_mnx, g_mny);
         return W2_ERR_BAD_ARG;
@@ -136,7 +180,12 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
     c->device = g_device;
     c->nx = nx; c->ny = ny; c->mnx = g_mnx; c->mny = g_mny;
     c->pitch = ((nx + 2 + 15) / 16) * 16;
-    c->rows = ny + 2;
+    c->rank = rank; c->world = world;
+    c->J0 = lay[0]; c->J1 = lay[1]; c->A0 = lay[2]; c->A1 = lay[3]; c->HG = lay[4];
+    c->E0 = rank == 0 ? 0 : c->J0;
+    c->E1 = rank == world - 1 ? ny + 1 : c->J1;
+    c->rows = c->A1 - c->A0 + 1;
+    c->row_off = (size_t)c->pitch * (size_t)c->A0;
     c->nelem = (size_t)c->pitch * (size_t)(c->rows + 1) + 512;  // guard: strip loads may overrun a row
     cudaDeviceProp prop;
     W2_CUDA(cudaGetDeviceProperties(&prop, c->device));
@@ -151,23 +200,27 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny) {
     for (int k = 0; k < 8; ++k) W2_CUDA(cudaEventCreate(&c->ev[k]));
     W2_CUDA(cudaMalloc((void **)&c->dreg, sizeof(W2Regions)));
     double **mp = &c->met.rau;
-    for (int k = 0; k < 30; ++k) W2_TRY(dalloc(&mp[k], c->nelem));
-    for (int k = 0; k < W2_F_COUNT; ++k) W2_TRY(dalloc(&c->fld[k], c->nelem));
-    W2_TRY(dalloc(&c->dus, c->nelem));
-    W2_TRY(dalloc(&c->dvs, c->nelem));
-    W2_TRY(dalloc(&c->div, c->nelem));
-    W2_CUDA(cudaMalloc((void **)&c->pmask, c->nelem));
-    W2_CUDA(cudaMemset(c->pmask, 0, c->nelem));
-    W2_CUDA(cudaMalloc((void **)&c->xmask, c->nelem));
-    W2_CUDA(cudaMalloc((void **)&c->ymask, c->nelem));
+    for (int k = 0; k < 30; ++k) W2_TRY(falloc(c, &mp[k]));
+    for (int k = 0; k < W2_F_COUNT; ++k) W2_TRY(falloc(c, &c->fld[k]));
+    W2_TRY(falloc(c, &c->dus));
+    W2_TRY(falloc(c, &c->dvs));
+    W2_TRY(falloc(c, &c->div));
+    W2_TRY(falloc(c, &c->x1));
+    W2_TRY(balloc(c, &c->pmask, 1));
+    W2_TRY(balloc(c, &c->xmask, 1));
+    W2_TRY(balloc(c, &c->ymask, 1));
     // chain arrays are read in whole segments by the tridiagonal solver: pad generously
     const long long nmax = ((long long)nx * (long long)ny / 4096 + 3) * 4096;
-    W2_TRY(dalloc(&c->ta, (size_t)nmax));
-    W2_TRY(dalloc(&c->td, (size_t)nmax));
-    W2_TRY(dalloc(&c->tc, (size_t)nmax));
-    W2_TRY(dalloc(&c->tb, (size_t)nmax));
-    W2_TRY(dalloc(&c->tx, (size_t)nmax > c->nelem ? (size_t)nmax : c->nelem));  // also used in field layout
-    W2_TRY(w2_tri_prepare(c, nmax));
+    if (world == 1) {   // chain-layout work of the line solvers and of the AltTridLU shim (one GPU only)
+        W2_TRY(dalloc(&c->ta, (size_t)nmax));
+        W2_TRY(dalloc(&c->td, (size_t)nmax));
+        W2_TRY(dalloc(&c->tc, (size_t)nmax));
+        W2_TRY(dalloc(&c->tb, (size_t)nmax));
+        W2_TRY(dalloc(&c->tx, (size_t)nmax));
+    }
+    // level-0 spike arrays hold only this rank's segments; the segment table and upper levels are global
+    const long long cap0 = world == 1 ? nmax : (long long)(c->rows + 2) * nx + 3 * 2048;
+    W2_TRY(w2_tri_prepare(c, nmax, cap0));
     W2_CUDA(cudaMalloc((void **)&c->d_norm, 64 * sizeof(unsigned long long)));
     W2_CUDA(cudaMemset(c->d_norm, 0, 64 * sizeof(unsigned long long)));
     W2_CUDA(cudaMalloc((void **)&c->d_flags, 64 * sizeof(int)));
@@ -183,10 +236,11 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     double **mp = &c->met.rau;
-    for (int k = 0; k < 30; ++k) cudaFree(mp[k]);
-    for (int k = 0; k < W2_F_COUNT; ++k) cudaFree(c->fld[k]);
-    cudaFree(c->dus); cudaFree(c->dvs); cudaFree(c->div); cudaFree(c->qh); cudaFree(c->pmask); cudaFree(c->xmask); cudaFree(c->ymask); cudaFree(c->pormap);
-    for (int k = 0; k < 4; ++k) cudaFree(c->sorf_buf[k]);
+    for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
+    for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);
+    ffree(c, c->dus); ffree(c, c->dvs); ffree(c, c->div); ffree(c, c->x1); ffree(c, c->qh);
+    bfree(c, c->pmask); bfree(c, c->xmask); bfree(c, c->ymask); bfree(c, c->pormap);
+    for (int k = 0; k < 4; ++k) ffree(c, c->sorf_buf[k]);
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
     w2_tri_release(c);
     cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);
@@ -197,16 +251,17 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     free(c);
 }
 
-// Host (0:mnx,0:mny) <-> device pitched copies of the (0..nx+1, 0..ny+1) window.
+// Host (0:mnx,0:mny) <-> device pitched copies of the (0..nx+1, 0..ny+1) window.  In a slab context the
+// host array holds this rank's rows only: host row 0 is global row A0 (wolfd2_b200_slab_layout).
 int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host) {
-    W2_CUDA(cudaMemcpy2DAsync(dev, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
-                              (size_t)(c->nx + 2) * 8, (size_t)(c->ny + 2), cudaMemcpyHostToDevice,
+    W2_CUDA(cudaMemcpy2DAsync(dev + c->row_off, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
+                              (size_t)(c->nx + 2) * 8, (size_t)c->rows, cudaMemcpyHostToDevice,
                               c->stream));
     return W2_OK;
 }
 int w2_download2d(wolfd2_ctx *c, double *host, const double *dev) {
-    W2_CUDA(cudaMemcpy2DAsync(host, (size_t)(c->mnx + 1) * 8, dev, (size_t)c->pitch * 8,
-                              (size_t)(c->nx + 2) * 8, (size_t)(c->ny + 2), cudaMemcpyDeviceToHost,
+    W2_CUDA(cudaMemcpy2DAsync(host, (size_t)(c->mnx + 1) * 8, dev + c->row_off, (size_t)c->pitch * 8,
+                              (size_t)(c->nx + 2) * 8, (size_t)c->rows, cudaMemcpyDeviceToHost,
                               c->stream));
     return W2_OK;
 }
@@ -227,14 +282,45 @@ extern "C" int wolfd2_b200_set_params(wolfd2_ctx *c, const wolfd2_params *par) {
 
 extern "C" int wolfd2_b200_create(wolfd2_ctx **out, const wolfd2_params *par, const wolfd2_regions *reg,
                                   const wolfd2_metrics *met) {
+    return wolfd2_b200_create_slab(out, par, reg, met, 0, 1);
+}
+
+// One context per rank of a multi-GPU run (after wolfd2_b200_comm_init).  par and reg describe the GLOBAL
+// grid; the metric arrays (and every field passed to upload/download/step_host) hold this rank's rows
+// A0..A1 of wolfd2_b200_slab_layout, host row 0 = global row A0.
+extern "C" int wolfd2_b200_create_slab(wolfd2_ctx **out, const wolfd2_params *par, const wolfd2_regions *reg,
+                                       const wolfd2_metrics *met, int32_t rank, int32_t world) {
     if (!out || !par || !reg || !met) return W2_ERR_BAD_ARG;
+    if (world > 1 && (world != w2_dist_world() || rank != w2_dist_rank())) {
+        w2_set_error("create_slab(rank %d of %d) does not match wolfd2_b200_comm_init (rank %d of %d)", rank, world,
+                     w2_dist_rank(), w2_dist_world());
+        return W2_ERR_BAD_ARG;
+    }
+    if (world > 1) {
+        if (par->nPpeSolver != W2_PPE_RB_SOR && par->nPpeSolver != W2_PPE_PAR_RB_SOR) {
+            w2_set_error("multi-GPU runs support ppe_solver 5/6 (rb_sor, par_rb_sor) only, got %d", par->nPpeSolver);
+            return W2_ERR_UNSUPPORTED;
+        }
+        if (!par->lCartesGrid || par->nx < 254) {
+            w2_set_error("multi-GPU runs need a Cartesian grid with nx >= 254 (fused SOR pipeline)");
+            return W2_ERR_UNSUPPORTED;
+        }
+    }
     wolfd2_ctx *c = nullptr;
-    W2_TRY(w2_ctx_create_raw(&c, par->nx, par->ny));
+    W2_TRY(w2_ctx_create_raw(&c, par->nx, par->ny, rank, world));
     int rc = wolfd2_b200_set_params(c, par);
     if (rc == W2_OK) {
         W2Regions r;
         rc = w2_fill_regions(&r, par->nx, par->ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp,
                              reg->dBCVal, reg->dPRporos, reg->dPRporc1, reg->dPRporc2);
+        if (rc == W2_OK && world > 1)   // the OUTLT2 ghost fills are recurrences along the whole face (bound_cond.f:611-614)
+            for (int q = 0; q < r.nreg && rc == W2_OK; ++q)
+                for (int k = 0; k < 4; ++k)
+                    if (r.bd[q][k] == W2_BM_OUTLT2) {
+                        w2_set_error("multi-GPU runs do not support OUTLT2 faces (region %d face %d)", q + 1, k + 1);
+                        rc = W2_ERR_UNSUPPORTED;
+                        break;
+                    }
         if (rc == W2_OK) rc = w2_ctx_set_regions(c, &r);
     }
     if (rc == W2_OK) {

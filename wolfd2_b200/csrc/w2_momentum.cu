@@ -59,13 +59,13 @@ template <int COMP, int STEP, bool POR>
 __global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
-                                                              long long nseg, int direct) {
+                                                              long long nseg, int direct, long long seg0) {
     extern __shared__ __align__(16) double sm[];
     double *s0 = sm, *s1 = sm + MR_LEN, *s2 = sm + 2 * MR_LEN, *s3 = sm + 3 * MR_LEN;
     __shared__ int s_ext[2];
     __shared__ double sSig;
     const int t = threadIdx.x;
-    const long long g = blockIdx.x;
+    const long long g = seg0 + blockIdx.x;   // global segment; Vg, Wg, ext are pre-shifted by the caller
     const long long ebase = g * (long long)TRI_S;
     const int pitch = m.pitch;
     constexpr int L = TRI_M - 2;
@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long lo
 template <int COMP>
 __global__ void __launch_bounds__(256) mom_finalize_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                            const double *__restrict__ Vg, const double *__restrict__ Wg,
-                                                           const double *__restrict__ sig, const int *__restrict__ ext) {
-    const long long g = blockIdx.x;
+                                                           const double *__restrict__ sig, const int *__restrict__ ext,
+                                                           long long seg0) {
+    const long long g = seg0 + blockIdx.x;
     const int pitch = m.pitch;
     const int extV = ext[2 * g], extW = ext[2 * g + 1];
     const double sl = g > 0 ? sig[g - 1] : 0.0, sr = sig[g];
@@ -182,11 +183,11 @@ __global__ void __launch_bounds__(256) mom_finalize_kernel(MomArgs m, long long 
 }
 
 // identity-row masks of the second split step (momentum.f:434-496 for u, :760-821 for v)
-__global__ void mom_mask_kernel(const W2Regions *__restrict__ R, int nx, int ny, int pitch,
+__global__ void mom_mask_kernel(const W2Regions *__restrict__ R, int nx, int jlo, int jhi, int pitch,
                                 unsigned char *__restrict__ xmask, unsigned char *__restrict__ ymask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i > nx + 1 || j > ny + 1) return;
+    const int j = jlo + blockIdx.y;
+    if (i > nx + 1 || j > jhi) return;
     unsigned char mx = 0, my = 0;
     for (int q = 0; q < R->nreg; ++q) {
         const int iW = R->iW[q], iE = R->iE[q], jS = R->jS[q], jN = R->jN[q];
@@ -212,32 +213,33 @@ __global__ void mom_mask_kernel(const W2Regions *__restrict__ R, int nx, int ny,
 }
 
 // us,vs <- un,vn on 1..nx+1, 1..ny+1 (:114-119)
-__global__ void __launch_bounds__(256) ql_init_kernel(int nx, int ny, int pitch, const double *__restrict__ un,
+__global__ void __launch_bounds__(256) ql_init_kernel(int nx, int jlo, int jhi, int pitch, const double *__restrict__ un,
                                                       const double *__restrict__ vn, double *__restrict__ us,
                                                       double *__restrict__ vs) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i > nx + 1) return;
-    for (int j = 1 + blockIdx.y; j <= ny + 1; j += gridDim.y) {
+    for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
         us[IDX(i, j)] = un[IDX(i, j)];
         vs[IDX(i, j)] = vn[IDX(i, j)];
     }
 }
 
 // us += dus, vs += dvs on 1..nx,1..ny (:171-176) fused with the two DMaxNorm scans (:179-180)
-__global__ void __launch_bounds__(256) ql_update_kernel(int nx, int ny, int pitch, const double *__restrict__ dus,
+__global__ void __launch_bounds__(256) ql_update_kernel(int nx, int ny, int jlo, int jhi, int seed, int pitch,
+                                                        const double *__restrict__ dus,
                                                         const double *__restrict__ dvs, double *__restrict__ us,
                                                         double *__restrict__ vs, unsigned long long *slots) {
     __shared__ double red[32];
     double mu = 0.0, mv = 0.0;
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= nx)
-        for (int j = 1 + blockIdx.y; j <= ny; j += gridDim.y) {
+        for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
             const double du = dus[IDX(i, j)], dv = dvs[IDX(i, j)];
             us[IDX(i, j)] = us[IDX(i, j)] + du;
             vs[IDX(i, j)] = vs[IDX(i, j)] + dv;
             if (i >= 2 && i <= nx - 1 && j >= 2 && j <= ny - 1) { mu = fmax(mu, fabs(du)); mv = fmax(mv, fabs(dv)); }
         }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // DMaxNorm seed |u(5,5)| (utility.f:493)
+    if (seed && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // DMaxNorm seed |u(5,5)| (utility.f:493)
         mu = fmax(mu, fabs(dus[IDX(5, 5)]));
         mv = fmax(mv, fabs(dvs[IDX(5, 5)]));
     }
@@ -249,11 +251,11 @@ __global__ void __launch_bounds__(256) ql_update_kernel(int nx, int ny, int pitc
 // ---- host side -----------------------------------------------------------------------------------
 // per-cell porous-region maps (6 planes): xd1,xd2 / yd1,yd2 = porous regions whose division range holds
 // the cell (momentum.f:310-319 / :635-644); xcp / ycp = last region whose PorosCoef assignment reaches it
-__global__ void por_map_kernel(const W2Regions *__restrict__ R, int nx, int ny, int pitch, size_t plane,
+__global__ void por_map_kernel(const W2Regions *__restrict__ R, int nx, int jlo, int jhi, int pitch, size_t plane,
                                unsigned char *__restrict__ maps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i > nx + 1 || j > ny + 1) return;
+    const int j = jlo + blockIdx.y;
+    if (i > nx + 1 || j > jhi) return;
     unsigned char xd[2] = {0, 0}, yd[2] = {0, 0}, xc = 0, yc = 0;
     int nxd = 0, nyd = 0;
     for (int q = 0; q < R->nreg; ++q) {
@@ -274,12 +276,12 @@ __global__ void por_map_kernel(const W2Regions *__restrict__ R, int nx, int ny, 
 
 int w2_build_mom_masks(wolfd2_ctx *c) {
     if (c->hreg.has_porous) {
-        if (!c->pormap) W2_CUDA(cudaMalloc((void **)&c->pormap, 6 * c->nelem));
-        dim3 g((c->nx + 2 + 255) / 256, c->ny + 2);
-        por_map_kernel<<<g, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, c->nelem, c->pormap);
+        W2_TRY(w2_alloc_pormap(c));
+        dim3 g((c->nx + 2 + 255) / 256, c->rows);
+        por_map_kernel<<<g, 256, 0, c->stream>>>(c->dreg, c->nx, c->A0, c->A1, c->pitch, c->nelem, c->pormap);
     }
-    dim3 grid((c->nx + 2 + 255) / 256, c->ny + 2);
-    mom_mask_kernel<<<grid, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, c->xmask, c->ymask);
+    dim3 grid((c->nx + 2 + 255) / 256, c->rows);
+    mom_mask_kernel<<<grid, 256, 0, c->stream>>>(c->dreg, c->nx, c->A0, c->A1, c->pitch, c->xmask, c->ymask);
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
@@ -297,9 +299,9 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xen = t.xen; m.yen = t.yen; m.xzc = t.xzc; m.yzc = t.yzc;
     m.xev = t.xev; m.yev = t.yev; m.xzv = t.xzv; m.yzv = t.yzv;
     m.xmask = c->xmask; m.ymask = c->ymask;
-    m.x1 = c->tx;
+    m.x1 = c->x1;
     m.porous = c->hreg.has_porous; m.R = c->dreg;
-    unsigned char *pm = c->pormap;
+    unsigned char *pm = c->pormap;   // planes are nelem bytes apart; the row shift is in the base pointer
     m.xd1 = pm; m.xd2 = pm + c->nelem; m.yd1 = pm + 2 * c->nelem; m.yd2 = pm + 3 * c->nelem;
     m.xcp = pm + 4 * c->nelem; m.ycp = pm + 5 * c->nelem;
 }
@@ -310,6 +312,50 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out);
 template <int COMP, int STEP>
 static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
     return c->hreg.has_porous ? mom_solve_impl<COMP, STEP, true>(c, m, n, out) : mom_solve_impl<COMP, STEP, false>(c, m, n, out);
+}
+
+// Chain unknowns [lo, hi) that lie in the rows this rank updates.  The level-0 segments keep their GLOBAL
+// boundaries (so every number is the one a single GPU computes); a rank reduces the segments that START in
+// its range, and the unknowns of its last segment that fall into the next slab's first rows are shipped
+// there after the second split step (mom_tail_exchange).
+template <int COMP>
+static void chain_range(const wolfd2_ctx *c, long long &lo, long long &hi) {
+    const int r0 = c->E0 > (COMP == 0 ? 2 : 1) ? c->E0 : (COMP == 0 ? 2 : 1);
+    const int r1 = c->E1 < c->ny ? c->E1 : c->ny;
+    if (COMP == 0) { lo = (long long)(r0 - 2) * c->nx; hi = (long long)(r1 - 1) * c->nx; }
+    else { lo = (long long)(r0 - 1) * (c->nx - 1); hi = (long long)r1 * (c->nx - 1); }
+}
+
+template <int COMP>
+static int chain_pieces(const wolfd2_ctx *c, double *f, long long e0, long long e1, W2Piece *pc, int maxpc) {
+    const int w = COMP == 0 ? c->nx : c->nx - 1;
+    int np = 0;
+    for (long long e = e0; e < e1;) {
+        const long long jj = e / w;
+        const int off = (int)(e - jj * w);
+        const long long cnt = (e1 - e) < (long long)(w - off) ? (e1 - e) : (long long)(w - off);
+        const int j = (COMP == 0 ? 2 : 1) + (int)jj, i = (COMP == 0 ? 1 : 2) + off;
+        if (np >= maxpc) return -1;
+        pc[np].p = f + (size_t)i + (size_t)c->pitch * (size_t)j;
+        pc[np].n = (size_t)cnt;
+        ++np;
+        e += cnt;
+    }
+    return np;
+}
+
+template <int COMP>
+static int mom_tail_exchange(wolfd2_ctx *c, double *out) {
+    if (c->world == 1) return W2_OK;
+    long long lo, hi;
+    chain_range<COMP>(c, lo, hi);
+    const long long s_lo = (lo + TRI_S - 1) / TRI_S, s_hi = (hi + TRI_S - 1) / TRI_S;
+    W2Piece up[16], dn[16];
+    int nup = 0, ndn = 0;
+    if (c->rank + 1 < c->world) nup = chain_pieces<COMP>(c, out, hi, s_hi * TRI_S, up, 16);
+    if (c->rank > 0) ndn = chain_pieces<COMP>(c, out, lo, s_lo * TRI_S, dn, 16);
+    if (nup < 0 || ndn < 0) { w2_set_error("momentum tail exchange: too many row pieces"); return W2_ERR_BAD_ARG; }
+    return w2_send_recv_pieces(c, up, nup, dn, ndn);
 }
 
 template <int COMP, int STEP, bool POR>
@@ -323,15 +369,33 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
     W2TriWork &w = c->tri;
     const long long nseg = (n + TRI_S - 1) / TRI_S;
     const int direct = nseg == 1;
-    mom_reduce_kernel<COMP, STEP, POR><<<(unsigned)nseg, TRI_T, smem, c->stream>>>(m, n, out, w.V0, w.W0, w.lv[0].seg, w.ext, nseg, direct);
+    long long s_lo = 0, s_hi = nseg;
+    if (c->world > 1) {
+        long long lo, hi;
+        chain_range<COMP>(c, lo, hi);
+        s_lo = (lo + TRI_S - 1) / TRI_S;
+        if (c->rank + 1 < c->world) s_hi = (hi + TRI_S - 1) / TRI_S;
+        if (direct || s_hi <= s_lo || (s_hi - s_lo) * TRI_S > w.cap) {
+            w2_set_error("momentum chain cannot be split across %d ranks (segments %lld..%lld)", c->world, s_lo, s_hi);
+            return W2_ERR_BAD_ARG;
+        }
+        W2_CUDA(cudaMemsetAsync(w.lv[0].seg, 0, 10 * (size_t)nseg * sizeof(double), c->stream));
+    }
+    double *V0 = w.V0 - s_lo * TRI_S, *W0 = w.W0 - s_lo * TRI_S;
+    int *ext = w.ext - 2 * s_lo;
+    mom_reduce_kernel<COMP, STEP, POR><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(m, n, out, V0, W0, w.lv[0].seg, ext, nseg,
+                                                                                           direct, s_lo);
     c->launches[1]++;
     if (!direct) {
+        // every rank holds the records of its own segments; summing with the zeros of the others is exact
+        W2_TRY(w2_allreduce_sum_f64(c, w.lv[0].seg, 10 * (size_t)nseg));
         const double *sigma = nullptr;
-        W2_TRY(w2_tri_upper(c, nseg, &sigma));
-        mom_finalize_kernel<COMP><<<(unsigned)nseg, 256, 0, c->stream>>>(m, n, out, w.V0, w.W0, sigma, w.ext);
+        W2_TRY(w2_tri_upper(c, nseg, &sigma));   // a few thousand unknowns: solved redundantly on every rank
+        mom_finalize_kernel<COMP><<<(unsigned)(s_hi - s_lo), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo);
         c->launches[1]++;
     }
     W2_CUDA(cudaGetLastError());
+    if (STEP == 2) W2_TRY(mom_tail_exchange<COMP>(c, out));
     return W2_OK;
 }
 
@@ -339,7 +403,7 @@ int w2_xmomentum(wolfd2_ctx *c, double *dus) {
     MomArgs m;
     fill_args(c, m);
     const long long n = (long long)c->nx * (c->ny - 1);
-    W2_TRY((mom_solve<0, 1>(c, m, n, c->tx)));   // :350-389, result in field layout
+    W2_TRY((mom_solve<0, 1>(c, m, n, c->x1)));   // :350-389, result in field layout
     W2_TRY((mom_solve<0, 2>(c, m, n, dus)));     // :396-510
     return W2_OK;
 }
@@ -348,7 +412,7 @@ int w2_ymomentum(wolfd2_ctx *c, double *dvs) {
     MomArgs m;
     fill_args(c, m);
     const long long n = (long long)(c->nx - 1) * c->ny;
-    W2_TRY((mom_solve<1, 1>(c, m, n, c->tx)));   // :675-716
+    W2_TRY((mom_solve<1, 1>(c, m, n, c->x1)));   // :675-716
     W2_TRY((mom_solve<1, 2>(c, m, n, dvs)));     // :723-834
     return W2_OK;
 }
@@ -359,8 +423,10 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
     double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS];
     *nQLiter = -1;  // :111
     if (init_star) {
-        dim3 g((nx + 1 + 255) / 256, (ny + 1) < 2048 ? (ny + 1) : 2048);
-        ql_init_kernel<<<g, 256, 0, c->stream>>>(nx, ny, c->pitch, c->fld[W2_F_UN], c->fld[W2_F_VN], us, vs);
+        // all held rows: un, vn have valid halos, so the copy needs no exchange
+        const int jlo = c->A0 > 1 ? c->A0 : 1, jhi = c->A1;
+        dim3 g((nx + 1 + 255) / 256, (jhi - jlo + 1) < 2048 ? (jhi - jlo + 1) : 2048);
+        ql_init_kernel<<<g, 256, 0, c->stream>>>(nx, jlo, jhi, c->pitch, c->fld[W2_F_UN], c->fld[W2_F_VN], us, vs);
         c->launches[1]++;
     }
     for (int m = 1; m <= c->par.mqiter; ++m) {
@@ -369,10 +435,17 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
         W2_TRY(w2_xmomentum(c, c->dus));   // :147
         W2_TRY(w2_ymomentum(c, c->dvs));   // :158
         W2_CUDA(cudaMemsetAsync(c->d_norm + 8, 0, 2 * sizeof(unsigned long long), c->stream));
-        dim3 g((nx + 255) / 256, ny < 2048 ? ny : 2048);
-        ql_update_kernel<<<g, 256, 0, c->stream>>>(nx, ny, c->pitch, c->dus, c->dvs, us, vs, c->d_norm + 8);
+        int jlo = 1, jhi = ny;
+        w2_clip(c, jlo, jhi);
+        dim3 g((nx + 255) / 256, (jhi - jlo + 1) < 2048 ? (jhi - jlo + 1) : 2048);
+        ql_update_kernel<<<g, 256, 0, c->stream>>>(nx, ny, jlo, jhi, c->rank == 0, c->pitch, c->dus, c->dvs, us, vs, c->d_norm + 8);
         c->launches[1]++;
         W2_CUDA(cudaGetLastError());
+        if (c->world > 1) {
+            W2_TRY(w2_allreduce_max_u64(c, c->d_norm + 8, 2));
+            double *uv[2] = {us, vs};
+            W2_TRY(w2_halo_exchange(c, uv, 2, c->HG));
+        }
         W2_CUDA(cudaMemcpyAsync(c->h_norm + 8, c->d_norm + 8, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         W2_CUDA(cudaStreamSynchronize(c->stream));
         double dif[2];

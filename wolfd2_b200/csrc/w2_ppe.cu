@@ -21,11 +21,11 @@
 #define P(i, j) p[IDX(i, j)]
 
 // ------------------------------------------------------------------ Ppe row mask
-__global__ void pmask_kernel(const W2Regions *__restrict__ R, int nx, int ny, int pitch,
+__global__ void pmask_kernel(const W2Regions *__restrict__ R, int nx, int jlo, int jhi, int pitch,
                              unsigned char *__restrict__ mask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i > nx + 1 || j > ny + 1) return;
+    const int j = jlo + blockIdx.y;
+    if (i > nx + 1 || j > jhi) return;
     unsigned char m = 0;
     for (int q = 0; q < R->nreg; ++q) {
         if (R->type[q] != W2_RM_BLOCKG) continue;
@@ -41,11 +41,11 @@ __global__ void pmask_kernel(const W2Regions *__restrict__ R, int nx, int ny, in
 
 int w2_build_pmask(wolfd2_ctx *c) {
     if (!c->hreg.has_blockage) {
-        W2_CUDA(cudaMemsetAsync(c->pmask, 0, c->nelem, c->stream));
+        W2_CUDA(cudaMemsetAsync(c->pmask + c->row_off, 0, c->nelem, c->stream));
         return W2_OK;
     }
-    dim3 grid((c->nx + 2 + 255) / 256, c->ny + 2);
-    pmask_kernel<<<grid, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, c->pmask);
+    dim3 grid((c->nx + 2 + 255) / 256, c->rows);
+    pmask_kernel<<<grid, 256, 0, c->stream>>>(c->dreg, c->nx, c->A0, c->A1, c->pitch, c->pmask);
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
@@ -111,7 +111,7 @@ int w2_divergence(wolfd2_ctx *c, const double *u, const double *v, double *div, 
 // Fused Divergence(nloc=1) + blockage zeroing + RhsPpe (Cartesian part): b = div/dk on 2..nx,2..ny.
 // If div_out != nullptr the masked divergence is also stored (needed when the grid is not
 // Cartesian and b is rebuilt every sweep, :425-427).
-__global__ void __launch_bounds__(256) div_rhs_kernel(int nx, int ny, int pitch, double dk,
+__global__ void __launch_bounds__(256) div_rhs_kernel(int nx, int jlo, int jhi, int pitch, double dk,
                                                       const double *__restrict__ xeu, const double *__restrict__ yeu,
                                                       const double *__restrict__ xzv, const double *__restrict__ yzv,
                                                       const double *__restrict__ u, const double *__restrict__ v,
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) div_rhs_kernel(int nx, int ny, int pitch,
                                                       int sentinel, double *__restrict__ b,
                                                       double *__restrict__ div_out) {
     const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-    for (int j = 2 + blockIdx.y; j <= ny; j += gridDim.y) {
+    for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
         if (i > nx) continue;
         double d = div_point<1>(i, j, pitch, xeu, yeu, xzv, yzv, u, v);
         const bool masked = has_mask && mask[IDX(i, j)];
@@ -260,9 +260,19 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
     SorCtl *ctl = (SorCtl *)c->d_flags;
     static_assert(sizeof(SorCtl) <= 64 * sizeof(int), "ctl block too large");
 
-    const int T = (rb_point && cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
+    int T = (rb_point && cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
+    if (c->world > 1) {
+        if (!(rb_point && cart && nx >= 254)) {
+            w2_set_error("multi-GPU runs support ppe_solver 5/6 on a Cartesian grid with nx >= 254 only");
+            return W2_ERR_UNSUPPORTED;
+        }
+        if (T == 0) T = 2;   // the plain half-sweep kernels have no slab path
+    }
     dim3 g2((nx - 1 + 255) / 256, (ny - 1) < 2048 ? (ny - 1) : 2048);
-    div_rhs_kernel<<<g2, 256, 0, c->stream>>>(nx, ny, pitch, par.dk, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv, u, v,
+    // every held row whose stencil is held too: on several GPUs this covers the halo rows the fused SOR
+    // pass reads (their us, vs are valid), so b needs no exchange of its own
+    const int bj0 = c->A0 + 1 > 2 ? c->A0 + 1 : 2, bj1 = c->A1 - 1 < ny ? c->A1 - 1 : ny;
+    div_rhs_kernel<<<g2, 256, 0, c->stream>>>(nx, bj0, bj1, pitch, par.dk, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv, u, v,
                                               c->pmask, has_mask, T > 0, b, cart ? nullptr : c->div);
     c->launches[2]++;
     if (T > 0) {
@@ -272,7 +282,7 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
         int iters = 0;
         cudaEventRecord(c->ev[4], c->stream);
         W2_TRY(w2_sor_fused(c, p, c->div, T, nSorConv, converged, &pf, &iters));
-        if (pf != p) W2_CUDA(cudaMemcpyAsync(p, pf, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (pf != p) W2_TRY(w2_copy_field(c, p, pf));
         cudaEventRecord(c->ev[5], c->stream);
         W2_CUDA(cudaStreamSynchronize(c->stream));
         float ms = 0.f;

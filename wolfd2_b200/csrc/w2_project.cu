@@ -44,13 +44,18 @@ int w2_project(wolfd2_ctx *c, const double *p, double *u, double *v) {
         const int uhi = (bE == W2_BM_INTERN || bE == W2_BM_OUTLT1) ? iE : iE - 1;
         const int vlo = (bS == W2_BM_OUTLT1) ? jS : jS + 1;
         const int vhi = (bN == W2_BM_INTERN || bN == W2_BM_OUTLT1) ? jN : jN - 1;
-        const int jbase = vlo < jS + 1 ? vlo : jS + 1;
-        const int jtop = jN;
+        // rows of this rank only (all rows on one GPU)
+        int ujlo = jS + 1, ujhi = jN, vjlo = vlo, vjhi = vhi;
+        w2_clip(c, ujlo, ujhi);
+        w2_clip(c, vjlo, vjhi);
+        if (ujhi < ujlo && vjhi < vjlo) continue;
+        const int jbase = (vjhi < vjlo || ujlo < vjlo) && ujhi >= ujlo ? ujlo : vjlo;
+        const int jtop = ujhi > vjhi ? ujhi : vjhi;
         int gy = jtop - jbase + 1;
         if (gy > 4096) gy = 4096;
         if (gy < 1) gy = 1;
         dim3 grid((c->nx + 2 + 255) / 256, gy);
-        project_region_kernel<<<grid, 256, 0, c->stream>>>(c->pitch, c->par.dk, ulo, uhi, jS + 1, jN, iW + 1, iE, vlo, vhi,
+        project_region_kernel<<<grid, 256, 0, c->stream>>>(c->pitch, c->par.dk, ulo, uhi, ujlo, ujhi, iW + 1, iE, vjlo, vjhi,
                                                            c->met.dju, c->met.djv, c->met.yeu, c->met.xzv, c->met.yzu,
                                                            c->met.xev, p, u, v, jbase);
         c->launches[3]++;
@@ -77,10 +82,8 @@ int w2_filter(wolfd2_ctx *c, int ncomp, double fp, double *qu) {
         w2_set_error("Wrong ncomp flag passed to Filter: %d (device supports _U_, _V_)", ncomp);  // :232-234
         return W2_ERR_BAD_ARG;
     }
-    if (!c->qh) {
-        W2_CUDA(cudaMalloc((void **)&c->qh, c->nelem * sizeof(double)));
-    }
-    W2_CUDA(cudaMemcpyAsync(c->qh, qu, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // :72-76
+    if (!c->qh) W2_TRY(w2_alloc_field(c, &c->qh));
+    W2_TRY(w2_copy_field(c, c->qh, qu));  // :72-76
     const W2Regions &R = c->hreg;
     for (int q = 0; q < R.nreg; ++q) {
         if (R.type[q] == W2_RM_BLOCKG) continue;
@@ -97,6 +100,7 @@ int w2_filter(wolfd2_ctx *c, int ncomp, double fp, double *qu) {
             jlo = (bS == W2_BM_OUTLT1) ? jS : jS + 1;
             jhi = (bN == W2_BM_INTERN || bN == W2_BM_OUTLT1) ? jN : jN - 1;
         }
+        w2_clip(c, jlo, jhi);
         if (ihi < ilo || jhi < jlo) continue;
         int gy = jhi - jlo + 1;
         if (gy > 4096) gy = 4096;
@@ -104,30 +108,34 @@ int w2_filter(wolfd2_ctx *c, int ncomp, double fp, double *qu) {
         filter_region_kernel<<<grid, 256, 0, c->stream>>>(c->pitch, fp, ilo, ihi, jlo, jhi, qu, c->qh);
         c->launches[3]++;
     }
-    W2_CUDA(cudaMemcpyAsync(qu, c->qh, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // :238-243
+    W2_TRY(w2_copy_field(c, qu, c->qh));  // :238-243
     W2_CUDA(cudaGetLastError());
+    if (c->world > 1) {   // the filtered field's halo rows come from their owners
+        double *f[1] = {qu};
+        W2_TRY(w2_halo_exchange(c, f, 1, c->HG));
+    }
     return W2_OK;
 }
 
 int w2_copy_field(wolfd2_ctx *c, double *dst, const double *src) {
-    W2_CUDA(cudaMemcpyAsync(dst, src, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    W2_CUDA(cudaMemcpyAsync(dst + c->row_off, src + c->row_off, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return W2_OK;
 }
 
 // ---------------------------------------------------------------------------- max-norms
 // DIFF: max |a-b|, seed (2,2) (:459); else max |a|, seed (5,5) (:493); both scan 2..nx-1,2..ny-1.
 template <bool DIFF>
-__global__ void __launch_bounds__(256) maxnorm_kernel(int nx, int ny, int pitch, const double *__restrict__ a,
+__global__ void __launch_bounds__(256) maxnorm_kernel(int nx, int jlo, int jhi, int seed, int pitch, const double *__restrict__ a,
                                                       const double *__restrict__ b, unsigned long long *slot) {
     __shared__ double red[32];
     double m = 0.0;
     const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= nx - 1)
-        for (int j = 2 + blockIdx.y; j <= ny - 1; j += gridDim.y) {
+        for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
             const double x = DIFF ? fabs(a[IDX(i, j)] - b[IDX(i, j)]) : fabs(a[IDX(i, j)]);
             m = fmax(m, x);
         }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (seed && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         const double s = DIFF ? fabs(a[IDX(2, 2)] - b[IDX(2, 2)]) : fabs(a[IDX(5, 5)]);
         m = fmax(m, s);
     }
@@ -140,26 +148,31 @@ int w2_norm_reset(wolfd2_ctx *c) {
     return W2_OK;
 }
 int w2_diffmaxnorm_async(wolfd2_ctx *c, const double *a, const double *b, int slot) {
-    int gy = c->ny - 2;
+    int jlo = 2, jhi = c->ny - 1;
+    w2_clip(c, jlo, jhi);
+    int gy = jhi - jlo + 1;
     if (gy > 1024) gy = 1024;
     if (gy < 1) gy = 1;
     dim3 grid((c->nx - 2 + 255) / 256, gy);
-    maxnorm_kernel<true><<<grid, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, a, b, c->d_norm + slot);
+    maxnorm_kernel<true><<<grid, 256, 0, c->stream>>>(c->nx, jlo, jhi, c->rank == 0, c->pitch, a, b, c->d_norm + slot);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
 int w2_dmaxnorm_async(wolfd2_ctx *c, const double *a, int slot) {
-    int gy = c->ny - 2;
+    int jlo = 2, jhi = c->ny - 1;
+    w2_clip(c, jlo, jhi);
+    int gy = jhi - jlo + 1;
     if (gy > 1024) gy = 1024;
     if (gy < 1) gy = 1;
     dim3 grid((c->nx - 2 + 255) / 256, gy);
-    maxnorm_kernel<false><<<grid, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, a, a, c->d_norm + slot);
+    maxnorm_kernel<false><<<grid, 256, 0, c->stream>>>(c->nx, jlo, jhi, c->rank == 0, c->pitch, a, a, c->d_norm + slot);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
 int w2_norm_fetch(wolfd2_ctx *c, int nslots, double *out) {
+    W2_TRY(w2_allreduce_max_u64(c, c->d_norm, nslots));
     W2_CUDA(cudaMemcpyAsync(c->h_norm, c->d_norm, nslots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     W2_CUDA(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < nslots; ++k) memcpy(&out[k], &c->h_norm[k], 8);

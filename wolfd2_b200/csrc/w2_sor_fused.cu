@@ -46,6 +46,8 @@ struct SorFCtl {           // device-resident loop control
 
 struct SorFArgs {
     int nx, ny, pitch;
+    int j0, j1;            // unknown rows relaxed by this launch: 2..ny, or this rank's slab
+    int ext_decide;        // 1: the pass is closed by sorf_decide_kernel after the max-norms were all-reduced
     int nstrips, nbands, rows_per_band, own_w;
     int msorit;
     double sorrel, sortol;
@@ -106,6 +108,31 @@ __global__ void sorf_ctl_reset(SorFCtl *c) {
     c->last_dif = 0ull;
 }
 
+// End of a pass of Tp fused iterations: test `m > 1 .and. dif < sortol` (:534) for each of them in order.
+__device__ __forceinline__ void sorf_close_pass(SorFCtl *ctl, int Tp, int cur, double sortol, int msorit) {
+    const int m = ctl->m;
+    int conv_t = -1;
+    unsigned long long last = 0ull;
+    for (int t = 0; t < Tp; ++t) {
+        const unsigned long long bits = atomicExch(&ctl->slot[t], 0ull);
+        last = bits;
+        const double dif = __longlong_as_double((long long)bits);
+        if (conv_t < 0 && (m + t + 1) > 1 && dif < sortol) conv_t = t;
+    }
+    ctl->ticket = 0;
+    if (ctl->redo > 0) {                       // this was the repeat of a converged prefix
+        ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1; ctl->redo = 0;
+    } else if (conv_t == Tp - 1) {             // converged exactly at the end of the pass
+        ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1;
+    } else if (conv_t >= 0) {                  // converged mid-pass: repeat conv_t+1 iterations
+        ctl->redo = conv_t + 1;
+    } else {
+        ctl->m = m + Tp; ctl->cur = cur ^ 1;
+        if (m + Tp >= msorit) ctl->done = 1;
+    }
+    ctl->last_dif = last;
+}
+
 template <int T> struct SorFCfg {
     static constexpr int R = (T == 1) ? 8 : 13;      // ring depth in rows (T=2: 108 KB -> two CTAs per SM)
     static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
@@ -146,8 +173,8 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
     const int own_lo = physL ? 2 : i0 + H;                             // owned columns (global i)
     const int own_hi = physR ? nx : min(nx, i0 + H + a.own_w - 1);
     // rows: band owns [jA, jB]; loads [jL0, jL1]; ring slot of a row = (row - jL0) mod R
-    const int jA = 2 + band * a.rows_per_band;
-    const int jB = min(ny, jA + a.rows_per_band - 1);
+    const int jA = a.j0 + band * a.rows_per_band;
+    const int jB = min(a.j1, jA + a.rows_per_band - 1);
     const int jL0 = max(1, jA - H), jL1 = min(ny + 1, jB + H);
 
     if (tid == 0) {
@@ -280,35 +307,23 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         if (tid == 0 && t < Tp) atomicMax(&ctl->slot[t], w2_dbits(m));
     }
     // ---- the last CTA closes the pass
-    if (tid == 0) {
+    if (tid == 0 && !a.ext_decide) {
         __threadfence();
         const int total = gridDim.x * gridDim.y;
         if (atomicAdd(&ctl->ticket, 1) == total - 1) {
             __threadfence();
-            int m = ctl->m;
-            int conv_t = -1;
-            unsigned long long last = 0ull;
-            for (int t = 0; t < Tp; ++t) {
-                const unsigned long long bits = atomicExch(&ctl->slot[t], 0ull);
-                last = bits;
-                const double dif = __longlong_as_double((long long)bits);
-                if (conv_t < 0 && (m + t + 1) > 1 && dif < a.sortol) conv_t = t;   // :534
-            }
-            ctl->ticket = 0;
-            if (ctl->redo > 0) {                       // this was the repeat of a converged prefix
-                ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1; ctl->redo = 0;
-            } else if (conv_t == Tp - 1) {             // converged exactly at the end of the pass
-                ctl->m = m + Tp; ctl->nconv = m + Tp; ctl->done = 1; ctl->cur = cur ^ 1;
-            } else if (conv_t >= 0) {                  // converged mid-pass: repeat conv_t+1 iterations
-                ctl->redo = conv_t + 1;
-            } else {
-                ctl->m = m + Tp; ctl->cur = cur ^ 1;
-                if (m + Tp >= a.msorit) ctl->done = 1;
-            }
-            ctl->last_dif = last;
+            sorf_close_pass(ctl, Tp, cur, a.sortol, a.msorit);
             __threadfence();
         }
     }
+}
+
+// Several GPUs: every rank's slots hold the max over its slab; after the all-reduce one thread per rank
+// takes the (identical) decision the last CTA takes on one GPU.
+__global__ void sorf_decide_kernel(SorFCtl *ctl, int T, double sortol, int msorit) {
+    if (ctl->done) return;
+    const int Tp = ctl->redo > 0 ? ctl->redo : min(T, msorit - ctl->m);
+    sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
 }
 
 // interleaved (reference order, i fastest) <-> colour-split rows.  TO_SPLIT: dst[j][ (i&1)*hp + i/2 ] = src[j][i]
@@ -329,6 +344,7 @@ __global__ void __launch_bounds__(256) sorf_pack_kernel(int pitch, int rows, con
 int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
     const int rows = c->rows + 1;
     dim3 grid((c->pitch + 255) / 256, rows < 2048 ? rows : 2048);
+    src += c->row_off; dst += c->row_off;   // the kernel walks the held rows from 0
     if (to_split) sorf_pack_kernel<true><<<grid, 256, 0, c->stream>>>(c->pitch, rows, src, dst);
     else sorf_pack_kernel<false><<<grid, 256, 0, c->stream>>>(c->pitch, rows, src, dst);
     c->launches[2]++;
@@ -357,10 +373,7 @@ static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done) {
     for (int k = 0; k < 4; ++k)
-        if (!c->sorf_buf[k]) {
-            W2_CUDA(cudaMalloc((void **)&c->sorf_buf[k], c->nelem * sizeof(double)));
-            W2_CUDA(cudaMemsetAsync(c->sorf_buf[k], 0, c->nelem * sizeof(double), c->stream));
-        }
+        if (!c->sorf_buf[k]) W2_TRY(w2_alloc_field(c, &c->sorf_buf[k]));
     double *pA = c->sorf_buf[0], *pB = c->sorf_buf[1], *rauS = c->sorf_buf[2], *rgvS = c->sorf_buf[3];
     (void)scratch;
     W2_TRY(w2_sorf_pack(c, p, pA, true));
@@ -372,6 +385,8 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     static_assert(sizeof(SorFCtl) <= 64 * sizeof(int), "ctl block too large");
     SorFArgs a;
     a.nx = nx; a.ny = ny; a.pitch = c->pitch;
+    a.j0 = c->J0; a.j1 = c->J1; a.ext_decide = c->world > 1;
+    const int nrows = c->J1 - c->J0 + 1;
     a.own_w = SF_W - 4 * T;
     a.nstrips = 1;
     while ((a.nstrips - 1) * a.own_w + SF_W < nx + 2) a.nstrips++;
@@ -390,9 +405,9 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     }
     int want = (per_sm * c->num_sms) / a.nstrips;
     if (want < 1) want = 1;
-    a.rows_per_band = (ny - 1 + want - 1) / want;
+    a.rows_per_band = (nrows + want - 1) / want;
     if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
-    a.nbands = (ny - 1 + a.rows_per_band - 1) / a.rows_per_band;
+    a.nbands = (nrows + a.rows_per_band - 1) / a.rows_per_band;
     a.msorit = par.msorit; a.sorrel = par.sorrel; a.sortol = par.sortol;
     a.rau = rauS; a.rgv = rgvS; a.b = c->fld[W2_F_B];
     a.pA = pA; a.pB = pB; a.ctl = ctl;
@@ -400,11 +415,11 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
 
     // the ghost ring of p is frozen during the solve (:431-446 never touches it): give the second
     // buffer the same ghosts
-    W2_CUDA(cudaMemcpyAsync(pB, pA, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    W2_TRY(w2_copy_field(c, pB, pA));
     sorf_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
     const int passes_total = (par.msorit + T - 1) / T + 1;
-    const double cells = (double)(nx - 1) * (double)(ny - 1);
-    int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + 4.0e-6));
+    const double cells = (double)(nx - 1) * (double)nrows;
+    int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + (c->world > 1 ? 4.0e-5 : 4.0e-6)));
     if (chunk < 4) chunk = 4;
     if (chunk > 128) chunk = 128;
     SorFCtl h;
@@ -423,6 +438,16 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
             if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
             else W2_TRY(launch_fused<2>(c, a, grid));
             c->launches[2]++;
+            if (c->world > 1) {
+                // slab run: global max-norms, the common decision, then the 2T halo rows of the iterate.
+                // Which buffer was written is known on the device only; the other one's halos are already
+                // right, so both are exchanged (a few hundred KB).
+                W2_TRY(w2_allreduce_max_u64(c, ctl->slot, T));
+                sorf_decide_kernel<<<1, 1, 0, c->stream>>>(ctl, T, par.sortol, par.msorit);
+                c->launches[2]++;
+                double *pp[2] = {pA, pB};
+                W2_TRY(w2_halo_exchange(c, pp, 2, 2 * T));
+            }
         }
         queued += n;
         W2_CUDA(cudaGetLastError());

@@ -7,6 +7,13 @@
 
 // ------------------------------------------------------------------------------ residency API
 
+// slab runs: Project (like the QL update and Filter) changes owned rows only; refresh the halo rows
+static int exchange_uv(wolfd2_ctx *c, double *u, double *v) {
+    if (c->world == 1) return W2_OK;
+    double *f[2] = {u, v};
+    return w2_halo_exchange(c, f, 2, c->HG);
+}
+
 extern "C" int wolfd2_b200_coldstart(wolfd2_ctx *c, int32_t *nSorConv) {
     if (!c) return W2_ERR_BAD_ARG;
     W2_CUDA(cudaSetDevice(c->device));
@@ -16,6 +23,7 @@ extern "C" int wolfd2_b200_coldstart(wolfd2_ctx *c, int32_t *nSorConv) {
     W2_TRY(w2_ppe(c, u, v, p, &nconv, &conv));     // :613
     W2_TRY(w2_pres_bc(c, p));                      // :623
     W2_TRY(w2_project(c, p, u, v));                // :629
+    W2_TRY(exchange_uv(c, u, v));
     W2_TRY(w2_vel_bc(c, u, v));                    // :637
     W2_CUDA(cudaStreamSynchronize(c->stream));
     if (nSorConv) *nSorConv = nconv;
@@ -50,6 +58,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     cudaEventRecord(c->ev[3], s);
     W2_TRY(w2_pres_bc(c, p));                       // :813
     W2_TRY(w2_project(c, p, us, vs));               // :820
+    W2_TRY(exchange_uv(c, us, vs));
     W2_TRY(w2_vel_bc(c, us, vs));                   // :829
     W2_TRY(w2_pres_bc(c, p));                       // :833
     W2_TRY(w2_copy_field(c, u, us));                // :864-870

@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(256) tri_finalize_kernel(long long n, const do
 // ---------------------------------------------------------------------- host driver
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-int w2_tri_prepare(wolfd2_ctx *c, long long nmax) {
+// nmax: unknowns of the (global) chain, sizes the segment tables and the upper levels; cap0: unknowns whose
+// level-0 spikes this rank stores (= nmax on one GPU)
+int w2_tri_prepare(wolfd2_ctx *c, long long nmax, long long cap0) {
     W2TriWork &w = c->tri;
     memset(&w, 0, sizeof(w));
-    w.cap = round_up(nmax, TRI_S) + TRI_S;
+    w.cap = round_up(cap0, TRI_S) + TRI_S;
     W2_CUDA(cudaMalloc((void **)&w.Y0, w.cap * sizeof(double)));
     W2_CUDA(cudaMalloc((void **)&w.V0, w.cap * sizeof(double)));
     W2_CUDA(cudaMalloc((void **)&w.W0, w.cap * sizeof(double)));

@@ -335,6 +335,9 @@ class Deck:
     fpv: float = 5e2
     x_nodes: np.ndarray = field(default=None, repr=False)
     y_nodes: np.ndarray = field(default=None, repr=False)
+    # one rank's share of a multi-GPU run: (rank, world, J0, J1, A0, A1, HG), wolfd2_b200/slab.py.  nx, ny,
+    # regions and params stay global; metrics and fields hold rows A0..A1 only (row 0 = global row A0)
+    slab: tuple = None
 
     @property
     def dk(self):  # src/file_manip.f:134
@@ -366,7 +369,28 @@ class Deck:
         return field2d(self.mnx, self.mny)
 
     def cells(self) -> int:
+        """Pressure unknowns (of this rank's slab, if any)."""
+        if self.slab:
+            return (self.nx - 1) * (self.slab[3] - self.slab[2] + 1)
         return (self.nx - 1) * (self.ny - 1)
+
+    def window(self, f_global: np.ndarray) -> np.ndarray:
+        """This rank's rows of a global field, in the local host layout."""
+        if not self.slab:
+            return f_global
+        a0, a1 = self.slab[4], self.slab[5]
+        out = self.new_field()
+        out[0:a1 - a0 + 1, :] = f_global[a0:a1 + 1, 0:self.mnx + 1]
+        return out
+
+    def to_slab(self, rank: int, world: int) -> "Deck":
+        """Cut a global deck into the share of `rank` (tests: slices the global metric arrays)."""
+        import dataclasses
+        from .slab import slab_layout
+        j0, j1, a0, a1, hg = slab_layout(self.nx, self.ny, world, rank)
+        d = dataclasses.replace(self, mny=a1 - a0, metrics={}, slab=(rank, world, j0, j1, a0, a1, hg))
+        d.metrics = {k: np.ascontiguousarray(v[a0:a1 + 1, :]) for k, v in self.metrics.items()}
+        return d
 
     # ---- reference-syntax files (SURVEY Appendix A) ---------------------------
     def write_reference_files(self, directory, n_time_steps=100):
@@ -438,8 +462,39 @@ class Deck:
                     f.write(" ".join(f"{v:.17g}" for v in flat[q:q + 4]) + "\n")
 
 
-def _mk(name, nx, ny, regions, re, dt, x=None, y=None, mnx=None, mny=None, **kw) -> Deck:
+def metrics_window(nx: int, ny: int, a0: int, a1: int, mnx: int, dlref: float = 1.0, lx: float = 1.0,
+                   ly: float = 1.0) -> dict:
+    """Metric arrays of a uniform grid on rows a0..a1 only (a multi-GPU rank never forms the global
+    arrays).  Every metric at row j is a formula of the node rows j-2..j+2, so running the same code on the
+    node rows a0-2..a1+2 and dropping the two rows at each cut reproduces the global values bit for bit
+    (the extrapolated mirror rows are right at the physical edges and discarded at the cuts)."""
+    lo, hi = max(1, a0 - 2), min(ny, a1 + 2)
+    xi = np.arange(nx, dtype=np.float64) / float(nx - 1) * lx
+    yj = np.arange(lo - 1, hi, dtype=np.float64) / float(ny - 1) * ly
+    nyw = hi - lo + 1
+    xw = np.broadcast_to(xi[None, :], (nyw, nx))
+    yw = np.broadcast_to(yj[:, None], (nyw, nx))
+    m = metrics_from_grid(xw, yw, mnx, nyw + 1, dlref)    # local row l <-> global row lo - 1 + l
+    out = {}
+    for k, v in m.items():
+        w = np.zeros((a1 - a0 + 1, mnx + 1))
+        g_lo, g_hi = max(a0, lo - 1), min(a1, hi + 1)          # rows 0 / ny+1 stay zero like the global arrays
+        w[g_lo - a0:g_hi - a0 + 1, :] = v[g_lo - (lo - 1):g_hi - (lo - 1) + 1, :]
+        out[k] = w
+    return out
+
+
+def _mk(name, nx, ny, regions, re, dt, x=None, y=None, mnx=None, mny=None, slab=None, **kw) -> Deck:
     mnx = mnx if mnx is not None else nx + 1   # smallest legal size, src/grid.f:551
+    if slab is not None:   # (rank, world): build this rank's rows directly (uniform grids)
+        from .slab import slab_layout
+        if x is not None:
+            raise ValueError("slab decks are built for uniform grids; cut others with Deck.to_slab")
+        rank, world = slab
+        j0, j1, a0, a1, hg = slab_layout(nx, ny, world, rank)
+        met = metrics_window(nx, ny, a0, a1, mnx, kw.get("dlref", 1.0))
+        return Deck(name=name, nx=nx, ny=ny, mnx=mnx, mny=a1 - a0, regions=regions.complete(), metrics=met,
+                    dt=dt, re=re, slab=(rank, world, j0, j1, a0, a1, hg), **kw)
     mny = mny if mny is not None else ny + 1
     if x is None:
         x, y = uniform_grid(nx, ny)

@@ -1,8 +1,8 @@
 """Host-side helpers for running the hot path on several GPUs of one node (one process per GPU).
 
 Row-slab decomposition in j: no tridiagonal line crosses a slab because both momentum split
-steps run along i.  Round 1 ships the partition arithmetic and the timing reduction; the
-device-side halo exchange is not implemented yet, so bench.py runs independent replicas at N > 1."""
+steps run along i.  The device side is csrc/w2_dist.cu; this module mirrors its partition
+arithmetic (checked against the library in tests) and carries the launcher-side helpers."""
 from __future__ import annotations
 
 
@@ -18,6 +18,47 @@ def slab_rows(ny: int, world: int, rank: int):
     j0 = 2 + rank * base + min(rank, rem)
     j1 = j0 + base + (1 if rank < rem else 0) - 1
     return j0, j1
+
+
+def halo_depth(nx: int, world: int) -> int:
+    """Halo rows on each side of a slab (w2_slab_layout in csrc/w2_context.cu): 2T = 4 rows for the fused
+    SOR pass, the rows a straddling 2048-unknown momentum segment reaches into, plus the stencil row."""
+    if world == 1:
+        return 0
+    return max(5, 4 + 2047 // (nx - 1))
+
+
+def slab_layout(nx: int, ny: int, world: int, rank: int):
+    """(J0, J1, A0, A1, HG): owned unknown rows, rows held in memory, halo depth."""
+    j0, j1 = slab_rows(ny, world, rank) if world > 1 else (2, ny)
+    hg = halo_depth(nx, world)
+    if world > 1 and (ny - 1) // world < 2 * hg:
+        raise ValueError(f"{ny - 1} rows cannot be split into {world} slabs of >= {2 * hg} rows")
+    a0 = 0 if rank == 0 else max(0, j0 - hg)
+    a1 = ny + 1 if rank == world - 1 else min(ny + 1, j1 + hg)
+    return j0, j1, a0, a1, hg
+
+
+def init_comm(dist, device_index: int):
+    """Create the library's NCCL communicator over the ranks of an initialised torch.distributed group:
+    rank 0 makes the id, the group broadcasts it (plumbing only), every rank joins."""
+    import ctypes as C
+    import torch
+    from . import api
+    L = api.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    api.set_device(device_index)
+    buf = (C.c_ubyte * 128)()
+    if rank == 0 and world > 1:
+        api._check(L.wolfd2_b200_comm_unique_id(buf), "comm_unique_id")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if world > 1:
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device_index)
+        dist.broadcast(t, 0)
+    ident = (C.c_ubyte * 128)(*[int(x) for x in t.cpu().tolist()])
+    api._check(L.wolfd2_b200_comm_init(rank, world, ident), "comm_init")
+    return rank, world
 
 
 def halo_rows(j0: int, j1: int, ny: int, depth: int):
