@@ -36,14 +36,24 @@ def stable_dt(n, re):
     return min(0.25 * h, 0.2 * re * h * h)
 
 
-def make_deck(workload, n, fixed_work, q_iters, s_iters):
+def global_ny(args, world):
+    """Weak scaling: every GPU keeps an n-row slab of an n x (n*world) grid; strong: the grid stays n x n."""
+    return args.n * world if args.scaling == "weak" else args.n
+
+
+def make_deck(workload, n, fixed_work, q_iters, s_iters, ny=None, slab=None):
     from wolfd2_b200 import deck as dk
+    ny = ny or n
+    kw = {"ny": ny}
+    if slab is not None:
+        kw["slab"] = slab          # (rank, world): this rank's rows only
+    nmax = max(n, ny)
     if workload == "cavity":
-        d = dk.cavity(n, re=1000.0, dt=stable_dt(n, 1000.0))
+        d = dk.cavity(n, re=1000.0, dt=stable_dt(nmax, 1000.0), **kw)
     elif workload == "channel":
-        d = dk.channel(n, re=100.0, dt=stable_dt(n, 100.0), fully_dev=True)
+        d = dk.channel(n, re=100.0, dt=stable_dt(nmax, 100.0), fully_dev=True, **kw)
     elif workload == "bstep":
-        d = dk.backward_step(n, re=100.0, dt=stable_dt(n, 100.0), fully_dev=True)
+        d = dk.backward_step(n, re=100.0, dt=stable_dt(nmax, 100.0), fully_dev=True, **kw)
     else:
         raise SystemExit(f"unknown workload {workload}")
     d.ppe_solver = "rb_sor"
@@ -58,15 +68,17 @@ def developed_state(d):
     """A smooth, non-quiescent restart field (one vortex filling the box) on the staggered locations of
     src/grid.f:337-359, so that the timed steps do not run on a mostly-zero cold start.  Returns u, v, p."""
     nx, ny = d.nx, d.ny
+    a0, a1 = (d.slab[4], d.slab[5]) if d.slab else (0, ny + 1)     # rows this rank holds
     u, v, p = d.new_field(), d.new_field(), d.new_field()
     xi = (np.arange(nx + 2) - 1.0) / (nx - 1.0)
-    yj = (np.arange(ny + 2) - 1.0) / (ny - 1.0)
+    yj = (np.arange(a0, a1 + 1) - 1.0) / (ny - 1.0)
     xh, yh = xi - 0.5 / (nx - 1.0), yj - 0.5 / (ny - 1.0)
     A = 0.2
+    nr = a1 - a0 + 1
     # psi = A sin^2(pi x) sin^2(pi y);  u = dpsi/dy at (x_i, y_{j-1/2}),  v = -dpsi/dx at (x_{i-1/2}, y_j)
-    u[:ny + 2, :nx + 2] = A * np.outer(np.pi * np.sin(2 * np.pi * yh), np.sin(np.pi * xi) ** 2)
-    v[:ny + 2, :nx + 2] = -A * np.outer(np.sin(np.pi * yj) ** 2, np.pi * np.sin(2 * np.pi * xh))
-    p[:ny + 2, :nx + 2] = 0.05 * np.outer(np.cos(np.pi * yh), np.cos(np.pi * xh))
+    u[:nr, :nx + 2] = A * np.outer(np.pi * np.sin(2 * np.pi * yh), np.sin(np.pi * xi) ** 2)
+    v[:nr, :nx + 2] = -A * np.outer(np.sin(np.pi * yj) ** 2, np.pi * np.sin(2 * np.pi * xh))
+    p[:nr, :nx + 2] = 0.05 * np.outer(np.cos(np.pi * yh), np.cos(np.pi * xh))
     return u, v, p
 
 
@@ -203,13 +215,15 @@ def run_reference(args):
     d = make_deck(args.workload, n, args.fixed_work, args.q_iters, args.s_iters)
     t, kind = cpu_steps(d, args.steps, warm=args.warmup)
     value = d.cells() * args.steps / t / 1e9
-    sample = (f"{args.workload} {n}x{n} (same deck family as the GPU arm's {args.n}x{args.n}; size bounded so the run "
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    nyg = global_ny(args, world)
+    sample = (f"{args.workload} {n}x{n} (same deck family as the GPU arm's {args.n}x{nyg}; size bounded so the run "
               f"ends in minutes), {args.steps} steps after {args.warmup} warm-up, 1 thread (the reference is serial)")
     line = {
         "impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, d),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, make_deck(args.workload, 256, args.fixed_work, args.q_iters, args.s_iters), world),
         "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "build": kind},
         "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,17 +232,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def config_dict(args, d):
-    return {"workload": f"{args.workload} {args.n}x{args.n} uniform grid, Re={d.re:g}, dt={d.dt:g}, ppe_solver rb_sor "
+def config_dict(args, d, world):
+    nyg = global_ny(args, world)
+    cells = (args.n - 1) * (nyg - 1)
+    re = d.re
+    dt = stable_dt(max(args.n, nyg), re)
+    return {"workload": f"{args.workload} {args.n}x{nyg} uniform grid, Re={re:g}, dt={dt:g}, ppe_solver rb_sor "
                         f"(BASELINE.json metric grid 4096^2; deck family of configs[{ {'channel': 2, 'cavity': 1, 'bstep': 2}[args.workload] }])",
             "mode": ("fixed-work: ql_tolerance 0, max_ql_iter %d, sor_tolerance 0, max_sor_iter %d" % (args.q_iters, args.s_iters))
             if args.fixed_work else "converged: ql_tolerance 1e-4, sor_tolerance 1e-8, max_sor_iter 2000",
-            "grid": [d.nx, d.ny], "cells": d.cells(),
-            "l2": "working set (>= 40 arrays x %.0f MB) exceeds the 126 MB L2; no flush needed" % (d.cells() * 8 / 1e6)
-            if d.cells() * 8 * 4 > 126e6 else "working set fits L2 (latency-bound regime)",
-            "parallelism": "1 GPU" if args.gpus == 1 else
-            f"{args.gpus} independent replicas, one per GPU (slab decomposition with halo exchange is not "
-            f"implemented yet: DESIGN.md section 7)"}
+            "grid": [args.n, nyg], "cells": cells,
+            "l2": "working set (>= 40 arrays x %.0f MB per GPU) exceeds the 126 MB L2; no flush needed" % (cells / world * 8 / 1e6)
+            if cells / world * 8 * 4 > 126e6 else "working set fits L2 (latency-bound regime)",
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} row slabs of ~{(nyg - 1) // world} rows, one process per GPU; NCCL halo exchange of us,vs per QL "
+            f"iteration and of p per fused SOR pass, all-reduced max-norms and tridiagonal segment records "
+            f"(wolfd2_b200/csrc/w2_dist.cu); results bit-identical to one GPU"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -244,8 +263,15 @@ def run_gpu(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api.set_device(local)
-    d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters)
-    cells = d.cells()
+    from wolfd2_b200 import slab
+    nyg = global_ny(args, world)
+    if world > 1:
+        slab.init_comm(dist, local)     # the library's own NCCL communicator; torch only carries the id
+        d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters, ny=nyg, slab=(rank, world))
+    else:
+        d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters)
+    cells = (d.nx - 1) * (d.ny - 1)          # pressure unknowns of the whole grid
+    cells_local = (d.nx - 1) * (d.slab[3] - d.slab[2] + 1) if d.slab else cells
     ctx = api.Context(d)
     for w, f in zip((api.F_U, api.F_V, api.F_P), developed_state(d)):
         ctx.upload(w, f)
@@ -272,9 +298,8 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = tm["total_ms"]
     launches = sum(tm["launches"].values()) - sum(l0.values())
-    from wolfd2_b200 import slab
     dev_ms = slab.max_over_ranks(dev_ms, dist, "cuda" if dist is not None else None)
-    value = cells * world * args.steps / (dev_ms * 1e-3) / 1e9
+    value = cells * args.steps / (dev_ms * 1e-3) / 1e9
     sor_iters = tm["sor_iters"]
     fused_T = int(os.environ.get("W2_SOR_T", "2"))
     iters_per_launch = fused_T if fused_T > 0 else 0.5          # T=0: one launch per colour half-sweep
@@ -295,21 +320,24 @@ def run_gpu(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_s = slab.max_over_ranks(e2e_s, dist, "cuda" if dist is not None else None)
-    e2e = cells * world * args.steps / e2e_s / 1e9
+    e2e = cells * args.steps / e2e_s / 1e9
     for nm, f in (("u", hu), ("v", hv), ("p", hp)):   # the timed run must have produced a sane flow
         if not np.isfinite(f).all() or np.abs(f).max() > 1.0e3:
             raise SystemExit(f"bench: field {nm} is not finite/bounded after the run (max {np.abs(f).max()})")
-    copy_bytes = 3 * (d.nx + 2) * (d.ny + 2) * 8
+    rows_held = (d.slab[5] - d.slab[4] + 1) if d.slab else d.ny + 2
+    copy_bytes = 3 * (d.nx + 2) * rows_held * 8 * world     # all ranks (their slabs are equal to within a row)
     for q in (pu, pv, pp):
         api.pinned_free(q)
     ctx.close()
+    if world > 1:
+        api.comm_finalize()
 
     if rank != 0:
         return
     peak, peak_src = measured_peak()
     # dominant kernel: the red/black SOR pass; one R/B iteration = 64 algorithmic B/cell,
     # a launch covers iters_per_launch iterations
-    alg_launch = cells * 64.0 * iters_per_launch
+    alg_launch = cells_local * 64.0 * iters_per_launch       # per GPU
     achieved = alg_launch / (sor_launch_ms * 1e-3) / 1e9 if sor_iters else 0.0
     kname = (f"sor_rb_fused_kernel<{fused_T}> ({fused_T} red+black iteration(s) per launch)" if fused_T > 0
              else "sor_rb_sweep (one colour half-sweep per launch)")
@@ -318,8 +346,9 @@ def run_gpu(args):
     line = {
         "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (uniform grid, analytic one-vortex restart field)",
-        "config": config_dict(args, d),
+        "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (uniform grid, analytic one-vortex restart field)",
+        "config": config_dict(args, d, world),
         "steps_per_s": args.steps / (dev_ms * 1e-3),
         "iterations": {"ql_per_step": float(np.mean(q_done)), "sor_per_step": float(np.mean(s_done))},
         "step_roofline": {"algorithmic_GB_per_step": step_bytes / 1e9,
@@ -333,7 +362,9 @@ def run_gpu(args):
                      "traffic": (tr or {}).get("dram_bytes_per_launch")
                      if (tr and tr.get("cells") == cells and tr.get("iterations_per_launch") == iters_per_launch) else None,
                      "note": "achieved counts ALGORITHMIC bytes; the fused kernel moves fewer (see traffic), "
-                             "so frac can exceed what a copy kernel reaches"},
+                             "so frac can exceed what a copy kernel reaches"
+                             + ("; per GPU, and at N>1 avg_launch_ms includes the NCCL all-reduce and halo exchange "
+                                "that follow every pass" if world > 1 else "")},
         "e2e": {"value": e2e, "unit": "Gcell-updates/s", "h2d_bytes_per_step": copy_bytes,
                 "d2h_bytes_per_step": copy_bytes, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches),
@@ -365,6 +396,8 @@ def main():
     ap.add_argument("--q-iters", type=int, default=2)
     ap.add_argument("--s-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = n x (n*N) grid, n rows per GPU; strong = the n x n grid cut into N slabs")
     args = ap.parse_args()
     args.fixed_work = args.mode == "fixed"
     if args.warmup < 3 and args.impl == "ours":

@@ -61,3 +61,92 @@ def test_gloo_world2_timing_reduction_and_neighbour_agreement():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out[0][0] == out[1][0] == 11.0
     assert out[0][1] and out[1][1]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# slab layout / slab decks (the host side of csrc/w2_dist.cu)
+
+def test_slab_layout_matches_library():
+    """wolfd2_b200/slab.py and the library compute the same partition (pure arithmetic, no GPU needed)."""
+    from wolfd2_b200 import api
+    for nx, ny, world in [(300, 120, 2), (512, 2048, 2), (4096, 4096, 8), (4096, 32768, 8), (260, 400, 3), (64, 64, 1)]:
+        for r in range(world):
+            assert api.slab_layout(nx, ny, world, r) == slab.slab_layout(nx, ny, world, r)
+    j0, j1, a0, a1, hg = slab.slab_layout(4096, 4096, 8, 3)
+    assert hg == 5 and a0 == j0 - 5 and a1 == j1 + 5
+    assert slab.slab_layout(300, 120, 2, 0)[4] == 10      # a 2048-unknown segment spans 7 rows of 299
+    with pytest.raises(ValueError):
+        slab.slab_layout(300, 40, 2, 0)                   # slabs must hold at least two halo depths
+    with pytest.raises(api.Wolfd2Error):
+        api.slab_layout(300, 40, 2, 0)
+
+
+def test_slab_deck_metrics_are_the_global_ones():
+    """A rank builds its metric rows from a node window; they must be bit-identical to the global arrays."""
+    import numpy as np
+    from wolfd2_b200 import deck
+    for nx, ny, world in [(300, 200, 2), (260, 97, 3), (300, 400, 4)]:
+        g = deck.cavity(nx, ny=ny, re=100.0)
+        held = np.zeros(ny + 2, dtype=int)
+        for r in range(world):
+            d = deck.cavity(nx, ny=ny, re=100.0, slab=(r, world))
+            cut = g.to_slab(r, world)
+            assert d.slab == cut.slab and d.mny == cut.mny
+            _, _, j0, j1, a0, a1, hg = d.slab
+            held[j0:j1 + 1] += 1
+            for k in d.metrics:
+                if not k.startswith("_"):
+                    assert np.array_equal(d.metrics[k], cut.metrics[k]), (nx, ny, world, r, k)
+            f = g.new_field()
+            f[:] = np.arange(f.size).reshape(f.shape)
+            assert np.array_equal(d.window(f)[:a1 - a0 + 1], f[a0:a1 + 1, :d.mnx + 1])
+        assert (held[2:ny + 1] == 1).all()                # every unknown row has exactly one owner
+
+
+def _halo_worker(rank, world, port, out):
+    """Replays w2_halo_exchange's row arithmetic with gloo send/recv on slab windows of one global field."""
+    import numpy as np
+    from wolfd2_b200 import deck
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = deck.cavity(300, ny=160, re=100.0)
+        d = g.to_slab(rank, world)
+        _, _, j0, j1, a0, a1, hg = d.slab
+        rng = np.random.default_rng(5)
+        f = g.new_field()
+        f[:] = rng.standard_normal(f.shape)
+        w = d.window(f).copy()
+        w[:j0 - a0] = 0.0                                   # wipe the halos, then refill them from the owners
+        w[j1 - a0 + 1:] = 0.0 if rank < world - 1 else w[j1 - a0 + 1:]
+        if rank == 0:
+            w[:2] = d.window(f)[:2]                         # rows 0,1 belong to rank 0
+        reqs = []
+        t = torch.from_numpy(w)
+        if rank + 1 < world:
+            reqs.append(dist.isend(t[j1 - hg + 1 - a0:j1 + 1 - a0].clone(), rank + 1))
+            up = torch.zeros(hg, t.shape[1], dtype=torch.float64)
+            reqs.append(dist.irecv(up, rank + 1))
+        if rank > 0:
+            reqs.append(dist.isend(t[j0 - a0:j0 + hg - a0].clone(), rank - 1))
+            dn = torch.zeros(hg, t.shape[1], dtype=torch.float64)
+            reqs.append(dist.irecv(dn, rank - 1))
+        for q in reqs:
+            q.wait()
+        if rank + 1 < world:
+            t[j1 + 1 - a0:j1 + 1 + hg - a0] = up
+        if rank > 0:
+            t[j0 - hg - a0:j0 - a0] = dn
+        out[rank] = bool(np.array_equal(w[:a1 - a0 + 1], d.window(f)[:a1 - a0 + 1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_halo_rows_reassemble_the_global_field():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29100 + (os.getpid() % 500)
+    mp.spawn(_halo_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
