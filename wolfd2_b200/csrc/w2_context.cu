@@ -240,6 +240,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);
     ffree(c, c->dus); ffree(c, c->dvs); ffree(c, c->div); ffree(c, c->x1); ffree(c, c->qh);
     bfree(c, c->pmask); bfree(c, c->xmask); bfree(c, c->ymask); bfree(c, c->pormap);
+    w2_peer_release(c);   // before the buffers the peers have mapped go away
     for (int k = 0; k < 4; ++k) ffree(c, c->sorf_buf[k]);
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
     w2_tri_release(c);

@@ -13,6 +13,7 @@
 // NCCL is loaded with dlopen so that the library still loads on machines without it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "w2.cuh"
@@ -23,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -36,7 +38,7 @@ int load_nccl() {
     N.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!N.h) { w2_set_error("multi-GPU run needs NCCL: dlopen(libnccl.so.2) failed: %s", dlerror()); return W2_ERR_UNSUPPORTED; }
 #define LOAD(sym) *(void **)(&N.sym) = dlsym(N.h, "nccl" #sym); if (!N.sym) { w2_set_error("NCCL symbol nccl" #sym " missing"); return W2_ERR_UNSUPPORTED; }
-    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Send) LOAD(Recv) LOAD(GroupStart) LOAD(GroupEnd)
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(AllGather) LOAD(Send) LOAD(Recv) LOAD(GroupStart) LOAD(GroupEnd)
     LOAD(GetErrorString)
 #undef LOAD
     return W2_OK;
@@ -131,4 +133,88 @@ int w2_send_recv_pieces(wolfd2_ctx *c, const W2Piece *up, int nup, const W2Piece
     W2_NCCL(N.GroupEnd());
     c->launches[0] += 1;
     return W2_OK;
+}
+
+// ---- peer memory for the fused SOR loop ----------------------------------------------------------------
+// Every rank exports its two colour-split pressure buffers and its mailbox with CUDA IPC; the handles travel
+// by one ncclAllGather.  Afterwards the SOR passes need no NCCL call: the kernel stores its edge rows
+// straight into the neighbours' halo rows and its max-norms into every rank's mailbox over NVLink.
+// Set W2_SOR_P2P=0 to keep the NCCL path (all-reduce + send/recv after every pass).
+int w2_peer_setup(wolfd2_ctx *c) {
+    W2Peer &P = c->peer;
+    if (P.state != 0) return W2_OK;
+    P.state = -1;
+    const char *e = getenv("W2_SOR_P2P");
+    // every rank must take the same branch: the decision depends only on the environment and the world size
+    if (c->world == 1 || c->world > W2_MAXRANKS || (e && atoi(e) == 0)) return W2_OK;
+    struct Handles { cudaIpcMemHandle_t a, b, m; int ok; int pad[15]; };
+    static_assert(sizeof(Handles) % 8 == 0, "handle record must be a multiple of 8 bytes");
+    Handles mine;
+    memset(&mine, 0, sizeof(mine));
+    W2Mail *mail = nullptr;
+    bool ok = cudaMalloc((void **)&mail, sizeof(W2Mail)) == cudaSuccess && cudaMemset(mail, 0, sizeof(W2Mail)) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.a, c->sorf_buf[0] + c->row_off) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.b, c->sorf_buf[1] + c->row_off) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.m, mail) == cudaSuccess;
+    mine.ok = ok ? 1 : 0;
+    cudaGetLastError();
+    Handles *d_all = nullptr, *h_all = (Handles *)malloc(sizeof(Handles) * c->world);
+    W2_CUDA(cudaMalloc((void **)&d_all, sizeof(Handles) * c->world));
+    W2_CUDA(cudaMemcpyAsync(d_all + c->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, c->stream));
+    W2_NCCL(N.AllGather(d_all + c->rank, d_all, sizeof(Handles), ncclChar, g_comm, c->stream));
+    W2_CUDA(cudaMemcpyAsync(h_all, d_all, sizeof(Handles) * c->world, cudaMemcpyDeviceToHost, c->stream));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_all);
+    int all_ok = 1;
+    for (int r = 0; r < c->world; ++r) all_ok &= h_all[r].ok;
+    // opening can fail too (no peer access between two devices): agree on the outcome with one more gather
+    int opened_ok = all_ok;
+    P.nopened = 0;
+    if (all_ok) {
+        for (int r = 0; r < c->world && opened_ok; ++r) {
+            if (r == c->rank) { P.mail[r] = mail; continue; }
+            void *m = nullptr;
+            if (cudaIpcOpenMemHandle(&m, h_all[r].m, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
+            P.opened[P.nopened++] = m;
+            P.mail[r] = (W2Mail *)m;
+            if (r == c->rank - 1 || r == c->rank + 1) {
+                void *a = nullptr, *b = nullptr;
+                if (cudaIpcOpenMemHandle(&a, h_all[r].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
+                P.opened[P.nopened++] = a;
+                if (cudaIpcOpenMemHandle(&b, h_all[r].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
+                P.opened[P.nopened++] = b;
+                int J0, J1, A0, A1, HG;
+                w2_slab_layout(c->nx, c->ny, c->world, r, &J0, &J1, &A0, &A1, &HG);
+                const int side = r == c->rank - 1 ? 0 : 1;
+                P.nbrA[side] = (double *)a - (size_t)c->pitch * (size_t)A0;   // peer rows are indexed globally too
+                P.nbrB[side] = (double *)b - (size_t)c->pitch * (size_t)A0;
+            }
+        }
+        cudaGetLastError();
+    }
+    free(h_all);
+    unsigned long long *d_flag = nullptr;
+    W2_CUDA(cudaMalloc((void **)&d_flag, 8));
+    unsigned long long bad = opened_ok ? 0ull : 1ull;
+    W2_CUDA(cudaMemcpyAsync(d_flag, &bad, 8, cudaMemcpyHostToDevice, c->stream));
+    W2_NCCL(N.AllReduce(d_flag, d_flag, 1, ncclUint64, ncclMax, g_comm, c->stream));
+    W2_CUDA(cudaMemcpyAsync(&bad, d_flag, 8, cudaMemcpyDeviceToHost, c->stream));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flag);
+    if (bad) {
+        fprintf(stderr, "wolfd2_b200: CUDA IPC peer mapping unavailable on rank %d; the SOR loop uses NCCL exchanges\n", c->rank);
+        for (int k = 0; k < P.nopened; ++k) cudaIpcCloseMemHandle(P.opened[k]);
+        P.nopened = 0;
+        cudaFree(mail);
+        return W2_OK;
+    }
+    P.state = 1;
+    return W2_OK;
+}
+
+void w2_peer_release(wolfd2_ctx *c) {
+    W2Peer &P = c->peer;
+    for (int k = 0; k < P.nopened; ++k) cudaIpcCloseMemHandle(P.opened[k]);
+    if (P.state == 1) cudaFree(P.mail[c->rank]);
+    memset(&P, 0, sizeof(P));
 }

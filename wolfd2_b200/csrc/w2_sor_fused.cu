@@ -22,6 +22,8 @@
 // iteration in the middle of a pass, the next launch redoes the pass from the untouched source
 // with exactly that many iterations -- the returned p and iteration count are those of the
 // reference.  Blockage (identity) rows arrive as a NaN sentinel in b.
+#include <stdlib.h>
+
 #include "w2.cuh"
 
 #define SF_W 256              // strip width held in shared memory (cells)
@@ -47,7 +49,12 @@ struct SorFCtl {           // device-resident loop control
 struct SorFArgs {
     int nx, ny, pitch;
     int j0, j1;            // unknown rows relaxed by this launch: 2..ny, or this rank's slab
-    int ext_decide;        // 1: the pass is closed by sorf_decide_kernel after the max-norms were all-reduced
+    int ext_decide;        // 0: one GPU, the last CTA closes the pass; 1: NCCL path, sorf_decide_kernel closes it after
+                           // the all-reduce; 2: peer-memory path, sorf_decide_p2p closes it from the mailboxes
+    // peer-memory path: rows j0..j0+2T-1 also go to the south neighbour's halo, j1-2T+1..j1 to the north one's
+    int rank, world;
+    double *nbrA[2], *nbrB[2];
+    W2Mail *mail[W2_MAXRANKS];
     int nstrips, nbands, rows_per_band, own_w;
     int msorit;
     double sorrel, sortol;
@@ -299,12 +306,58 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         gst += pitch;
     }
 
+    // ---- peer-memory path: the slab's edge rows are the neighbours' halo rows.  The band that owns them
+    // copies its columns of those 2T rows (just written, still in L2) into the neighbour's destination buffer
+    // with plain stores over NVLink -- outside the streaming loop, whose critical path stays as on one GPU.
+    if (a.ext_decide == 2) {
+        __syncthreads();   // the rows stored by this CTA's last stage are visible to all its threads
+        const int ow = own_hi - own_lo + 1;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            double *nd = cur ? a.nbrA[sd] : a.nbrB[sd];
+            const bool mine = sd ? (jB == a.j1) : (jA == a.j0);
+            if (nd == nullptr || !mine) continue;
+            const int row0 = sd ? a.j1 - H + 1 : a.j0;
+            for (int k = tid; k < H * ow; k += blockDim.x) {
+                const int rr = k / ow, i = own_lo + (k - rr * ow);
+                const size_t off = (size_t)pitch * (size_t)(row0 + rr) + (size_t)(i & 1) * hp + (size_t)(i >> 1);
+                nd[off] = pdst[off];
+            }
+        }
+    }
     // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const double v = ((stage - 1) >> 1) == t ? lmax : 0.0;
         const double m = w2_block_max(v, red);
         if (tid == 0 && t < Tp) atomicMax(&ctl->slot[t], w2_dbits(m));
+    }
+    // ---- peer-memory path: the last CTA publishes this slab's max-norms in every rank's mailbox
+    if (tid == 0 && a.ext_decide == 2) {
+        __threadfence_system();       // this CTA's peer stores (ordered before by the barriers above) are visible
+        const int total = gridDim.x * gridDim.y;
+        if (atomicAdd(&ctl->ticket, 1) == total - 1) {
+            __threadfence_system();
+            W2Mail *me = a.mail[a.rank];
+            const unsigned long long seq = me->my_seq + 1ull;
+            const int par = (int)(seq & 1ull);
+            unsigned long long bits[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) bits[t] = atomicExch(&ctl->slot[t], 0ull);
+            for (int r = 0; r < a.world; ++r) {
+                volatile unsigned long long *dst = a.mail[r]->slot[par][a.rank];
+#pragma unroll
+                for (int t = 0; t < T; ++t) dst[t] = bits[t];
+            }
+            __threadfence_system();
+            for (int r = 0; r < a.world; ++r) {
+                volatile unsigned long long *fl = &a.mail[r]->seq[par][a.rank];
+                *fl = seq;
+            }
+            me->my_seq = seq;
+            ctl->ticket = 0;
+            __threadfence_system();
+        }
     }
     // ---- the last CTA closes the pass
     if (tid == 0 && !a.ext_decide) {
@@ -324,6 +377,57 @@ __global__ void sorf_decide_kernel(SorFCtl *ctl, int T, double sortol, int msori
     if (ctl->done) return;
     const int Tp = ctl->redo > 0 ? ctl->redo : min(T, msorit - ctl->m);
     sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
+}
+
+// Peer-memory path.  One warp: lane r waits for rank r's record of the pass this rank has just finished
+// (a grid-wide barrier across the GPUs), lane 0 then takes the common decision from the maxima of all slabs.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void sorf_decide_p2p(SorFCtl *ctl, W2Mail *mail, int world, int T, double sortol, int msorit) {
+    if (ctl->done) return;
+    const int lane = threadIdx.x;
+    const unsigned long long seq = mail->my_seq;
+    const int par = (int)(seq & 1ull);
+    bool ok = true;
+    if (lane < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&mail->seq[par][lane]) != seq)
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }   // ~10 s: a peer is gone
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane != 0) return;
+    if (!ok) { mail->timeout = 1; ctl->done = 1; return; }
+    const int Tp = ctl->redo > 0 ? ctl->redo : min(T, msorit - ctl->m);
+    for (int t = 0; t < Tp; ++t) {
+        unsigned long long m = 0ull;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long v = ld_acquire_sys(&mail->slot[par][r][t]);
+            m = v > m ? v : m;
+        }
+        ctl->slot[t] = m;
+    }
+    sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
+}
+
+// Start-of-solve barrier: tells every rank that this rank's two pressure buffers are initialised (so peer
+// stores into their halo rows may begin) and waits for the same word from the others.
+__global__ void sorf_ready_p2p(SorFArgs a, unsigned long long solve) {
+    const int lane = threadIdx.x;
+    W2Mail *me = a.mail[a.rank];
+    bool ok = true;
+    if (lane < a.world) {
+        __threadfence_system();
+        volatile unsigned long long *fl = &a.mail[lane]->ready[a.rank];
+        *fl = solve;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&me->ready[lane]) < solve)
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0 && !ok) { me->timeout = 1; a.ctl->done = 1; }
 }
 
 // interleaved (reference order, i fastest) <-> colour-split rows.  TO_SPLIT: dst[j][ (i&1)*hp + i/2 ] = src[j][i]
@@ -386,6 +490,18 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     SorFArgs a;
     a.nx = nx; a.ny = ny; a.pitch = c->pitch;
     a.j0 = c->J0; a.j1 = c->J1; a.ext_decide = c->world > 1;
+    static const int dbg_decide = getenv("W2_SOR_DBG_DECIDE") ? atoi(getenv("W2_SOR_DBG_DECIDE")) : 0;   // timing experiments
+    if (c->world == 1 && dbg_decide) a.ext_decide = 1;
+    a.rank = c->rank; a.world = c->world;
+    memset(a.nbrA, 0, sizeof(a.nbrA)); memset(a.nbrB, 0, sizeof(a.nbrB)); memset(a.mail, 0, sizeof(a.mail));
+    if (c->world > 1) {
+        W2_TRY(w2_peer_setup(c));
+        if (c->peer.state == 1) {
+            a.ext_decide = 2;
+            for (int sd = 0; sd < 2; ++sd) { a.nbrA[sd] = c->peer.nbrA[sd]; a.nbrB[sd] = c->peer.nbrB[sd]; }
+            for (int r = 0; r < c->world; ++r) a.mail[r] = c->peer.mail[r];
+        }
+    }
     const int nrows = c->J1 - c->J0 + 1;
     a.own_w = SF_W - 4 * T;
     a.nstrips = 1;
@@ -417,6 +533,10 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     // buffer the same ghosts
     W2_TRY(w2_copy_field(c, pB, pA));
     sorf_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
+    if (a.ext_decide == 2) {
+        sorf_ready_p2p<<<1, 32, 0, c->stream>>>(a, ++c->peer.solves);
+        c->launches[2]++;
+    }
     const int passes_total = (par.msorit + T - 1) / T + 1;
     const double cells = (double)(nx - 1) * (double)nrows;
     int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + (c->world > 1 ? 4.0e-5 : 4.0e-6)));
@@ -438,7 +558,11 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
             if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
             else W2_TRY(launch_fused<2>(c, a, grid));
             c->launches[2]++;
-            if (c->world > 1) {
+            if (a.ext_decide == 2) {
+                // slab run over peer memory: the kernel has already stored its edge rows and max-norms remotely
+                sorf_decide_p2p<<<1, 32, 0, c->stream>>>(ctl, a.mail[a.rank], c->world, T, par.sortol, par.msorit);
+                c->launches[2]++;
+            } else if (a.ext_decide == 1) {
                 // slab run: global max-norms, the common decision, then the 2T halo rows of the iterate.
                 // Which buffer was written is known on the device only; the other one's halos are already
                 // right, so both are exchanged (a few hundred KB).
@@ -457,6 +581,11 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         if (h.done) break;
     }
     if (!h.done) { w2_set_error("fused SOR did not terminate"); return W2_ERR_CUDA; }
+    if (a.ext_decide == 2) {
+        int to = 0;
+        W2_CUDA(cudaMemcpy(&to, &a.mail[a.rank]->timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (to) { w2_set_error("fused SOR: timed out waiting for a peer GPU (rank %d of %d)", c->rank, c->world); return W2_ERR_CUDA; }
+    }
     if (converged) *converged = h.nconv > 0;
     if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : par.msorit;
     if (iters_done) *iters_done = h.m;
