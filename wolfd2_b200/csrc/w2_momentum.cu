@@ -56,7 +56,7 @@ __device__ __forceinline__ void chain_ij(const MomArgs &m, long long e, int &i, 
 #define MR_LEN (TRI_S + TRI_S / 8)
 
 template <int COMP, int STEP, bool POR>
-__global__ void __launch_bounds__(TRI_T, 2) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
+__global__ void __launch_bounds__(TRI_T, 512 / TRI_T) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
                                                               long long nseg, int direct, long long seg0) {

@@ -51,10 +51,6 @@ struct SorFArgs {
     int j0, j1;            // unknown rows relaxed by this launch: 2..ny, or this rank's slab
     int ext_decide;        // 0: one GPU, the last CTA closes the pass; 1: NCCL path, sorf_decide_kernel closes it after
                            // the all-reduce; 2: peer-memory path, sorf_decide_p2p closes it from the mailboxes
-    // peer-memory path: rows j0..j0+2T-1 also go to the south neighbour's halo, j1-2T+1..j1 to the north one's
-    int rank, world;
-    double *nbrA[2], *nbrB[2];
-    W2Mail *mail[W2_MAXRANKS];
     int nstrips, nbands, rows_per_band, own_w;
     int msorit;
     double sorrel, sortol;
@@ -65,6 +61,14 @@ struct SorFArgs {
     const double *rau, *rgv, *b;
     double *pA, *pB;
     SorFCtl *ctl;
+};
+
+// one rank's slab: rows j0..j0+2T-1 also go to the south neighbour's halo, j1-2T+1..j1 to the north one's.
+// A separate argument type keeps the one-GPU kernel's parameter block (and with it its code) unchanged.
+struct SorFSlabArgs : SorFArgs {
+    int rank, world;
+    double *nbrA[2], *nbrB[2];
+    W2Mail *mail[W2_MAXRANKS];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -145,6 +149,9 @@ template <int T> struct SorFCfg {
     static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
 };
 
+// The same kernel serves one GPU (rows 2..ny, the last CTA closes the pass) and one rank's row slab (rows
+// j0..j1, ext_decide != 0: the pass is closed by a follow-up kernel).  The multi-GPU plumbing lives in that
+// follow-up kernel: anything added here, even dead code, was seen to perturb the streaming loop's code.
 template <int T>
 __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused_kernel(SorFArgs a) {
     constexpr int NS = 2 * T;                 // half-sweep stages
@@ -306,58 +313,12 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         gst += pitch;
     }
 
-    // ---- peer-memory path: the slab's edge rows are the neighbours' halo rows.  The band that owns them
-    // copies its columns of those 2T rows (just written, still in L2) into the neighbour's destination buffer
-    // with plain stores over NVLink -- outside the streaming loop, whose critical path stays as on one GPU.
-    if (a.ext_decide == 2) {
-        __syncthreads();   // the rows stored by this CTA's last stage are visible to all its threads
-        const int ow = own_hi - own_lo + 1;
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            double *nd = cur ? a.nbrA[sd] : a.nbrB[sd];
-            const bool mine = sd ? (jB == a.j1) : (jA == a.j0);
-            if (nd == nullptr || !mine) continue;
-            const int row0 = sd ? a.j1 - H + 1 : a.j0;
-            for (int k = tid; k < H * ow; k += blockDim.x) {
-                const int rr = k / ow, i = own_lo + (k - rr * ow);
-                const size_t off = (size_t)pitch * (size_t)(row0 + rr) + (size_t)(i & 1) * hp + (size_t)(i >> 1);
-                nd[off] = pdst[off];
-            }
-        }
-    }
     // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const double v = ((stage - 1) >> 1) == t ? lmax : 0.0;
         const double m = w2_block_max(v, red);
         if (tid == 0 && t < Tp) atomicMax(&ctl->slot[t], w2_dbits(m));
-    }
-    // ---- peer-memory path: the last CTA publishes this slab's max-norms in every rank's mailbox
-    if (tid == 0 && a.ext_decide == 2) {
-        __threadfence_system();       // this CTA's peer stores (ordered before by the barriers above) are visible
-        const int total = gridDim.x * gridDim.y;
-        if (atomicAdd(&ctl->ticket, 1) == total - 1) {
-            __threadfence_system();
-            W2Mail *me = a.mail[a.rank];
-            const unsigned long long seq = me->my_seq + 1ull;
-            const int par = (int)(seq & 1ull);
-            unsigned long long bits[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) bits[t] = atomicExch(&ctl->slot[t], 0ull);
-            for (int r = 0; r < a.world; ++r) {
-                volatile unsigned long long *dst = a.mail[r]->slot[par][a.rank];
-#pragma unroll
-                for (int t = 0; t < T; ++t) dst[t] = bits[t];
-            }
-            __threadfence_system();
-            for (int r = 0; r < a.world; ++r) {
-                volatile unsigned long long *fl = &a.mail[r]->seq[par][a.rank];
-                *fl = seq;
-            }
-            me->my_seq = seq;
-            ctl->ticket = 0;
-            __threadfence_system();
-        }
     }
     // ---- the last CTA closes the pass
     if (tid == 0 && !a.ext_decide) {
@@ -379,42 +340,87 @@ __global__ void sorf_decide_kernel(SorFCtl *ctl, int T, double sortol, int msori
     sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
 }
 
-// Peer-memory path.  One warp: lane r waits for rank r's record of the pass this rank has just finished
-// (a grid-wide barrier across the GPUs), lane 0 then takes the common decision from the maxima of all slabs.
+// Peer-memory path: the kernel that follows every slab pass.  (1) The slab's first / last 2T rows are the
+// neighbours' halo rows: CTA (strip, side) copies its columns of them (just written, still in L2) into the
+// neighbour's destination buffer with plain stores over NVLink.  (2) The last CTA to finish publishes this
+// slab's max-norms and the pass number in every rank's mailbox (system-scope release), then (3) its first warp
+// waits for the same record from every rank -- a barrier across the GPUs -- and takes the common decision.
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void sorf_decide_p2p(SorFCtl *ctl, W2Mail *mail, int world, int T, double sortol, int msorit) {
+__global__ void __launch_bounds__(256) sorf_edge_kernel(SorFSlabArgs a, int T) {
+    SorFCtl *ctl = a.ctl;
     if (ctl->done) return;
-    const int lane = threadIdx.x;
-    const unsigned long long seq = mail->my_seq;
+    __shared__ int s_last;
+    const int H = 2 * T, tid = threadIdx.x;
+    const int cur = ctl->cur;                       // the pass just run wrote the other buffer
+    const double *pdst = cur ? a.pA : a.pB;
+    const int sd = blockIdx.y;                      // 0: rows j0.. to rank-1, 1: rows ..j1 to rank+1
+    double *nd = cur ? a.nbrA[sd] : a.nbrB[sd];
+    if (nd != nullptr) {
+        const int i0 = blockIdx.x * a.own_w;
+        const bool physL = blockIdx.x == 0, physR = (i0 + SF_W - 1 >= a.nx + 1);
+        const int own_lo = physL ? 2 : i0 + H;
+        const int own_hi = physR ? a.nx : min(a.nx, i0 + H + a.own_w - 1);
+        const int ow = own_hi - own_lo + 1, hp = a.pitch >> 1;
+        const int row0 = sd ? a.j1 - H + 1 : a.j0;
+        for (int k = tid; k < H * ow; k += blockDim.x) {
+            const int rr = k / ow, i = own_lo + (k - rr * ow);
+            const size_t off = (size_t)a.pitch * (size_t)(row0 + rr) + (size_t)(i & 1) * hp + (size_t)(i >> 1);
+            nd[off] = pdst[off];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();                     // this CTA's peer stores are visible before its ticket
+        s_last = atomicAdd(&ctl->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!s_last || tid >= 32) return;
+    W2Mail *me = a.mail[a.rank];
+    const unsigned long long seq = me->my_seq + 1ull;
     const int par = (int)(seq & 1ull);
+    if (tid == 0) {
+        __threadfence_system();
+        for (int r = 0; r < a.world; ++r) {
+            volatile unsigned long long *dst = a.mail[r]->slot[par][a.rank];
+            for (int t = 0; t < T; ++t) dst[t] = ctl->slot[t];
+        }
+        __threadfence_system();
+        for (int r = 0; r < a.world; ++r) {
+            volatile unsigned long long *fl = &a.mail[r]->seq[par][a.rank];
+            *fl = seq;
+        }
+        me->my_seq = seq;
+        ctl->ticket = 0;
+    }
+    __syncwarp();
     bool ok = true;
-    if (lane < world) {
+    if (tid < a.world) {
         const long long t0 = clock64();
-        while (ld_acquire_sys(&mail->seq[par][lane]) != seq)
+        while (ld_acquire_sys(&me->seq[par][tid]) != seq)
             if (clock64() - t0 > 20000000000ll) { ok = false; break; }   // ~10 s: a peer is gone
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane != 0) return;
-    if (!ok) { mail->timeout = 1; ctl->done = 1; return; }
-    const int Tp = ctl->redo > 0 ? ctl->redo : min(T, msorit - ctl->m);
+    if (tid != 0) return;
+    if (!ok) { me->timeout = 1; ctl->done = 1; return; }
+    const int Tp = ctl->redo > 0 ? ctl->redo : min(T, a.msorit - ctl->m);
     for (int t = 0; t < Tp; ++t) {
         unsigned long long m = 0ull;
-        for (int r = 0; r < world; ++r) {
-            const unsigned long long v = ld_acquire_sys(&mail->slot[par][r][t]);
+        for (int r = 0; r < a.world; ++r) {
+            const unsigned long long v = ld_acquire_sys(&me->slot[par][r][t]);
             m = v > m ? v : m;
         }
         ctl->slot[t] = m;
     }
-    sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
+    sorf_close_pass(ctl, Tp, cur, a.sortol, a.msorit);
 }
 
 // Start-of-solve barrier: tells every rank that this rank's two pressure buffers are initialised (so peer
 // stores into their halo rows may begin) and waits for the same word from the others.
-__global__ void sorf_ready_p2p(SorFArgs a, unsigned long long solve) {
+__global__ void sorf_ready_p2p(SorFSlabArgs a, unsigned long long solve) {
     const int lane = threadIdx.x;
     W2Mail *me = a.mail[a.rank];
     bool ok = true;
@@ -457,16 +463,23 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 }
 
 // ---------------------------------------------------------------------------------------- host
-static bool g_attr_set[3] = {false, false, false};
 
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     const size_t smem = SorFCfg<T>::smem;
-    if (!g_attr_set[T]) {
+    static bool attr_set = false;
+    if (!attr_set) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_attr_set[T] = true;
+        attr_set = true;
     }
     sor_rb_fused_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
+    return W2_OK;
+}
+template <int T>
+static int fused_occupancy(int *per_sm) {
+    const size_t smem = SorFCfg<T>::smem;
+    cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, sor_rb_fused_kernel<T>, T * 2 * SF_TPS, smem);
     return W2_OK;
 }
 
@@ -487,11 +500,9 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     const int nx = c->nx, ny = c->ny;
     SorFCtl *ctl = (SorFCtl *)c->d_flags;
     static_assert(sizeof(SorFCtl) <= 64 * sizeof(int), "ctl block too large");
-    SorFArgs a;
+    SorFSlabArgs a;
     a.nx = nx; a.ny = ny; a.pitch = c->pitch;
     a.j0 = c->J0; a.j1 = c->J1; a.ext_decide = c->world > 1;
-    static const int dbg_decide = getenv("W2_SOR_DBG_DECIDE") ? atoi(getenv("W2_SOR_DBG_DECIDE")) : 0;   // timing experiments
-    if (c->world == 1 && dbg_decide) a.ext_decide = 1;
     a.rank = c->rank; a.world = c->world;
     memset(a.nbrA, 0, sizeof(a.nbrA)); memset(a.nbrB, 0, sizeof(a.nbrB)); memset(a.mail, 0, sizeof(a.mail));
     if (c->world > 1) {
@@ -508,17 +519,9 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     while ((a.nstrips - 1) * a.own_w + SF_W < nx + 2) a.nstrips++;
     // bands: exactly one resident wave of CTAs (a partial second wave would double the pass time)
     int per_sm = 1;
-    {
-        const size_t smem1 = SorFCfg<1>::smem, smem2 = SorFCfg<2>::smem;
-        if (T == 1) {
-            cudaFuncSetAttribute(sor_rb_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<1>, 2 * SF_TPS, smem1);
-        } else {
-            cudaFuncSetAttribute(sor_rb_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_rb_fused_kernel<2>, 4 * SF_TPS, smem2);
-        }
-        if (per_sm < 1) per_sm = 1;
-    }
+    if (T == 1) fused_occupancy<1>(&per_sm);
+    else fused_occupancy<2>(&per_sm);
+    if (per_sm < 1) per_sm = 1;
     int want = (per_sm * c->num_sms) / a.nstrips;
     if (want < 1) want = 1;
     a.rows_per_band = (nrows + want - 1) / want;
@@ -559,8 +562,8 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
             else W2_TRY(launch_fused<2>(c, a, grid));
             c->launches[2]++;
             if (a.ext_decide == 2) {
-                // slab run over peer memory: the kernel has already stored its edge rows and max-norms remotely
-                sorf_decide_p2p<<<1, 32, 0, c->stream>>>(ctl, a.mail[a.rank], c->world, T, par.sortol, par.msorit);
+                // slab run over peer memory: edge rows and max-norms go to the peers, then the common decision
+                sorf_edge_kernel<<<dim3(a.nstrips, 2), 256, 0, c->stream>>>(a, T);
                 c->launches[2]++;
             } else if (a.ext_decide == 1) {
                 // slab run: global max-norms, the common decision, then the 2T halo rows of the iterate.

@@ -2,7 +2,7 @@
 #pragma once
 #include "w2.cuh"
 
-#define TRI_T 256
+#define TRI_T 128
 #define TRI_M 8
 #define TRI_S (TRI_T * TRI_M)
 

@@ -87,7 +87,7 @@ struct ProvSeg {  // rows of the separator system of the level below, formed fro
 
 // ---------------------------------------------------------------------- reduce kernel
 template <class Prov>
-__global__ void __launch_bounds__(TRI_T, 2) tri_reduce_kernel(Prov prov, long long n, double *__restrict__ Yg,
+__global__ void __launch_bounds__(TRI_T, 512 / TRI_T) tri_reduce_kernel(Prov prov, long long n, double *__restrict__ Yg,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, long long nseg, int direct,
                                                               double *__restrict__ xout) {
