@@ -46,6 +46,25 @@ __device__ __forceinline__ void chain_ij(const MomArgs &m, long long e, int &i, 
     else { const int w = m.nx - 1; const int jj = (int)(e / w); j = 1 + jj; i = 2 + (int)(e - (long long)jj * w); }
 }
 
+// Walking a segment in the coalesced mapping (element t, t+TRI_T, ...): one 64-bit division per thread for
+// the segment base, then add-and-wrap.  (chain_ij per element costs two 64-bit divisions per unknown, which
+// was ~25 % of the kernel's instructions.)
+template <int COMP>
+struct ChainWalk {
+    int w, j, pos;   // row length, current row, 0-based position in the row
+    __device__ __forceinline__ ChainWalk(const MomArgs &m, long long e) {
+        w = COMP == 0 ? m.nx : m.nx - 1;
+        const long long jj = e / w;
+        j = (COMP == 0 ? 2 : 1) + (int)jj;
+        pos = (int)(e - jj * w);
+    }
+    __device__ __forceinline__ int i() const { return (COMP == 0 ? 1 : 2) + pos; }
+    __device__ __forceinline__ void advance(int d) {
+        pos += d;
+        while (pos >= w) { pos -= w; ++j; }
+    }
+};
+
 // ---- fused assembly + level-0 reduce --------------------------------------------------------------------
 // One CTA per segment of TRI_S chain unknowns.  Rows are assembled in a coalesced mapping (thread <->
 // consecutive i), transposed through shared memory to the solver's chunk mapping (thread <-> 8
@@ -72,14 +91,15 @@ __global__ void __launch_bounds__(TRI_T, 512 / TRI_T) mom_reduce_kernel(MomArgs 
     if (t == 0) { s_ext[0] = 0; s_ext[1] = 0; }
 
     // ---- phase A: assemble rows, coalesced (the cheap second-step rows are unrolled for more loads in flight)
+    ChainWalk<COMP> wa(m, ebase + t);
 #pragma unroll(STEP == 2 ? 4 : 2)
     for (int q = 0; q < TRI_M; ++q) {
         const int el = t + TRI_T * q;
         const long long e = ebase + el;
         double a1 = 0.0, a2 = 1.0, a3 = 0.0, b = 0.0;
         if (e < n) {
-            int i, j;
-            chain_ij<COMP>(m, e, i, j);
+            const int i = wa.i(), j = wa.j;
+            wa.advance(TRI_T);
             if (POR) mom_po::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
             else mom_np::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
             if (e == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
@@ -133,13 +153,14 @@ __global__ void __launch_bounds__(TRI_T, 512 / TRI_T) mom_reduce_kernel(MomArgs 
     }
     __syncthreads();
     const int extV = s_ext[0], extW = s_ext[1];
+    ChainWalk<COMP> wc(m, ebase + t);
 #pragma unroll 1
     for (int q = 0; q < TRI_M; ++q) {
         const int el = t + TRI_T * q;
         const long long e = ebase + el;
         if (e >= n) break;
-        int i, j;
-        chain_ij<COMP>(m, e, i, j);
+        const int i = wc.i(), j = wc.j;
+        wc.advance(TRI_T);
         const int p = MR_PAD(el);
         out[IDX(i, j)] = s0[p];
         if (!direct) {

@@ -6,6 +6,20 @@
 #define TRI_M 8
 #define TRI_S (TRI_T * TRI_M)
 
+// 1/x for the pivots of the elimination: hardware seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps in
+// FMA arithmetic, ~1 ulp, 5 instructions instead of the ~25 of the IEEE division sequence with its
+// special-case path.  Pivots here are O(1) by diagonal dominance (never 0, inf, NaN or subnormal).  The
+// parallel elimination order already differs from AltTridLU's, so nothing here is meant to be bit-exact
+// (tolerances: DESIGN.md section 5); the point-wise SOR and stencil kernels keep true divisions.
+__device__ __forceinline__ double tri_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = __fma_rn(-x, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-x, y, 1.0);
+    return __fma_rn(y, e, y);
+}
+
 // Input: this thread's TRI_M consecutive rows (A,D,C,B).  Output: for each of them the coefficients of
 //   x = Ye - Sg[g-1]*Ve - Sg[g]*We
 // where Sg[g] is the CTA's separator (its last unknown) and Sg[g-1] that of the previous segment, plus
@@ -21,11 +35,11 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
     double y[TRI_M - 1], v[TRI_M - 1], w[TRI_M - 1], cp[TRI_M - 1];
     // --- thread-level elimination of the M-1 interior unknowns, 3 right-hand sides
     {
-        double inv = 1.0 / D[0];
+        double inv = tri_rcp(D[0]);
         cp[0] = C[0] * inv; y[0] = B[0] * inv; v[0] = A[0] * inv;
 #pragma unroll
         for (int k = 1; k <= L; ++k) {
-            inv = 1.0 / (D[k] - A[k] * cp[k - 1]);
+            inv = tri_rcp(D[k] - A[k] * cp[k - 1]);
             cp[k] = C[k] * inv;
             y[k] = (B[k] - A[k] * y[k - 1]) * inv;
             v[k] = (-A[k] * v[k - 1]) * inv;
@@ -67,7 +81,7 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
         double aH = 0.0, dH = 1.0, cH = 0.0, yH = 0.0, vH = 0.0, wH = 0.0;
         if (lo >= 0) { aL = sA[lo]; dL = sD[lo]; cL = sC[lo]; yL = sY[lo]; vL = sV[lo]; wL = sW[lo]; }
         if (hi < TRI_T) { aH = sA[hi]; dH = sD[hi]; cH = sC[hi]; yH = sY[hi]; vH = sV[hi]; wH = sW[hi]; }
-        const double al = -rA / dL, ga = -rC / dH;
+        const double al = -rA * tri_rcp(dL), ga = -rC * tri_rcp(dH);
         rD = rD + al * cL + ga * aH;
         rY = rY + al * yL + ga * yH;
         rV = rV + al * vL + ga * vH;
@@ -78,7 +92,7 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
     }
     // separator solution, as coefficients of (1, Sg[g-1], Sg[g])
     double sy, sv, sw;
-    if (t < TRI_T - 1) { const double inv = 1.0 / rD; sy = rY * inv; sv = rV * inv; sw = rW * inv; }
+    if (t < TRI_T - 1) { const double inv = tri_rcp(rD); sy = rY * inv; sv = rV * inv; sw = rW * inv; }
     else { sy = 0.0; sv = 0.0; sw = -1.0; }
     sY[t] = sy; sV[t] = sv; sW[t] = sw;
     __syncthreads();
