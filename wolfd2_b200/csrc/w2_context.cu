@@ -198,6 +198,8 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     }
     W2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 8; ++k) W2_CUDA(cudaEventCreate(&c->ev[k]));
+    W2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    W2_CUDA(cudaEventCreateWithFlags(&c->ev_p, cudaEventDisableTiming));
     W2_CUDA(cudaMalloc((void **)&c->dreg, sizeof(W2Regions)));
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) W2_TRY(falloc(c, &mp[k]));
@@ -248,16 +250,18 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     cudaFreeHost(c->h_norm); cudaFreeHost(c->h_flags);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (int k = 0; k < 8; ++k) cudaEventDestroy(c->ev[k]);
+    cudaEventDestroy(c->ev_p);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     free(c);
 }
 
 // Host (0:mnx,0:mny) <-> device pitched copies of the (0..nx+1, 0..ny+1) window.  In a slab context the
 // host array holds this rank's rows only: host row 0 is global row A0 (wolfd2_b200_slab_layout).
-int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host) {
+int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host, cudaStream_t stream) {
     W2_CUDA(cudaMemcpy2DAsync(dev + c->row_off, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
                               (size_t)(c->nx + 2) * 8, (size_t)c->rows, cudaMemcpyHostToDevice,
-                              c->stream));
+                              stream ? stream : c->stream));
     return W2_OK;
 }
 int w2_download2d(wolfd2_ctx *c, double *host, const double *dev) {

@@ -73,9 +73,12 @@ struct ChainWalk {
 // spikes V/W go to chain-layout arrays only over the prefix/suffix where they are not exactly zero.
 #define MR_PAD(x) ((x) + ((x) >> 3))
 #define MR_LEN (TRI_S + TRI_S / 8)
+#ifndef MOM_MINB
+#define MOM_MINB (640 / TRI_T)
+#endif
 
 template <int COMP, int STEP, bool POR>
-__global__ void __launch_bounds__(TRI_T, 512 / TRI_T) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
+__global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
                                                               long long nseg, int direct, long long seg0) {

@@ -38,7 +38,6 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     cudaEventRecord(c->ev[0], s);
     // :696-704  time-level n copies (t is identically zero on this path; d never changes, so
     // dn == d and both stay as uploaded)
-    W2_TRY(w2_copy_field(c, pn, p));
     W2_TRY(w2_copy_field(c, un, u));
     W2_TRY(w2_copy_field(c, vn, v));
     W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D]));
@@ -48,6 +47,10 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     int nQL = -1, nSor = 0, conv = 0;
     // us == un here, so the initialisation loop of nAuxMomentum (:114-119) is a no-op
     W2_TRY(w2_nauxmomentum(c, /*init_star=*/0, &nQL));   // :753
+    // The momentum solve does not read p; step_host uploads p on a second stream meanwhile.  pn <- p (:696)
+    // therefore happens here, after that upload has landed.
+    if (c->p_pending) { W2_CUDA(cudaStreamWaitEvent(s, c->ev_p, 0)); c->p_pending = 0; }
+    W2_TRY(w2_copy_field(c, pn, p));
     cudaEventRecord(c->ev[1], s);
     if (c->par.nfiltu == 1) W2_TRY(w2_filter(c, W2_U, c->par.fpu, us));   // :783
     if (c->par.nfiltv == 1) W2_TRY(w2_filter(c, W2_V, c->par.fpv, vs));   // :788
@@ -108,8 +111,15 @@ extern "C" int wolfd2_b200_step_host(wolfd2_ctx *c, int32_t nsteps, double *u, d
     W2_CUDA(cudaSetDevice(c->device));
     W2_TRY(w2_upload2d(c, c->fld[W2_F_U], u));
     W2_TRY(w2_upload2d(c, c->fld[W2_F_V], v));
-    W2_TRY(w2_upload2d(c, c->fld[W2_F_P], p));
+    if (nsteps > 0) {   // p is first needed after the momentum solve: its upload overlaps it (one_step waits on ev_p)
+        W2_TRY(w2_upload2d(c, c->fld[W2_F_P], p, c->copy_stream));
+        W2_CUDA(cudaEventRecord(c->ev_p, c->copy_stream));
+        c->p_pending = 1;
+    } else {
+        W2_TRY(w2_upload2d(c, c->fld[W2_F_P], p));
+    }
     int rc = wolfd2_b200_step(c, nsteps, logs);
+    if (c->p_pending) { cudaStreamSynchronize(c->copy_stream); c->p_pending = 0; }   // a failed step never waited
     if (rc != W2_OK && rc != W2_ERR_DIVERGED) return rc;
     W2_TRY(w2_download2d(c, u, c->fld[W2_F_U]));
     W2_TRY(w2_download2d(c, v, c->fld[W2_F_V]));
