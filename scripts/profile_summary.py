@@ -1,0 +1,81 @@
+"""Summaries committed under profiles/: (1) per-kernel totals of an ncu launch list
+(`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file launches.csv python bench.py ...`),
+(2) selected raw metrics of `ncu --set full` reports.  Usage:
+    python scripts/profile_summary.py launches gpurun_out/launches.csv [skip_first_n]
+    python scripts/profile_summary.py raw gpurun_out/x.ncu-rep [...]"""
+import csv
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+METRICS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size",
+           "launch__registers_per_thread", "launch__waves_per_multiprocessor",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
+
+
+def short(name):
+    name = re.sub(r"^void ", "", name)
+    name = re.sub(r"\(.*$", "", name)
+    return name.replace("(int)", "").replace("(bool)", "")
+
+
+def launches(path, skip=0):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    h = rows[0]
+    ik, iv, im = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name")
+    agg = OrderedDict()
+    seen = 0
+    for r in rows[1:]:
+        if r[im] != "gpu__time_duration.sum":
+            continue
+        seen += 1
+        if seen <= skip:
+            continue
+        a = agg.setdefault(short(r[ik]), [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[iv]) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    print(f"{'kernel':46s}{'n':>6s}{'avg_us':>10s}{'share%':>8s}")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:46s}{n:6d}{t / n:10.1f}{100 * t / tot:8.1f}")
+    grp = {"SOR (fused pass, pack, reset)": ("sor", "sorf"), "momentum (assemble+reduce, upper levels, finalize, QL update)":
+           ("mom_", "tri_", "ql_"), "other (div/rhs, project, ghost fills, norms, masks)": ()}
+    used = set()
+    for g, keys in grp.items():
+        if keys:
+            ks = [k for k in agg if k.startswith(keys)]
+            used.update(ks)
+        else:
+            ks = [k for k in agg if k not in used]
+        print(f"# {g}: {100 * sum(agg[k][1] for k in ks) / tot:.1f} %")
+    print(f"# total {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches")
+
+
+def raw(paths):
+    for p in paths:
+        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        h = rows[0]
+        print(f"## report: {p.split('/')[-1]}")
+        for m in METRICS:
+            if m in h:
+                i = h.index(m)
+                print(f"{m:90s} {[short(r[i]) if m == 'Kernel Name' else r[i] for r in rows[1:]]}")
+        print()
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    else:
+        raw(sys.argv[2:])

@@ -59,9 +59,14 @@ struct ChainWalk {
         pos = (int)(e - jj * w);
     }
     __device__ __forceinline__ int i() const { return (COMP == 0 ? 1 : 2) + pos; }
-    __device__ __forceinline__ void advance(int d) {
+    __device__ __forceinline__ void advance(int d) {       // d of the order of w or less
         pos += d;
         while (pos >= w) { pos -= w; ++j; }
+    }
+    __device__ __forceinline__ void advance_far(int d) {   // any d >= 0 (one 32-bit division)
+        pos += d;
+        const int k = pos / w;
+        pos -= k * w; j += k;
     }
 };
 
@@ -183,26 +188,31 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
 }
 
 // x = Y - Sg[g-1]*V - Sg[g]*W in field layout, touching only the unknowns whose spike entries are non-zero
+// (a few dozen per segment: the spikes of a diagonally dominant system decay fast).  One warp per segment.
 template <int COMP>
 __global__ void __launch_bounds__(256) mom_finalize_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                            const double *__restrict__ Vg, const double *__restrict__ Wg,
                                                            const double *__restrict__ sig, const int *__restrict__ ext,
-                                                           long long seg0) {
-    const long long g = seg0 + blockIdx.x;
+                                                           long long seg0, long long seg1) {
+    const long long g = seg0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= seg1) return;
+    const int lane = threadIdx.x & 31;
     const int pitch = m.pitch;
     const int extV = ext[2 * g], extW = ext[2 * g + 1];
     const double sl = g > 0 ? sig[g - 1] : 0.0, sr = sig[g];
     const int lo2 = max(extV, TRI_S - extW);   // start of the W-only part
     const int cnt = extV + (TRI_S - lo2);
-    for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+    const ChainWalk<COMP> base(m, g * (long long)TRI_S);
+    for (int q = lane; q < cnt; q += 32) {
         const int el = q < extV ? q : lo2 + (q - extV);
         const long long e = g * (long long)TRI_S + el;
         if (e >= n) continue;
-        int i, j;
-        chain_ij<COMP>(m, e, i, j);
+        ChainWalk<COMP> w = base;
+        w.advance_far(el);
+        const int i = w.i(), j = w.j;
         const double v = el < extV ? Vg[e] : 0.0;
-        const double w = el >= TRI_S - extW ? Wg[e] : 0.0;
-        out[IDX(i, j)] = out[IDX(i, j)] - sl * v - sr * w;
+        const double ww = el >= TRI_S - extW ? Wg[e] : 0.0;
+        out[IDX(i, j)] = out[IDX(i, j)] - sl * v - sr * ww;
     }
 }
 
@@ -415,7 +425,7 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
         W2_TRY(w2_allreduce_sum_f64(c, w.lv[0].seg, 10 * (size_t)nseg));
         const double *sigma = nullptr;
         W2_TRY(w2_tri_upper(c, nseg, &sigma));   // a few thousand unknowns: solved redundantly on every rank
-        mom_finalize_kernel<COMP><<<(unsigned)(s_hi - s_lo), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo);
+        mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
         c->launches[1]++;
     }
     W2_CUDA(cudaGetLastError());
