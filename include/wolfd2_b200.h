@@ -76,6 +76,28 @@ typedef struct wolfd2_regions {
     const double  *dPRporc2;
 } wolfd2_regions;
 
+/* Thermal energy equation: what main.f passes to ThermEnergy / TempBoundCond / EqState /
+ * Filter(_T_) (src/main.f:840-894, 955) that is not in wolfd2_params / wolfd2_regions.  Tables in the Fortran
+ * layout: nTRgType(mgri,mgrj) {RT_NOSRCE 0, RT_HEATGN 1, RT_TEMPER 2}, nTemBdTp(mgri,mgrj,4) {BT_INTERN 0,
+ * BT_TEMPER 1, BT_HTFLUX 2} (include/wolfd2.h:26-32), dTRgVal, dHGSTval(mgri,mgrj); the temperature BC values
+ * are dBCVal(.,.,.,_T_) of wolfd2_regions. */
+typedef struct wolfd2_thermal {
+    int32_t nthermen;          /* 1: solve the thermal energy equation (thermal_energy)   */
+    int32_t neqstate;          /* 1: density from the ideal-gas law after every M-E iteration */
+    int32_t nfiltt;            /* 1: Shuman filter on t (filter_t <fpt>)                  */
+    int32_t reserved_;
+    double  pe;                /* Peclet number re*Pr                                     */
+    double  dmeittol;          /* tolerance of the momentum-energy iterations             */
+    double  fpt;
+    double  uref, densref, tmax, tref, rconst;   /* EqState, src/thermal.f:283-327        */
+    const int32_t *nTRgType;
+    const int32_t *nTemBdTp;
+    const double  *dTRgVal;
+    const double  *dHGSTval;
+} wolfd2_thermal;
+enum { W2_RT_NOSRCE = 0, W2_RT_HEATGN = 1, W2_RT_TEMPER = 2 };
+enum { W2_BT_INTERN = 0, W2_BT_TEMPER = 1, W2_BT_HTFLUX = 2 };
+
 /* The 30 metric arrays produced by Metric (src/grid.f:368-535), each
  * REAL*8 (0:mnx,0:mny), zero outside 1..nx,1..ny (static storage in main.f). */
 typedef struct wolfd2_metrics {
@@ -103,7 +125,8 @@ enum { W2_OK = 0, W2_ERR_NO_DEVICE = 1, W2_ERR_BAD_ARG = 2, W2_ERR_UNSUPPORTED =
 
 /* field selectors for wolfd2_b200_upload_field / download_field */
 enum { W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_US = 3, W2_F_VS = 4, W2_F_UN = 5,
-       W2_F_VN = 6, W2_F_PN = 7, W2_F_D = 8, W2_F_DN = 9, W2_F_B = 10, W2_F_COUNT = 11 };
+       W2_F_VN = 6, W2_F_PN = 7, W2_F_D = 8, W2_F_DN = 9, W2_F_B = 10,
+       W2_F_T = 11, W2_F_TS = 12, W2_F_TN = 13, W2_F_COUNT = 14 };
 
 /* ---- library-wide configuration ------------------------------------------------ */
 
@@ -129,6 +152,10 @@ int wolfd2_b200_create(wolfd2_ctx **out, const wolfd2_params *par,
                        const wolfd2_regions *reg, const wolfd2_metrics *met);
 void wolfd2_b200_destroy(wolfd2_ctx *ctx);
 int wolfd2_b200_set_params(wolfd2_ctx *ctx, const wolfd2_params *par);
+/* Switch the thermal energy equation on (or, with th->nthermen == 0, off) for the following steps: the
+ * momentum-energy iteration loop of src/main.f:736-880 then runs up to par->nmeiter times per step with
+ * ThermEnergy, EqState and the t-norm inside, Filter(_T_) and TempBoundCond after it.  One GPU only. */
+int wolfd2_b200_set_thermal(wolfd2_ctx *ctx, const wolfd2_thermal *th);
 
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
@@ -265,6 +292,21 @@ void filter_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp,
 double diffmaxnorm_(const int32_t *nx, const int32_t *ny, const double *un,
                     const double *u);
 double dmaxnorm_(const int32_t *nx, const int32_t *ny, const double *u);
+
+/* src/bound_cond.f:1030-1034 */
+void tempboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal, const double *dBCVal, double *t);
+/* src/thermal.f:24-33 */
+void thermenergy_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dk, const double *pe,
+    const double *dTRgVal, const double *dHGSTval, const double *dBCVal,
+    const double *rau, const double *rbu, const double *rbv, const double *rgv, const double *djc,
+    const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+    const double *xec, const double *yec, const double *xzc, const double *yzc,
+    const double *un, const double *vn, const double *u, const double *v, const double *tn, double *t);
+/* src/thermal.f:283-285 */
+void eqstate_(const int32_t *nx, const int32_t *ny, const double *uref, const double *densref,
+    const double *tmax, const double *tref, const double *rconst, const double *p, const double *t, double *den);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ static double *W_qh;                   /* Filter local (utility.f:65) */
 static double *W_pn;                   /* SlorRBP local pn (pressure.f:1008) */
 static double *W_aline, *W_bline, *W_plold; /* Slor* locals (pressure.f:700) */
 static double *W_dif;                  /* SorRBP automatic array dif (pressure.f:574) */
+static double *W_cu1, *W_cun, *W_cv1, *W_cvn, *W_s, *W_ta, *W_tb; /* ThermEnergy locals (thermal.f:87-91) */
 
 static double *zalloc(size_t n) {
     double *p = (double *)calloc(n ? n : 1, sizeof(double));
@@ -102,6 +103,9 @@ void orc_config(int32_t mnx, int32_t mny, int32_t mgri, int32_t mgrj) {
     size_t mnl = (size_t)(mnx > mny ? mnx : mny);
     W_aline = zalloc(3 * mnl); W_bline = zalloc(mnl); W_plold = zalloc(mnl);
     W_dif = zalloc(NFULL);
+    free(W_cu1); free(W_cun); free(W_cv1); free(W_cvn); free(W_s); free(W_ta); free(W_tb);
+    W_cu1 = zalloc(NFULL); W_cun = zalloc(NFULL); W_cv1 = zalloc(NFULL); W_cvn = zalloc(NFULL); W_s = zalloc(NFULL);
+    W_ta = zalloc(3 * (size_t)MN); W_tb = zalloc((size_t)MN);
     orc_errflag = 0;
 }
 int32_t orc_get_errflag(void) { return orc_errflag; }
@@ -1647,6 +1651,168 @@ void orc_setupbcs_complete(int32_t nx, int32_t ny, const int32_t *nReg, int32_t 
         }
 }
 
+
+/* ================================ thermal.f ====================================== */
+#define TRT(ir, jr) nTRgType[((ir) - 1) + MGRI * ((jr) - 1)]
+#define TB(ir, jr, k) nTemBdTp[((ir) - 1) + MGRI * (((jr) - 1) + MGRJ * ((k) - 1))]
+enum { RT_NOSRCE = 0, RT_HEATGN = 1, RT_TEMPER = 2 };
+enum { BT_INTERN = 0, BT_TEMPER = 1, BT_HTFLUX = 2 };
+
+/* TempBoundCond, src/bound_cond.f:1030-1204 */
+void orc_tempboundcond_(const int32_t *nx_, const int32_t *ny_, const int32_t *nReg, const int32_t *nRegBrd,
+                        const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal,
+                        const double *dBCVal, double *t) {
+    (void)nx_; (void)ny_;
+    const double dTwo = 2.0;
+    int i, j;
+    for (int jreg = 1; jreg <= nReg[_J_]; ++jreg)
+        for (int ireg = 1; ireg <= nReg[_I_]; ++ireg) {
+            int iW = RB(ireg, jreg, WEST), iE = RB(ireg, jreg, EAST);
+            int jS = RB(ireg, jreg, SOUTH), jN = RB(ireg, jreg, NORTH);
+            if (TRT(ireg, jreg) == RT_TEMPER) { /* :1083-1113 */
+                for (j = jS + 1; j <= jN; ++j)
+                    for (i = iW + 1; i <= iE; ++i) A(t, i, j) = PR(dTRgVal, ireg, jreg);
+                for (j = jS + 1; j <= jN; ++j) A(t, iW + 1, j) = dTwo * BV(ireg, jreg, WEST, _T_) - A(t, iW, j);
+                for (j = jS + 1; j <= jN; ++j) A(t, iE, j) = dTwo * BV(ireg, jreg, EAST, _T_) - A(t, iE + 1, j);
+                for (i = iW + 1; i <= iE; ++i) A(t, i, jS + 1) = dTwo * BV(ireg, jreg, SOUTH, _T_) - A(t, i, jS);
+                for (i = iW + 1; i <= iE; ++i) A(t, i, jN) = dTwo * BV(ireg, jreg, NORTH, _T_) - A(t, i, jN + 1);
+                continue;
+            }
+            switch (TB(ireg, jreg, WEST)) { /* :1118-1136 */
+            case BT_INTERN: break;
+            case BT_TEMPER: for (j = jS + 1; j <= jN; ++j) A(t, iW, j) = dTwo * BV(ireg, jreg, WEST, _T_) - A(t, iW + 1, j); break;
+            case BT_HTFLUX: for (j = jS + 1; j <= jN; ++j) A(t, iW, j) = BV(ireg, jreg, WEST, _T_) + A(t, iW + 1, j); break;
+            default: fprintf(stderr, "Wrong nTemBdTp W flag in region %d,%d\n", ireg, jreg); orc_errflag = 1; return;
+            }
+            switch (TB(ireg, jreg, EAST)) { /* :1139-1156 */
+            case BT_INTERN: break;
+            case BT_TEMPER: for (j = jS + 1; j <= jN; ++j) A(t, iE + 1, j) = dTwo * BV(ireg, jreg, EAST, _T_) - A(t, iE, j); break;
+            case BT_HTFLUX: for (j = jS + 1; j <= jN; ++j) A(t, iE + 1, j) = BV(ireg, jreg, EAST, _T_) + A(t, iE, j); break;
+            default: fprintf(stderr, "Wrong nTemBdTp E flag in region %d,%d\n", ireg, jreg); orc_errflag = 1; return;
+            }
+            switch (TB(ireg, jreg, SOUTH)) { /* :1160-1177 */
+            case BT_INTERN: break;
+            case BT_TEMPER: for (i = iW + 1; i <= iE; ++i) A(t, i, jS) = dTwo * BV(ireg, jreg, SOUTH, _T_) - A(t, i, jS + 1); break;
+            case BT_HTFLUX: for (i = iW + 1; i <= iE; ++i) A(t, i, jS) = BV(ireg, jreg, SOUTH, _T_) + A(t, i, jS + 1); break;
+            default: fprintf(stderr, "Wrong nTemBdTp S flag in region %d,%d\n", ireg, jreg); orc_errflag = 1; return;
+            }
+            switch (TB(ireg, jreg, NORTH)) { /* :1181-1198 */
+            case BT_INTERN: break;
+            case BT_TEMPER: for (i = iW + 1; i <= iE; ++i) A(t, i, jN + 1) = dTwo * BV(ireg, jreg, NORTH, _T_) - A(t, i, jN); break;
+            case BT_HTFLUX: for (i = iW + 1; i <= iE; ++i) A(t, i, jN + 1) = BV(ireg, jreg, NORTH, _T_) + A(t, i, jN); break;
+            default: fprintf(stderr, "Wrong nTemBdTp N flag in region %d,%d\n", ireg, jreg); orc_errflag = 1; return;
+            }
+        }
+}
+
+/* ThermEnergy, src/thermal.f:24-272 */
+void orc_thermenergy_(const int32_t *nx_, const int32_t *ny_, const int32_t *nReg, const int32_t *nRegBrd,
+                      const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dk_, const double *pe_,
+                      const double *dTRgVal, const double *dHGSTval, const double *dBCVal,
+                      const double *rau, const double *rbu, const double *rbv, const double *rgv, const double *djc,
+                      const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+                      const double *xec, const double *yec, const double *xzc, const double *yzc,
+                      const double *un, const double *vn, const double *u, const double *v,
+                      const double *tn, double *t) {
+    const int nx = *nx_, ny = *ny_;
+    const double dk = *dk_, pe = *pe_;
+    const double dZero = 0.0, dOne = 1.0, dTwo = 2.0, dHalf = 0.5;
+    double *cu1 = W_cu1, *cun = W_cun, *cv1 = W_cv1, *cvn = W_cvn, *s = W_s, *a = W_ta, *b = W_tb;
+    int i, j, ind;
+    double rkj, c, d;
+    const double pe1 = dOne / pe;                                   /* :101 */
+#define AA(k, ind) a[((k) - 1) + 3 * ((size_t)(ind) - 1)]
+    orc_tempboundcond_(nx_, ny_, nReg, nRegBrd, nTRgType, nTemBdTp, dTRgVal, dBCVal, t);   /* :104 */
+    if (orc_errflag) return;
+    { const int32_t c6 = 6, c3 = 3, z = 0;                          /* :114-119 */
+      orc_convcoef_(nx_, ny_, &c6, &z, xzc, xec, yzc, yec, u, v, cu1, cv1);
+      orc_convcoef_(nx_, ny_, &c3, &z, xzv, xeu, yzv, yeu, un, vn, cun, cvn); }
+    for (int jreg = 1; jreg <= nReg[_J_]; ++jreg)                   /* :123-147 */
+        for (int ireg = 1; ireg <= nReg[_I_]; ++ireg) {
+            int iW = RB(ireg, jreg, WEST), iE = RB(ireg, jreg, EAST);
+            int jS = RB(ireg, jreg, SOUTH), jN = RB(ireg, jreg, NORTH);
+            const double val = TRT(ireg, jreg) == RT_HEATGN ? PR(dHGSTval, ireg, jreg) : dZero;
+            for (j = jS + 1; j <= jN; ++j)
+                for (i = iW + 1; i <= iE; ++i) A(s, i, j) = val;
+        }
+    for (j = 2; j <= ny; ++j)                                       /* :153-199 */
+        for (i = 2; i <= nx; ++i) {
+            ind = (j - 2) * (nx - 1) + i - 1;
+            rkj = dk * A(djc, i, j) * dHalf;
+            if (A(cu1, i, j) >= dZero) {
+                AA(1, ind) = rkj * (-A(cu1, i - 1, j) - pe1 * A(rau, i - 1, j));
+                AA(2, ind) = dOne + rkj * (A(cu1, i, j) + pe1 * (A(rau, i, j) + A(rau, i - 1, j)));
+                AA(3, ind) = rkj * (-pe1 * A(rau, i, j));
+            } else {
+                AA(1, ind) = rkj * (-pe1 * A(rau, i - 1, j));
+                AA(2, ind) = dOne + rkj * (-A(cu1, i, j) + pe1 * (A(rau, i, j) + A(rau, i - 1, j)));
+                AA(3, ind) = rkj * (A(cu1, i + 1, j) - pe1 * A(rau, i, j));
+            }
+            c = -A(cvn, i, j - 1) * A(tn, i, j - 1) - A(cun, i - 1, j) * A(tn, i - 1, j)
+                + (A(cun, i, j) - A(cun, i - 1, j) + A(cvn, i, j) - A(cvn, i, j - 1)) * A(tn, i, j)
+                + A(cun, i, j) * A(tn, i + 1, j) + A(cvn, i, j) * A(tn, i, j + 1);
+            d = A(rau, i, j) * (A(tn, i + 1, j) - A(tn, i, j))
+                - A(rau, i - 1, j) * (A(tn, i, j) - A(tn, i - 1, j))
+                + A(rbu, i, j) * (A(tn, i + 1, j + 1) + A(tn, i, j + 1) - A(tn, i + 1, j - 1) - A(tn, i, j - 1))
+                - A(rbu, i - 1, j) * (A(tn, i, j + 1) + A(tn, i - 1, j + 1) - A(tn, i, j - 1) - A(tn, i - 1, j - 1))
+                + A(rbv, i, j) * (A(tn, i + 1, j + 1) + A(tn, i + 1, j) - A(tn, i - 1, j + 1) - A(tn, i - 1, j))
+                - A(rbv, i, j - 1) * (A(tn, i + 1, j) + A(tn, i + 1, j - 1) - A(tn, i - 1, j) - A(tn, i - 1, j - 1))
+                + A(rgv, i, j) * (A(tn, i, j + 1) - A(tn, i, j))
+                - A(rgv, i, j - 1) * (A(tn, i, j) - A(tn, i, j - 1));
+            b[ind - 1] = dk * A(s, i, j) * dHalf + dTwo * rkj * (-c + pe1 * d);
+        }
+    { const int32_t n = (nx - 1) * (ny - 1); orc_alttridlu_(&n, a, b); }   /* :203 */
+    for (j = 2; j <= ny; ++j)                                       /* :208-238 (rhs = first-step solution) */
+        for (i = 2; i <= nx; ++i) {
+            ind = (j - 2) * (nx - 1) + i - 1;
+            rkj = dk * A(djc, i, j) * dHalf;
+            if (A(cv1, i, j) >= dZero) {
+                AA(1, ind) = rkj * (-A(cv1, i, j - 1) - pe1 * A(rgv, i, j - 1));
+                AA(2, ind) = dOne + rkj * (A(cv1, i, j) + pe1 * (A(rgv, i, j) + A(rgv, i, j - 1)));
+                AA(3, ind) = rkj * (-pe1 * A(rgv, i, j));
+            } else {
+                AA(1, ind) = rkj * (-pe1 * A(rgv, i, j - 1));
+                AA(2, ind) = dOne + rkj * (-A(cv1, i, j) + pe1 * (A(rgv, i, j) + A(rgv, i, j - 1)));
+                AA(3, ind) = rkj * (A(cv1, i, j + 1) - pe1 * A(rgv, i, j));
+            }
+        }
+    for (int jreg = 1; jreg <= nReg[_J_]; ++jreg)                   /* :242-266 */
+        for (int ireg = 1; ireg <= nReg[_I_]; ++ireg) {
+            if (TRT(ireg, jreg) != RT_TEMPER) continue;
+            int iW = RB(ireg, jreg, WEST), iE = RB(ireg, jreg, EAST);
+            int jS = RB(ireg, jreg, SOUTH), jN = RB(ireg, jreg, NORTH);
+            for (j = jS + 1; j <= jN; ++j)
+                for (i = iW + 1; i <= iE; ++i) {
+                    ind = (j - 2) * (nx - 1) + i - 1;
+                    AA(1, ind) = dZero; AA(2, ind) = dOne; AA(3, ind) = dZero; b[ind - 1] = dZero;
+                }
+        }
+    { const int32_t n = (nx - 1) * (ny - 1); orc_alttridlu_(&n, a, b); }   /* :270 */
+    for (j = 2; j <= ny; ++j)                                       /* :274-279 */
+        for (i = 2; i <= nx; ++i) {
+            ind = (j - 2) * (nx - 1) + i - 1;
+            A(t, i, j) = A(t, i, j) + b[ind - 1];
+        }
+#undef AA
+}
+
+/* EqState, src/thermal.f:283-327 */
+void orc_eqstate_(const int32_t *nx_, const int32_t *ny_, const double *uref_, const double *densref_,
+                  const double *tmax_, const double *tref_, const double *rconst_,
+                  const double *p, const double *t, double *den) {
+    const int nx = *nx_, ny = *ny_;
+    const double uref = *uref_, densref = *densref_, tmax = *tmax_, tref = *tref_, rconst = *rconst_;
+    const double dZero = 0.0, dOne = 1.0;
+    const double pref = densref * rconst * tref;
+    for (int j = 2; j <= ny; ++j)
+        for (int i = 2; i <= nx; ++i) {
+            const double c1 = A(p, i, j) * densref * (uref * uref) + pref;   /* uref**2 */
+            const double c2 = densref * rconst * (A(t, i, j) * (tmax - tref) + tref);
+            A(den, i, j) = c1 / c2 - dOne;
+            if (fabs(A(den, i, j)) < 1.e-10) A(den, i, j) = dZero;
+        }
+}
+
 /* ================================== main.f ======================================= */
 
 typedef struct orc_state {
@@ -1676,13 +1842,15 @@ void orc_coldstart(const wolfd2_params *par, const wolfd2_regions *reg, const wo
     orc_velboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nMomBdTp, reg->dBCVal, u, v);
 }
 
-/* Step body, src/main.f:690-981 for nthermen=0, neqstate=0, nsmallscl=0 (cold flow).
- * t and d are passed so that the copies/norms of :696-704, :857-870, :965 are reproduced. */
-int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
-                 double *u, double *v, double *p, double *t, double *d,
-                 int32_t nsteps, wolfd2_step_log *logs) {
+/* Step body, src/main.f:690-981 with nsmallscl=0.  th == NULL (or th->nthermen == 0): cold flow;
+ * otherwise the momentum-energy iterations with ThermEnergy / EqState (:736-880), Filter(_T_) (:890)
+ * and TempBoundCond (:955).  t and d are passed in either case (copies/norms of :696-704, :857-870, :965). */
+int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
+                         const wolfd2_thermal *th, double *u, double *v, double *p, double *t, double *d,
+                         int32_t nsteps, wolfd2_step_log *logs) {
     const int32_t nx = par->nx, ny = par->ny;
-    const int32_t cU = _U_, cV = _V_;
+    const int32_t cU = _U_, cV = _V_, cT = _T_;
+    const int nthermen = th ? th->nthermen : 0, neqstate = th ? th->neqstate : 0;
     int i, j;
     step_work();
     double *un = S_un, *vn = S_vn, *pn = S_pn, *tn = S_tn, *dn = S_dn, *us = S_us, *vs = S_vs, *ts = S_ts;
@@ -1693,7 +1861,7 @@ int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolf
                 A(tn, i, j) = A(t, i, j); A(dn, i, j) = A(d, i, j);
             }
         int nmeiter = par->nmeiter;
-        if (nmeiter > 0) nmeiter = 1;                                  /* :736 (nthermen != 1) */
+        if (nthermen != 1 && nmeiter > 0) nmeiter = 1;                 /* :736 */
         int32_t nQLiter = 0, nSorConv = 0;
         for (int l = 1; l <= nmeiter; ++l) {
             for (j = 0; j <= ny + 1; ++j)                              /* :741-747 */
@@ -1722,14 +1890,32 @@ int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolf
                          m->dju, m->djv, m->yeu, m->xzv, m->yzu, m->xev, p, us, vs);                   /* :820 */
             orc_velboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nMomBdTp, reg->dBCVal, us, vs);   /* :829 */
             orc_presboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp, reg->dBCVal, p);
-            /* :857-859 norms are computed but only used for the M-E test (l>1), skipped at nmeiter=1 */
+            if (nthermen == 1)                                         /* :840-850 */
+                orc_thermenergy_(&nx, &ny, reg->nReg, reg->nRegBrd, th->nTRgType, th->nTemBdTp, &par->dk, &th->pe,
+                                 th->dTRgVal, th->dHGSTval, reg->dBCVal, m->rau, m->rbu, m->rbv, m->rgv, m->djc,
+                                 m->xeu, m->yeu, m->xzv, m->yzv, m->xec, m->yec, m->xzc, m->yzc,
+                                 un, vn, us, vs, tn, ts);
+            if (orc_errflag) return 1;
+            if (neqstate == 1)                                         /* :853-855 */
+                orc_eqstate_(&nx, &ny, &th->uref, &th->densref, &th->tmax, &th->tref, &th->rconst, p, ts, d);
+            double dme[3];                                             /* :857-859 */
+            dme[0] = orc_diffmaxnorm_(&nx, &ny, u, us);
+            dme[1] = orc_diffmaxnorm_(&nx, &ny, v, vs);
+            dme[2] = orc_diffmaxnorm_(&nx, &ny, t, ts);
             for (j = 0; j <= ny + 1; ++j)                              /* :864-870 */
                 for (i = 0; i <= nx + 1; ++i) {
                     A(u, i, j) = A(us, i, j); A(v, i, j) = A(vs, i, j); A(t, i, j) = A(ts, i, j);
                 }
+            double dmemax = dme[0] > dme[1] ? dme[0] : dme[1];         /* :873-877 */
+            dmemax = dmemax > dme[2] ? dmemax : dme[2];
+            if (l > 1 && th && dmemax < th->dmeittol) break;
         }
+        if (nthermen == 1 && th->nfiltt == 1)                          /* :890-894 */
+            orc_filter_(&nx, &ny, &cT, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp, th->nTRgType, &th->fpt, t);
         orc_velboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nMomBdTp, reg->dBCVal, u, v);         /* :946 */
         orc_presboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp, reg->dBCVal, p);
+        if (nthermen == 1)                                             /* :955 */
+            orc_tempboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, th->nTRgType, th->nTemBdTp, th->dTRgVal, reg->dBCVal, t);
         double dif[4];
         dif[0] = orc_diffmaxnorm_(&nx, &ny, pn, p);                    /* :962-965 */
         dif[1] = orc_diffmaxnorm_(&nx, &ny, un, u);
@@ -1747,4 +1933,10 @@ int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolf
         if (difmax > 1.e12) { fprintf(stderr, "* Solution diverged. Please reduce CFL number.\n"); return 2; } /* :969-972 */
     }
     return 0;
+}
+
+int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
+                 double *u, double *v, double *p, double *t, double *d,
+                 int32_t nsteps, wolfd2_step_log *logs) {
+    return orc_step_thermal(par, reg, m, NULL, u, v, p, t, d, nsteps, logs);
 }

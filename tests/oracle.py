@@ -54,6 +54,10 @@ class Oracle:
                                       C.POINTER(_abi.Metrics)] + [_abi.c_f64p] * 5 + \
                                      [C.c_int32, C.POINTER(_abi.StepLog)]
         self.lib.orc_step.restype = C.c_int32
+        self.lib.orc_step_thermal.argtypes = [C.POINTER(_abi.Params), C.POINTER(_abi.Regions), C.POINTER(_abi.Metrics),
+                                              C.POINTER(_abi.Thermal)] + [_abi.c_f64p] * 5 + \
+                                             [C.c_int32, C.POINTER(_abi.StepLog)]
+        self.lib.orc_step_thermal.restype = C.c_int32
         self.lib.orc_ppe_matrix.argtypes = [C.c_int32, C.c_int32, _abi.c_i32p, _abi.c_i32p, _abi.c_i32p,
                                             _abi.c_f64p, _abi.c_f64p, _abi.c_f64p, _abi.c_f64p]
         self.lib.orc_grid.argtypes = [C.c_int32, C.c_int32, C.c_double, _abi.c_f64p, _abi.c_f64p,
@@ -99,8 +103,13 @@ class Oracle:
         t = deck.new_field() if t is None else t
         d = deck.new_field() if d is None else d
         logs = (_abi.StepLog * nsteps)()
-        rc = self.lib.orc_step(C.byref(par), C.byref(reg), C.byref(met),
-                               *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)
+        if getattr(deck, "thermal", False):
+            th = deck.thermal_struct()
+            rc = self.lib.orc_step_thermal(C.byref(par), C.byref(reg), C.byref(met), C.byref(th),
+                                           *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)
+        else:
+            rc = self.lib.orc_step(C.byref(par), C.byref(reg), C.byref(met),
+                                   *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)
         return rc, [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, dif=list(l.dif)) for l in logs]
 
 

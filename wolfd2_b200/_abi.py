@@ -43,6 +43,12 @@ SIGNATURES = {
     # src/utility.f:446, 479
     "diffmaxnorm_": (C.c_double, "ii" "DD"),
     "dmaxnorm_": (C.c_double, "ii" "D"),
+    # src/bound_cond.f:1030-1034
+    "tempboundcond_": (None, "ii" "II" "II" "DD" "D"),
+    # src/thermal.f:24-33
+    "thermenergy_": (None, "ii" "II" "II" "dd" "DDD" "DDDDD" "DDDD" "DDDD" "DDDDDD"),
+    # src/thermal.f:283-285
+    "eqstate_": (None, "ii" "ddddd" "DDD"),
 }
 
 _KIND = {"i": c_i32p, "o": c_i32p, "d": c_f64p, "I": c_i32p, "D": c_f64p}
@@ -127,6 +133,15 @@ METRIC_NAMES = ("rau rbu rbv rgv ran rbn rgn rac rbc rgc dju djv djc djn "
 
 class Metrics(C.Structure):
     _fields_ = [(n, c_f64p) for n in METRIC_NAMES]
+
+
+class Thermal(C.Structure):
+    """wolfd2_thermal of include/wolfd2_b200.h."""
+    _fields_ = [("nthermen", C.c_int32), ("neqstate", C.c_int32), ("nfiltt", C.c_int32), ("reserved_", C.c_int32),
+                ("pe", C.c_double), ("dmeittol", C.c_double), ("fpt", C.c_double),
+                ("uref", C.c_double), ("densref", C.c_double), ("tmax", C.c_double), ("tref", C.c_double),
+                ("rconst", C.c_double),
+                ("nTRgType", c_i32p), ("nTemBdTp", c_i32p), ("dTRgVal", c_f64p), ("dHGSTval", c_f64p)]
 
 
 class StepLog(C.Structure):

@@ -19,12 +19,12 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import Metrics, Params, Regions, StepLog, c_f64p
+from ._abi import Metrics, Params, Regions, StepLog, Thermal, c_f64p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwolfd2_b200.so")
 
-F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B = range(11)
+F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B, F_T, F_TS, F_TN = range(14)
 
 _lib = None
 _fn = None
@@ -56,6 +56,7 @@ def lib():
     L.wolfd2_b200_destroy.argtypes = [C.c_void_p]
     L.wolfd2_b200_destroy.restype = None
     L.wolfd2_b200_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.wolfd2_b200_set_thermal.argtypes = [C.c_void_p, C.POINTER(Thermal)]
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_coldstart.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -111,6 +112,9 @@ VelBoundCond = _routine("velboundcond")
 PresBoundCond = _routine("presboundcond")
 VelOutflowBCs = _routine("veloutflowbcs")
 Filter = _routine("filter")
+TempBoundCond = _routine("tempboundcond")
+ThermEnergy = _routine("thermenergy")
+EqState = _routine("eqstate")
 DiffMaxNorm = _routine("diffmaxnorm")
 DMaxNorm = _routine("dmaxnorm")
 
@@ -132,6 +136,9 @@ class Context:
             _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
                    "wolfd2_b200_create")
         self._h = h
+        if getattr(deck, "thermal", False):
+            self._th = deck.thermal_struct()
+            _check(L.wolfd2_b200_set_thermal(h, C.byref(self._th)), "wolfd2_b200_set_thermal")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -150,6 +157,14 @@ class Context:
         for k, v in kw.items():
             setattr(self._par, k, v)
         _check(lib().wolfd2_b200_set_params(self._h, C.byref(self._par)), "wolfd2_b200_set_params")
+
+    def set_thermal(self, **kw):
+        """Change fields of the wolfd2_thermal block (e.g. nthermen=0) for the following steps."""
+        if not hasattr(self, "_th"):
+            self._th = self.deck.thermal_struct()
+        for k, v in kw.items():
+            setattr(self._th, k, v)
+        _check(lib().wolfd2_b200_set_thermal(self._h, C.byref(self._th)), "wolfd2_b200_set_thermal")
 
     def upload(self, which, arr):
         assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]

@@ -211,6 +211,10 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     W2_TRY(balloc(c, &c->pmask, 1));
     W2_TRY(balloc(c, &c->xmask, 1));
     W2_TRY(balloc(c, &c->ymask, 1));
+    W2_TRY(balloc(c, &c->tmask, 1));
+    W2_TRY(falloc(c, &c->heat_s));
+    W2_CUDA(cudaMalloc((void **)&c->dth, sizeof(W2Thermal)));
+    c->th.pe = 1.0;
     // chain arrays are read in whole segments by the tridiagonal solver: pad generously
     const long long nmax = ((long long)nx * (long long)ny / 4096 + 3) * 4096;
     if (world == 1) {   // chain-layout work of the line solvers and of the AltTridLU shim (one GPU only)
@@ -241,7 +245,8 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);
     ffree(c, c->dus); ffree(c, c->dvs); ffree(c, c->div); ffree(c, c->x1); ffree(c, c->qh);
-    bfree(c, c->pmask); bfree(c, c->xmask); bfree(c, c->ymask); bfree(c, c->pormap);
+    bfree(c, c->pmask); bfree(c, c->xmask); bfree(c, c->ymask); bfree(c, c->pormap); bfree(c, c->tmask);
+    ffree(c, c->heat_s); cudaFree(c->dth);
     w2_peer_release(c);   // before the buffers the peers have mapped go away
     for (int k = 0; k < 4; ++k) ffree(c, c->sorf_buf[k]);
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
@@ -344,6 +349,7 @@ extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const doub
     if (!c || !host || which < 0 || which >= W2_F_COUNT) return W2_ERR_BAD_ARG;
     W2_CUDA(cudaSetDevice(c->device));
     W2_TRY(w2_upload2d(c, c->fld[which], host));
+    if (which == W2_F_D || which == W2_F_DN) c->dn_valid = 0;
     W2_CUDA(cudaStreamSynchronize(c->stream));
     return W2_OK;
 }

@@ -26,6 +26,10 @@ struct MomArgs {
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
     const unsigned char *xmask, *ymask;
     const double *x1;  // first-step solution, field layout
+    // thermal energy equation (COMP 2, thermal.f:24-272): time-level-n temperature, heat source, fixed-T mask
+    const double *tn, *heat, *rau, *rbu, *rbv, *rgv, *djc;
+    const unsigned char *tmask;
+    double pe;
     // porous regions (RM_POROUS): per-cell region maps, see por_map_kernel
     int porous;
     const W2Regions *R;
@@ -39,11 +43,16 @@ namespace mom_po { constexpr bool kPorous = true;
 #include "w2_mom_rows.inc"
 }
 
-// chain index e (0-based, reference ordering momentum.f:353 / :677) -> grid point
+// Chain geometry (0-based index e, reference ordering momentum.f:353 / :677, thermal.f:155):
+// COMP 0 = u: i=1..nx, j=2..ny;  COMP 1 = v: i=2..nx, j=1..ny;  COMP 2 = t: i=2..nx, j=2..ny
+#define CH_W(COMP, nx) ((COMP) == 0 ? (nx) : (nx) - 1)   /* unknowns per grid row */
+#define CH_I0(COMP) ((COMP) == 0 ? 1 : 2)
+#define CH_J0(COMP) ((COMP) == 1 ? 1 : 2)
 template <int COMP>
 __device__ __forceinline__ void chain_ij(const MomArgs &m, long long e, int &i, int &j) {
-    if (COMP == 0) { const int jj = (int)(e / m.nx); j = 2 + jj; i = 1 + (int)(e - (long long)jj * m.nx); }
-    else { const int w = m.nx - 1; const int jj = (int)(e / w); j = 1 + jj; i = 2 + (int)(e - (long long)jj * w); }
+    const int w = CH_W(COMP, m.nx);
+    const int jj = (int)(e / w);
+    j = CH_J0(COMP) + jj; i = CH_I0(COMP) + (int)(e - (long long)jj * w);
 }
 
 // Walking a segment in the coalesced mapping (element t, t+TRI_T, ...): one 64-bit division per thread for
@@ -53,12 +62,12 @@ template <int COMP>
 struct ChainWalk {
     int w, j, pos;   // row length, current row, 0-based position in the row
     __device__ __forceinline__ ChainWalk(const MomArgs &m, long long e) {
-        w = COMP == 0 ? m.nx : m.nx - 1;
+        w = CH_W(COMP, m.nx);
         const long long jj = e / w;
-        j = (COMP == 0 ? 2 : 1) + (int)jj;
+        j = CH_J0(COMP) + (int)jj;
         pos = (int)(e - jj * w);
     }
-    __device__ __forceinline__ int i() const { return (COMP == 0 ? 1 : 2) + pos; }
+    __device__ __forceinline__ int i() const { return CH_I0(COMP) + pos; }
     __device__ __forceinline__ void advance(int d) {       // d of the order of w or less
         pos += d;
         while (pos >= w) { pos -= w; ++j; }
@@ -334,6 +343,8 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xev = t.xev; m.yev = t.yev; m.xzv = t.xzv; m.yzv = t.yzv;
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->x1;
+    m.tn = c->fld[W2_F_TN]; m.heat = c->heat_s; m.tmask = c->tmask; m.pe = c->th.pe;
+    m.rau = t.rau; m.rbu = t.rbu; m.rbv = t.rbv; m.rgv = t.rgv; m.djc = t.djc;
     m.porous = c->hreg.has_porous; m.R = c->dreg;
     unsigned char *pm = c->pormap;   // planes are nelem bytes apart; the row shift is in the base pointer
     m.xd1 = pm; m.xd2 = pm + c->nelem; m.yd1 = pm + 2 * c->nelem; m.yd2 = pm + 3 * c->nelem;
@@ -354,21 +365,21 @@ static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
 // there after the second split step (mom_tail_exchange).
 template <int COMP>
 static void chain_range(const wolfd2_ctx *c, long long &lo, long long &hi) {
-    const int r0 = c->E0 > (COMP == 0 ? 2 : 1) ? c->E0 : (COMP == 0 ? 2 : 1);
+    const int r0 = c->E0 > CH_J0(COMP) ? c->E0 : CH_J0(COMP);
     const int r1 = c->E1 < c->ny ? c->E1 : c->ny;
-    if (COMP == 0) { lo = (long long)(r0 - 2) * c->nx; hi = (long long)(r1 - 1) * c->nx; }
-    else { lo = (long long)(r0 - 1) * (c->nx - 1); hi = (long long)r1 * (c->nx - 1); }
+    lo = (long long)(r0 - CH_J0(COMP)) * CH_W(COMP, c->nx);
+    hi = (long long)(r1 + 1 - CH_J0(COMP)) * CH_W(COMP, c->nx);
 }
 
 template <int COMP>
 static int chain_pieces(const wolfd2_ctx *c, double *f, long long e0, long long e1, W2Piece *pc, int maxpc) {
-    const int w = COMP == 0 ? c->nx : c->nx - 1;
+    const int w = CH_W(COMP, c->nx);
     int np = 0;
     for (long long e = e0; e < e1;) {
         const long long jj = e / w;
         const int off = (int)(e - jj * w);
         const long long cnt = (e1 - e) < (long long)(w - off) ? (e1 - e) : (long long)(w - off);
-        const int j = (COMP == 0 ? 2 : 1) + (int)jj, i = (COMP == 0 ? 1 : 2) + off;
+        const int j = CH_J0(COMP) + (int)jj, i = CH_I0(COMP) + off;
         if (np >= maxpc) return -1;
         pc[np].p = f + (size_t)i + (size_t)c->pitch * (size_t)j;
         pc[np].n = (size_t)cnt;
@@ -448,6 +459,19 @@ int w2_ymomentum(wolfd2_ctx *c, double *dvs) {
     const long long n = (long long)(c->nx - 1) * c->ny;
     W2_TRY((mom_solve<1, 1>(c, m, n, c->x1)));   // :675-716
     W2_TRY((mom_solve<1, 2>(c, m, n, dvs)));     // :723-834
+    return W2_OK;
+}
+
+// ThermEnergy's two split steps (thermal.f:153-270) on the chain of (nx-1)(ny-1) temperature unknowns; the
+// increment lands in dts (field layout).  The convective coefficients come from us, vs (first argument pair of
+// the reference call, main.f:849) and un, vn; TempBoundCond and the update t += dts are the caller's.
+int w2_thermal_solve(wolfd2_ctx *c, double *dts) {
+    if (c->world > 1) { w2_set_error("the thermal energy equation is not supported on several GPUs"); return W2_ERR_UNSUPPORTED; }
+    MomArgs m;
+    fill_args(c, m);
+    const long long n = (long long)(c->nx - 1) * (c->ny - 1);
+    W2_TRY((mom_solve_impl<2, 1, false>(c, m, n, c->x1)));
+    W2_TRY((mom_solve_impl<2, 2, false>(c, m, n, dts)));
     return W2_OK;
 }
 

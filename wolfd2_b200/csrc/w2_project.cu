@@ -78,18 +78,21 @@ __global__ void __launch_bounds__(256) filter_region_kernel(int pitch, double fp
 }
 
 int w2_filter(wolfd2_ctx *c, int ncomp, double fp, double *qu) {
-    if (ncomp != W2_U && ncomp != W2_V) {
-        w2_set_error("Wrong ncomp flag passed to Filter: %d (device supports _U_, _V_)", ncomp);  // :232-234
+    if (ncomp != W2_U && ncomp != W2_V && ncomp != W2_T) {
+        w2_set_error("Wrong ncomp flag passed to Filter: %d", ncomp);  // :232-234
         return W2_ERR_BAD_ARG;
     }
     if (!c->qh) W2_TRY(w2_alloc_field(c, &c->qh));
     W2_TRY(w2_copy_field(c, c->qh, qu));  // :72-76
     const W2Regions &R = c->hreg;
     for (int q = 0; q < R.nreg; ++q) {
-        if (R.type[q] == W2_RM_BLOCKG) continue;
+        if (ncomp == W2_T ? c->hth.ttype[q] == W2_BT_TEMPER /* sic: a BT_ constant against nTRgType, :212 */
+                          : R.type[q] == W2_RM_BLOCKG) continue;
         const int iW = R.iW[q], iE = R.iE[q], jS = R.jS[q], jN = R.jN[q];
         int ilo, ihi, jlo, jhi;
-        if (ncomp == W2_U) {
+        if (ncomp == W2_T) {   // :221-226
+            ilo = iW + 1; ihi = iE; jlo = jS + 1; jhi = jN;
+        } else if (ncomp == W2_U) {
             const int bW = R.bd[q][W2_WEST - 1], bE = R.bd[q][W2_EAST - 1];
             ilo = (bW == W2_BM_OUTLT1) ? iW : iW + 1;
             ihi = (bE == W2_BM_INTERN || bE == W2_BM_OUTLT1) ? iE : iE - 1;

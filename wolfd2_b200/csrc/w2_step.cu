@@ -31,56 +31,85 @@ extern "C" int wolfd2_b200_coldstart(wolfd2_ctx *c, int32_t *nSorConv) {
 }
 
 static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
-    double *u = c->fld[W2_F_U], *v = c->fld[W2_F_V], *p = c->fld[W2_F_P];
-    double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS];
-    double *un = c->fld[W2_F_UN], *vn = c->fld[W2_F_VN], *pn = c->fld[W2_F_PN];
+    double *u = c->fld[W2_F_U], *v = c->fld[W2_F_V], *p = c->fld[W2_F_P], *t = c->fld[W2_F_T];
+    double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS], *ts = c->fld[W2_F_TS];
+    double *un = c->fld[W2_F_UN], *vn = c->fld[W2_F_VN], *pn = c->fld[W2_F_PN], *tn = c->fld[W2_F_TN];
+    const bool thermal = c->th.nthermen == 1;
     cudaStream_t s = c->stream;
     cudaEventRecord(c->ev[0], s);
-    // :696-704  time-level n copies (t is identically zero on this path; d never changes, so
-    // dn == d and both stay as uploaded)
+    // :696-704  time-level n copies (without the thermal energy equation t is identically zero; d only
+    // changes through EqState, so dn is refreshed only then)
     W2_TRY(w2_copy_field(c, un, u));
     W2_TRY(w2_copy_field(c, vn, v));
-    W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D]));
-    // :741-747  starred quantities (nmeiter is forced to 1 without thermal energy, :736)
-    W2_TRY(w2_copy_field(c, us, u));
-    W2_TRY(w2_copy_field(c, vs, v));
+    if (thermal) W2_TRY(w2_copy_field(c, tn, t));
+    if (thermal || !c->dn_valid) { W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D])); c->dn_valid = 1; }
+    int nme = c->par.nmeiter;
+    if (!thermal && nme > 0) nme = 1;                        // :736
     int nQL = -1, nSor = 0, conv = 0;
-    // us == un here, so the initialisation loop of nAuxMomentum (:114-119) is a no-op
-    W2_TRY(w2_nauxmomentum(c, /*init_star=*/0, &nQL));   // :753
-    // The momentum solve does not read p; step_host uploads p on a second stream meanwhile.  pn <- p (:696)
-    // therefore happens here, after that upload has landed.
-    if (c->p_pending) { W2_CUDA(cudaStreamWaitEvent(s, c->ev_p, 0)); c->p_pending = 0; }
-    W2_TRY(w2_copy_field(c, pn, p));
-    cudaEventRecord(c->ev[1], s);
-    if (c->par.nfiltu == 1) W2_TRY(w2_filter(c, W2_U, c->par.fpu, us));   // :783
-    if (c->par.nfiltv == 1) W2_TRY(w2_filter(c, W2_V, c->par.fpv, vs));   // :788
-    W2_TRY(w2_vel_bc(c, us, vs));                   // :793
-    W2_TRY(w2_pres_bc(c, p));                       // :797
-    cudaEventRecord(c->ev[2], s);
-    W2_TRY(w2_ppe(c, us, vs, p, &nSor, &conv));     // :803
-    cudaEventRecord(c->ev[3], s);
-    W2_TRY(w2_pres_bc(c, p));                       // :813
-    W2_TRY(w2_project(c, p, us, vs));               // :820
-    W2_TRY(exchange_uv(c, us, vs));
-    W2_TRY(w2_vel_bc(c, us, vs));                   // :829
-    W2_TRY(w2_pres_bc(c, p));                       // :833
-    W2_TRY(w2_copy_field(c, u, us));                // :864-870
-    W2_TRY(w2_copy_field(c, v, vs));
+    for (int l = 1; l <= nme; ++l) {                         // momentum-energy iterations, :738-880
+        // :741-747  starred quantities
+        W2_TRY(w2_copy_field(c, us, u));
+        W2_TRY(w2_copy_field(c, vs, v));
+        if (thermal) W2_TRY(w2_copy_field(c, ts, t));
+        // us == un on the first pass, so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
+        // on later passes it resets us, vs to un, vn as the reference does
+        W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1, &nQL));   // :753
+        if (l == 1) {
+            // The momentum solve does not read p; step_host uploads p on a second stream meanwhile.  pn <- p
+            // (:696) therefore happens here, after that upload has landed.
+            if (c->p_pending) { W2_CUDA(cudaStreamWaitEvent(s, c->ev_p, 0)); c->p_pending = 0; }
+            W2_TRY(w2_copy_field(c, pn, p));
+            cudaEventRecord(c->ev[1], s);
+        }
+        if (c->par.nfiltu == 1) W2_TRY(w2_filter(c, W2_U, c->par.fpu, us));   // :783
+        if (c->par.nfiltv == 1) W2_TRY(w2_filter(c, W2_V, c->par.fpv, vs));   // :788
+        W2_TRY(w2_vel_bc(c, us, vs));                   // :793
+        W2_TRY(w2_pres_bc(c, p));                       // :797
+        if (l == 1) cudaEventRecord(c->ev[2], s);
+        W2_TRY(w2_ppe(c, us, vs, p, &nSor, &conv));     // :803
+        if (l == 1) cudaEventRecord(c->ev[3], s);
+        W2_TRY(w2_pres_bc(c, p));                       // :813
+        W2_TRY(w2_project(c, p, us, vs));               // :820
+        W2_TRY(exchange_uv(c, us, vs));
+        W2_TRY(w2_vel_bc(c, us, vs));                   // :829
+        W2_TRY(w2_pres_bc(c, p));                       // :833
+        if (thermal) W2_TRY(w2_thermenergy(c, ts));     // :840-850
+        if (thermal && c->th.neqstate == 1) W2_TRY(w2_eqstate(c, p, ts, c->fld[W2_F_D]));   // :853-855
+        double dme[3] = {0, 0, 0};
+        if (nme > 1) {                                  // :857-859 (only the l > 1 test reads them)
+            W2_TRY(w2_norm_reset(c));
+            W2_TRY(w2_diffmaxnorm_async(c, u, us, 0));
+            W2_TRY(w2_diffmaxnorm_async(c, v, vs, 1));
+            W2_TRY(w2_diffmaxnorm_async(c, t, ts, 2));
+            W2_TRY(w2_norm_fetch(c, 3, dme));
+        }
+        W2_TRY(w2_copy_field(c, u, us));                // :864-870
+        W2_TRY(w2_copy_field(c, v, vs));
+        if (thermal) W2_TRY(w2_copy_field(c, t, ts));
+        double dmemax = dme[0] > dme[1] ? dme[0] : dme[1];
+        dmemax = dmemax > dme[2] ? dmemax : dme[2];
+        if (l > 1 && dmemax < c->th.dmeittol) break;    // :873-877
+    }
+    if (thermal && c->th.nfiltt == 1) W2_TRY(w2_filter(c, W2_T, c->th.fpt, t));   // :890-894
     W2_TRY(w2_vel_bc(c, u, v));                     // :946
     W2_TRY(w2_pres_bc(c, p));                       // :950
+    if (thermal) W2_TRY(w2_temp_bc(c, t));          // :955
     W2_TRY(w2_norm_reset(c));
-    W2_TRY(w2_diffmaxnorm_async(c, pn, p, 0));      // :962-964
+    W2_TRY(w2_diffmaxnorm_async(c, pn, p, 0));      // :962-965
     W2_TRY(w2_diffmaxnorm_async(c, un, u, 1));
     W2_TRY(w2_diffmaxnorm_async(c, vn, v, 2));
+    if (thermal) W2_TRY(w2_diffmaxnorm_async(c, tn, t, 3));
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
-    W2_TRY(w2_norm_fetch(c, 3, dif));               // syncs the stream
+    W2_TRY(w2_norm_fetch(c, thermal ? 4 : 3, dif)); // syncs the stream
     float t_tot = 0, t_mom = 0, t_bc1 = 0, t_ppe = 0, t_tail = 0;
-    cudaEventElapsedTime(&t_tot, c->ev[0], c->ev[6]);
-    cudaEventElapsedTime(&t_mom, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&t_bc1, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&t_ppe, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&t_tail, c->ev[3], c->ev[6]);
+    if (nme > 0) {
+        cudaEventElapsedTime(&t_tot, c->ev[0], c->ev[6]);
+        cudaEventElapsedTime(&t_mom, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&t_bc1, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&t_ppe, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&t_tail, c->ev[3], c->ev[6]);
+    }
     c->last_ms[0] += t_tot; c->last_ms[1] += t_mom; c->last_ms[2] += t_ppe; c->last_ms[3] += t_bc1 + t_tail;
     double difmax = dif[0];
     for (int q = 1; q < 4; ++q) difmax = difmax > dif[q] ? difmax : dif[q];
@@ -269,13 +298,64 @@ extern "C" void project_(const int32_t *nx, const int32_t *ny, const int32_t *nR
 extern "C" void filter_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *nReg,
                         const int32_t *nRegBrd, const int32_t *nRegType, const int32_t *nMomBdTp,
                         const int32_t *nTRgType, const double *fp, double *qu) {
-    (void)nTRgType;
     const char *who = "filter_";
     wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
     shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, nullptr, nullptr, nullptr, nullptr, who);
+    if (*ncomp == W2_T) SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nullptr, nullptr, nullptr), who);
     up(c, c->fld[W2_F_US], qu, who);
     SHIM_TRY(w2_filter(c, *ncomp, *fp, c->fld[W2_F_US]), who);
     down(c, qu, c->fld[W2_F_US], who);
+    sync(c, who);
+}
+
+extern "C" void tempboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                               const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal,
+                               const double *dBCVal, double *t) {
+    const char *who = "tempboundcond_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nullptr, nullptr, dBCVal, nullptr, nullptr, nullptr, who);
+    SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nTemBdTp, dTRgVal, nullptr), who);
+    up(c, c->fld[W2_F_T], t, who);
+    SHIM_TRY(w2_temp_bc(c, c->fld[W2_F_T]), who);
+    down(c, t, c->fld[W2_F_T], who);
+    sync(c, who);
+}
+
+extern "C" void thermenergy_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                             const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dk, const double *pe,
+                             const double *dTRgVal, const double *dHGSTval, const double *dBCVal,
+                             const double *rau, const double *rbu, const double *rbv, const double *rgv, const double *djc,
+                             const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+                             const double *xec, const double *yec, const double *xzc, const double *yzc,
+                             const double *un, const double *vn, const double *u, const double *v,
+                             const double *tn, double *t) {
+    const char *who = "thermenergy_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nullptr, nullptr, dBCVal, nullptr, nullptr, nullptr, who);
+    SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nTemBdTp, dTRgVal, dHGSTval), who);
+    c->par.dk = *dk; c->th.pe = *pe;
+    W2Metrics &m = c->met;
+    up(c, m.rau, rau, who); up(c, m.rbu, rbu, who); up(c, m.rbv, rbv, who); up(c, m.rgv, rgv, who); up(c, m.djc, djc, who);
+    up(c, m.xeu, xeu, who); up(c, m.yeu, yeu, who); up(c, m.xzv, xzv, who); up(c, m.yzv, yzv, who);
+    up(c, m.xec, xec, who); up(c, m.yec, yec, who); up(c, m.xzc, xzc, who); up(c, m.yzc, yzc, who);
+    up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
+    up(c, c->fld[W2_F_US], u, who); up(c, c->fld[W2_F_VS], v, who);
+    up(c, c->fld[W2_F_TN], tn, who); up(c, c->fld[W2_F_TS], t, who);
+    cudaMemsetAsync(c->dus + c->row_off, 0, c->nelem * sizeof(double), c->stream);
+    SHIM_TRY(w2_thermenergy(c, c->fld[W2_F_TS]), who);
+    down(c, t, c->fld[W2_F_TS], who);
+    sync(c, who);
+}
+
+extern "C" void eqstate_(const int32_t *nx, const int32_t *ny, const double *uref, const double *densref,
+                         const double *tmax, const double *tref, const double *rconst, const double *p,
+                         const double *t, double *den) {
+    const char *who = "eqstate_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    c->th.uref = *uref; c->th.densref = *densref; c->th.tmax = *tmax; c->th.tref = *tref; c->th.rconst = *rconst;
+    up(c, c->fld[W2_F_P], p, who); up(c, c->fld[W2_F_T], t, who); up(c, c->fld[W2_F_D], den, who);
+    SHIM_TRY(w2_eqstate(c, c->fld[W2_F_P], c->fld[W2_F_T], c->fld[W2_F_D]), who);
+    down(c, den, c->fld[W2_F_D], who);
     sync(c, who);
 }
 

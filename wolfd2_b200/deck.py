@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._abi import METRIC_NAMES, Metrics, Params, Regions, c_f64p, c_i32p
+from ._abi import METRIC_NAMES, Metrics, Params, Regions, Thermal, c_f64p, c_i32p
 
 # include/wolfd2.h:15-59
 RM_BLOCKG, RM_INTERN, RM_POROUS = 0, 1, 2
@@ -25,6 +25,8 @@ BM_INTERN, BM_WALL1, BM_WALL2, BM_INLET, BM_OUTLT1, BM_OUTLT2 = 0, 1, 2, 3, 4, 5
 WEST, EAST, SOUTH, NORTH = 1, 2, 3, 4
 _U_, _V_, _P_, _T_ = 1, 2, 3, 4
 FACE = {"w": WEST, "e": EAST, "s": SOUTH, "n": NORTH}
+RT_NOSRCE, RT_HEATGN, RT_TEMPER = 0, 1, 2
+BT_INTERN, BT_TEMPER, BT_HTFLUX = 0, 1, 2
 PPE_SOLVERS = {"sor": 1, "lsor": 2, "rb_lsor": 3, "par_rb_lsor": 4, "rb_sor": 5, "par_rb_sor": 6}
 
 
@@ -182,6 +184,15 @@ class RegionTables:
         self.nMomBdTp[EAST - 1, :nj, ni - 1] = BM_WALL1
         self.nMomBdTp[SOUTH - 1, 0, :ni] = BM_WALL1
         self.nMomBdTp[NORTH - 1, nj - 1, :ni] = BM_WALL1
+        # thermal defaults (parse.f:2340-2376): no heat source, interfaces inside, adiabatic outer walls
+        self.nTRgType = np.zeros((mgrj, mgri), dtype=np.int32)
+        self.nTemBdTp = np.zeros((4, mgrj, mgri), dtype=np.int32)
+        self.dTRgVal = np.zeros((mgrj, mgri), dtype=np.float64)
+        self.dHGSTval = np.zeros((mgrj, mgri), dtype=np.float64)
+        self.nTemBdTp[WEST - 1, :nj, 0] = BT_HTFLUX
+        self.nTemBdTp[EAST - 1, :nj, ni - 1] = BT_HTFLUX
+        self.nTemBdTp[SOUTH - 1, 0, :ni] = BT_HTFLUX
+        self.nTemBdTp[NORTH - 1, nj - 1, :ni] = BT_HTFLUX
         self._completed = False
 
     # -- statements ------------------------------------------------------------
@@ -245,6 +256,43 @@ class RegionTables:
         self.nRegType[jr - 1, ir - 1] = RM_POROUS
         self._porous = getattr(self, "_porous", {})
         self._porous[(ir, jr)] = (poros, c1, c2)
+        return self
+
+    # -- thermal statements (already non-dimensional values; the reference scales them in parse.f) ------
+    def wall_temperature(self, ir, jr, face, temp):
+        """Fixed-temperature face (BT_TEMPER, e.g. parse.f:1557): ghost = 2*temp - inner."""
+        k = self._k(face)
+        self.nTemBdTp[k - 1, jr - 1, ir - 1] = BT_TEMPER
+        self.dBCVal[_T_ - 1, k - 1, jr - 1, ir - 1] = temp
+        return self
+
+    def wall_heat_flux(self, ir, jr, face, flux=0.0):
+        """Prescribed-flux face (BT_HTFLUX, parse.f:1924): ghost = flux + inner; 0 = adiabatic."""
+        k = self._k(face)
+        self.nTemBdTp[k - 1, jr - 1, ir - 1] = BT_HTFLUX
+        self.dBCVal[_T_ - 1, k - 1, jr - 1, ir - 1] = flux
+        return self
+
+    def heat_generation(self, ir, jr, value):
+        """Region with a (dimensionless) volumetric heat source (RT_HEATGN, parse.f:1789)."""
+        self.nTRgType[jr - 1, ir - 1] = RT_HEATGN
+        self.dHGSTval[jr - 1, ir - 1] = value
+        return self
+
+    def fixed_temperature_region(self, ir, jr, temp):
+        """Region held at `temp` (RT_TEMPER, parse.f:1826-1845): its faces and the neighbours' facing faces
+        become BT_TEMPER with the same value."""
+        ni, nj = int(self.nReg[0]), int(self.nReg[1])
+        self.nTRgType[jr - 1, ir - 1] = RT_TEMPER
+        self.dTRgVal[jr - 1, ir - 1] = temp
+        for k in (WEST, EAST, SOUTH, NORTH):
+            self.nTemBdTp[k - 1, jr - 1, ir - 1] = BT_TEMPER
+            self.dBCVal[_T_ - 1, k - 1, jr - 1, ir - 1] = temp
+        for (di, dj, k) in ((-1, 0, EAST), (1, 0, WEST), (0, -1, NORTH), (0, 1, SOUTH)):
+            i2, j2 = ir + di, jr + dj
+            if 1 <= i2 <= ni and 1 <= j2 <= nj:
+                self.nTemBdTp[k - 1, j2 - 1, i2 - 1] = BT_TEMPER
+                self.dBCVal[_T_ - 1, k - 1, j2 - 1, i2 - 1] = temp
         return self
 
     # -- SetUpBCs post-processing, src/bound_cond.f:165-223 ----------------------
@@ -335,6 +383,17 @@ class Deck:
     fpv: float = 5e2
     x_nodes: np.ndarray = field(default=None, repr=False)
     y_nodes: np.ndarray = field(default=None, repr=False)
+    # thermal energy equation (thermal_energy / eq_state / filter_t of the reference's input deck)
+    thermal: bool = False
+    eqstate: bool = False
+    nfiltt: int = 0
+    fpt: float = 5e2
+    prandtl: float = 0.71
+    dmeittol: float = 1e-6
+    densref: float = 1.2
+    tmax: float = 310.0
+    tref: float = 300.0
+    rconst: float = 287.0
     # one rank's share of a multi-GPU run: (rank, world, J0, J1, A0, A1, HG), wolfd2_b200/slab.py.  nx, ny,
     # regions and params stay global; metrics and fields hold rows A0..A1 only (row 0 = global row A0)
     slab: tuple = None
@@ -358,6 +417,22 @@ class Deck:
         p.qtol, p.sortol, p.sorrel = self.qtol, self.sortol, self.sorrel
         p.fpu, p.fpv = self.fpu, self.fpv
         return p
+
+    @property
+    def pe(self):   # Peclet number, src/file_manip.f
+        return self.re * self.prandtl
+
+    def thermal_struct(self) -> Thermal:
+        t = Thermal()
+        t.nthermen, t.neqstate, t.nfiltt = int(self.thermal), int(self.eqstate), self.nfiltt
+        t.pe, t.dmeittol, t.fpt = self.pe, self.dmeittol, self.fpt
+        t.uref, t.densref, t.tmax, t.tref, t.rconst = self.uref, self.densref, self.tmax, self.tref, self.rconst
+        r = self.regions
+        t.nTRgType = r.nTRgType.ctypes.data_as(c_i32p)
+        t.nTemBdTp = r.nTemBdTp.ctypes.data_as(c_i32p)
+        t.dTRgVal = r.dTRgVal.ctypes.data_as(c_f64p)
+        t.dHGSTval = r.dHGSTval.ctypes.data_as(c_f64p)
+        return t
 
     def metrics_struct(self) -> Metrics:
         m = Metrics()
@@ -525,3 +600,15 @@ def backward_step(n=64, re=100.0, dt=0.01, ny=None, fully_dev=True, **kw) -> Dec
     reg.blockage(1, 1).inlet(1, 2, "w", normal_vel=1.0)
     reg.outlet(2, 1, "e", fully_dev=fully_dev).outlet(2, 2, "e", fully_dev=fully_dev)
     return _mk(f"bstep{nx}x{ny}_re{re:g}", nx, ny, reg, re, dt, **kw)
+
+
+def heated_cavity(n=64, re=100.0, dt=0.01, ny=None, t_hot=1.0, t_cold=0.0, **kw) -> Deck:
+    """Differentially heated cavity: west wall hot, east wall cold, adiabatic top and bottom, buoyancy through
+    the ideal-gas density (EqState) in the v-momentum equation; thermal energy equation on."""
+    nx, ny = n, (ny or n)
+    reg = RegionTables(nx, ny)
+    reg.wall_temperature(1, 1, "w", t_hot).wall_temperature(1, 1, "e", t_cold)
+    kw.setdefault("thermal", True)
+    kw.setdefault("eqstate", True)
+    kw.setdefault("nmeiter", 3)
+    return _mk(f"heated_cavity{nx}x{ny}_re{re:g}", nx, ny, reg, re, dt, **kw)
