@@ -45,7 +45,14 @@ module wolfd2_gpu
     real(c_double)     :: dif(4)
   end type w2_step_log
 
-  integer(c_int32_t), parameter :: W2_F_U = 0, W2_F_V = 1, W2_F_P = 2
+  ! struct wolfd2_thermal: thermal energy equation (thermal.f, main.f:840-894)
+  type, bind(C) :: w2_thermal
+    integer(c_int32_t) :: nthermen, neqstate, nfiltt, reserved
+    real(c_double)     :: pe, dmeittol, fpt, uref, densref, tmax, tref, rconst
+    type(c_ptr)        :: nTRgType, nTemBdTp, dTRgVal, dHGSTval
+  end type w2_thermal
+
+  integer(c_int32_t), parameter :: W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_D = 8, W2_F_T = 11
 
   interface
     ! replaces the compile-time include/config.f:19-26
@@ -104,6 +111,41 @@ module wolfd2_gpu
       integer(c_int32_t), value :: nsteps
       real(c_double), intent(inout) :: u(*), v(*), p(*)
       type(w2_step_log), intent(out) :: logs(*)
+    end function
+
+    ! thermal energy equation on / off for the following steps
+    integer(c_int) function wolfd2_b200_set_thermal(ctx, th) bind(C, name='wolfd2_b200_set_thermal')
+      import :: c_int, c_ptr, w2_thermal
+      type(c_ptr), value :: ctx
+      type(w2_thermal), intent(in) :: th
+    end function
+
+    ! several GPUs (one process each): slab layout, NCCL communicator, slab context
+    integer(c_int) function wolfd2_b200_slab_layout(nx, ny, world, rank, lay) bind(C, name='wolfd2_b200_slab_layout')
+      import :: c_int, c_int32_t
+      integer(c_int32_t), value :: nx, ny, world, rank
+      integer(c_int32_t), intent(out) :: lay(5)
+    end function
+    integer(c_int) function wolfd2_b200_set_device(device) bind(C, name='wolfd2_b200_set_device')
+      import :: c_int, c_int32_t
+      integer(c_int32_t), value :: device
+    end function
+    integer(c_int) function wolfd2_b200_comm_unique_id(id) bind(C, name='wolfd2_b200_comm_unique_id')
+      import :: c_int, c_int8_t
+      integer(c_int8_t), intent(out) :: id(128)
+    end function
+    integer(c_int) function wolfd2_b200_comm_init(rank, world, id) bind(C, name='wolfd2_b200_comm_init')
+      import :: c_int, c_int32_t, c_int8_t
+      integer(c_int32_t), value :: rank, world
+      integer(c_int8_t), intent(in) :: id(128)
+    end function
+    integer(c_int) function wolfd2_b200_create_slab(ctx, par, reg, met, rank, world) bind(C, name='wolfd2_b200_create_slab')
+      import :: c_int, c_int32_t, c_ptr, w2_params, w2_regions, w2_metrics
+      type(c_ptr), intent(out) :: ctx
+      type(w2_params),  intent(in) :: par
+      type(w2_regions), intent(in) :: reg
+      type(w2_metrics), intent(in) :: met
+      integer(c_int32_t), value :: rank, world
     end function
   end interface
 end module wolfd2_gpu

@@ -29,20 +29,27 @@ def cases():
     c["channel22x18_mc"] = d
     d = dk.backward_step(26, re=100.0, dt=0.01, ny=20); d.msorit = 400; d.sorrel = 1.6
     c["bstep26x20"] = d
+    d = dk.heated_cavity(26, re=100.0, dt=0.01, ny=22); d.msorit = 300; d.sorrel = 1.5   # thermal energy + EqState, 3 M-E iterations
+    c["heated_cavity26x22"] = d
     return c
 
 
 def run(d, nsteps=4):
     o = get_oracle()
-    u, v, p = d.new_field(), d.new_field(), d.new_field()
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    thermal = getattr(d, "thermal", False)
+    if thermal:
+        t[:d.ny + 2, :d.nx + 2] = 0.5
     ncold = o.coldstart(d, u, v, p)
     out = {"ncold": np.array(ncold)}
     nql, nsor, dif = [], [], []
     for k in range(nsteps):
-        rc, lg = o.step(d, u, v, p, 1)
+        rc, lg = o.step(d, u, v, p, 1, t=t, d=den)
         assert rc == 0
-        nql.append(lg[0]["nQLiter"]); nsor.append(lg[0]["nSorConv"]); dif.append(lg[0]["dif"][:3])
+        nql.append(lg[0]["nQLiter"]); nsor.append(lg[0]["nSorConv"]); dif.append(lg[0]["dif"][:4 if thermal else 3])
         out[f"u{k}"], out[f"v{k}"], out[f"p{k}"] = u.copy(), v.copy(), p.copy()
+        if thermal:
+            out[f"t{k}"], out[f"d{k}"] = t.copy(), den.copy()
     out["nql"], out["nsor"], out["dif"] = np.array(nql), np.array(nsor), np.array(dif)
     return out
 

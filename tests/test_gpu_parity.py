@@ -353,7 +353,7 @@ def test_ppe_fused_pipeline_bitwise(api, orc, k, T):
         api.set_option("sor_fused_T", -1)
 
 
-@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20"])
+@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20", "heated_cavity26x22"])
 def test_time_steps_against_committed_golden(api, name):
     """CUDA path vs the committed fixtures (tests/golden/*.npz, made by make_golden.py) -- no oracle
     involved at run time."""
@@ -364,14 +364,21 @@ def test_time_steps_against_committed_golden(api, name):
     import make_golden
     d = make_golden.cases()[name]
     ref = np.load(os.path.join(here, "golden", name + ".npz"))
+    thermal = "t0" in ref
+    fields = [("u", api.F_U), ("v", api.F_V), ("p", api.F_P)] + ([("t", api.F_T), ("d", api.F_D)] if thermal else [])
     with api.Context(d) as ctx:
         z = d.new_field()
         for w in (api.F_U, api.F_V, api.F_P):
             ctx.upload(w, z)
+        if thermal:
+            t0 = d.new_field()
+            t0[:d.ny + 2, :d.nx + 2] = 0.5
+            ctx.upload(api.F_T, t0)
         assert ctx.coldstart() == int(ref["ncold"])
         for k in range(4):
             lg = ctx.step(1)[0]
             assert lg["nQLiter"] == int(ref["nql"][k]) and lg["nSorConv"] == int(ref["nsor"][k])
-            for f, w in (("u", api.F_U), ("v", api.F_V), ("p", api.F_P)):
+            for f, w in fields:
                 assert rel_l2(ctx.download(w), ref[f"{f}{k}"]) <= TOL_STEP, (name, f, k)
-            np.testing.assert_allclose(lg["dif"][:3], ref["dif"][k], rtol=1e-9, atol=1e-14)
+            n = ref["dif"].shape[1]
+            np.testing.assert_allclose(lg["dif"][:n], ref["dif"][k], rtol=1e-9, atol=1e-14)

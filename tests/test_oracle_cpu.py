@@ -186,6 +186,11 @@ def test_subscript_checked_build_runs_clean():
         o.coldstart(d, u, v, p)
         rc, _ = o.step(d, u, v, p, 2)
         assert rc == 0 and o.lib.orc_get_errflag() == 0
+    d = dk.heated_cavity(19, re=100.0, dt=0.005, ny=15, nfiltt=1)       # ThermEnergy, TempBoundCond, EqState, Filter(_T_)
+    d.msorit = 30
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    rc, _ = o.step(d, u, v, p, 2, t=t, d=den)
+    assert rc == 0 and o.lib.orc_get_errflag() == 0
 
 
 # ------------------------------------------------------------------ external physical check
@@ -221,7 +226,7 @@ def test_cavity_matches_ghia_at_doubled_reynolds(orc):
 
 
 # ------------------------------------------------------------------ regression fixtures
-@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20"])
+@pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20", "heated_cavity26x22"])
 def test_oracle_reproduces_golden_fixtures(orc, name):
     import make_golden
     d = make_golden.cases()[name]
@@ -230,5 +235,46 @@ def test_oracle_reproduces_golden_fixtures(orc, name):
     assert int(got["ncold"]) == int(ref["ncold"])
     assert np.array_equal(got["nql"], ref["nql"]) and np.array_equal(got["nsor"], ref["nsor"])
     for k in range(4):
-        for f in "uvp":
+        for f in ("uvptd" if f"t0" in ref else "uvp"):
             assert np.array_equal(got[f"{f}{k}"], ref[f"{f}{k}"]), (name, f, k)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Thermal energy row: analytic pins of ThermEnergy + TempBoundCond
+
+def _conduction_deck(regions, n=24, ny=20, re=10.0):
+    pe = re * 0.71
+    h = 1.0 / (n - 1)
+    dt = 0.2 * pe * h * h          # the split steps give no implicit j-coupling: keep dt/(Pe h^2) small
+    d = dk._mk("conduction", n, ny, regions, re, dt, thermal=True, eqstate=False, nmeiter=1, sortol=1e-8, msorit=50)
+    return d, pe, h, int(6 * pe / dt)
+
+
+def test_pure_conduction_reaches_the_linear_profile(orc):
+    """Fluid at rest between a hot (T=1) and a cold (T=0) wall, adiabatic top and bottom: the steady state of
+    the thermal energy equation is the linear profile, whatever the split steps do on the way."""
+    reg = dk.RegionTables(24, 20).wall_temperature(1, 1, "w", 1.0).wall_temperature(1, 1, "e", 0.0)
+    d, pe, h, steps = _conduction_deck(reg)
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    t[:d.ny + 2, :d.nx + 2] = 0.5
+    rc, logs = orc.step(d, u, v, p, steps, t=t, d=den)
+    assert rc == 0 and np.abs(u).max() == 0.0 and np.abs(v).max() == 0.0
+    x = (np.arange(2, d.nx + 1) - 1.5) / (d.nx - 1)        # cell centres between the walls at i = 1 and i = nx
+    assert np.abs(t[2:d.ny + 1, 2:d.nx + 1] - (1.0 - x)[None, :]).max() < 1e-12
+    assert logs[-1]["dif"][3] < 1e-14
+
+
+def test_uniform_heat_source_gives_the_discrete_parabola(orc):
+    """Both walls at T=0, uniform source s: steady T = (s Pe / 4) (x(1-x) + h^2/4) exactly on this grid -- the
+    h^2/4 is the linear ghost extrapolation at the walls, the 1/4 (not 1/2) is the reference's dk*s/2 source
+    term entering one split step only (thermal.f:198)."""
+    s = 3.0
+    reg = dk.RegionTables(24, 20).wall_temperature(1, 1, "w", 0.0).wall_temperature(1, 1, "e", 0.0)
+    reg.heat_generation(1, 1, s)
+    d, pe, h, steps = _conduction_deck(reg)
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    rc, _ = orc.step(d, u, v, p, steps, t=t, d=den)
+    assert rc == 0
+    x = (np.arange(2, d.nx + 1) - 1.5) / (d.nx - 1)
+    exact = s * pe / 4.0 * (x * (1.0 - x) + h * h / 4.0)
+    assert np.abs(t[2:d.ny + 1, 2:d.nx + 1] - exact[None, :]).max() < 1e-11
