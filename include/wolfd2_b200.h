@@ -98,6 +98,32 @@ typedef struct wolfd2_thermal {
 enum { W2_RT_NOSRCE = 0, W2_RT_HEATGN = 1, W2_RT_TEMPER = 2 };
 enum { W2_BT_INTERN = 0, W2_BT_TEMPER = 1, W2_BT_HTFLUX = 2 };
 
+/* ATD small-scale model: the arguments of SmallScale (src/small_scale.f:31-49) that main.f
+ * passes at src/main.f:647-665 and :912-930 and that are not in wolfd2_params / wolfd2_regions / wolfd2_thermal.
+ * Defaults: src/parse.f:144-178.  The thermal region tables (nTRgType, nTemBdTp, dTRgVal) must have been given
+ * with wolfd2_b200_set_thermal (nthermen may be 0): SmallScale calls TempBoundCond and Filter(_T_) in any case. */
+typedef struct wolfd2_smallscale {
+    int32_t nsmallscl;         /* 1: small_scale given                                     */
+    int32_t nssPpeSlvr;        /* atd_ppe_solver id 1..6 (default 1)                       */
+    int32_t mssSorIt;          /* atd_max_sor_iter (default 2000)                          */
+    int32_t reserved_;
+    double  dlref, uref, tref, tmax;
+    double  pe;
+    double  ssSorTol, ssSorRel;
+    double  ssFiltPar[4];      /* Fortran ssFiltPar(1:4): (_U_), (_V_), unused, (_T_)      */
+    double  ssCu0, ssTsCoef, ssHsCoef, ssTemCoef, ssBnCrit, ssRMpMax, ssRMpExp;
+} wolfd2_smallscale;
+
+/* Lagrangian particle trajectories: scalar arguments of Traject (src/traject.f:154-164).
+ * nTrMethod 1 = HeunTrap, 2 = FwdEuler; nTrCdEq 1 Stokes, 2 Chein, 3 White, 4 Tilly. */
+typedef struct wolfd2_traject {
+    int32_t ntr;               /* number of particles                                      */
+    int32_t ntsubstp;          /* sub-steps per flow time step                             */
+    int32_t nTrMethod, nTrCdEq, mTrHTmit;
+    int32_t reserved_;
+    double  densref, dTrHTtol, dTrHTdel;
+} wolfd2_traject;
+
 /* The 30 metric arrays produced by Metric (src/grid.f:368-535), each
  * REAL*8 (0:mnx,0:mny), zero outside 1..nx,1..ny (static storage in main.f). */
 typedef struct wolfd2_metrics {
@@ -126,7 +152,10 @@ enum { W2_OK = 0, W2_ERR_NO_DEVICE = 1, W2_ERR_BAD_ARG = 2, W2_ERR_UNSUPPORTED =
 /* field selectors for wolfd2_b200_upload_field / download_field */
 enum { W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_US = 3, W2_F_VS = 4, W2_F_UN = 5,
        W2_F_VN = 6, W2_F_PN = 7, W2_F_D = 8, W2_F_DN = 9, W2_F_B = 10,
-       W2_F_T = 11, W2_F_TS = 12, W2_F_TN = 13, W2_F_COUNT = 14 };
+       W2_F_T = 11, W2_F_TS = 12, W2_F_TN = 13,
+       /* small-scale fields; they exist once wolfd2_b200_set_smallscale has been called */
+       W2_F_USS = 14, W2_F_VSS = 15, W2_F_PSS = 16, W2_F_TSS = 17, W2_F_COUNT = 18 };
+#define W2_F_CORE 14   /* fields every context holds */
 
 /* ---- library-wide configuration ------------------------------------------------ */
 
@@ -156,6 +185,26 @@ int wolfd2_b200_set_params(wolfd2_ctx *ctx, const wolfd2_params *par);
  * momentum-energy iteration loop of src/main.f:736-880 then runs up to par->nmeiter times per step with
  * ThermEnergy, EqState and the t-norm inside, Filter(_T_) and TempBoundCond after it.  One GPU only. */
 int wolfd2_b200_set_thermal(wolfd2_ctx *ctx, const wolfd2_thermal *th);
+
+/* ATD small-scale model on (ss->nsmallscl == 1) or off for the following steps: the blocks of src/main.f:706-727 and
+ * :896-940 then run inside wolfd2_b200_step.  The thermal region tables must have been given with
+ * wolfd2_b200_set_thermal before (nthermen may be 0).  One GPU only. */
+int wolfd2_b200_set_smallscale(wolfd2_ctx *ctx, const wolfd2_smallscale *ss);
+/* src/main.f:643-665: SmallScale with initflg = 0 on the context's current u, v, t (seeds the maps, computes the
+ * first uss, vss, pss, tss); call after uploading the initial / restart fields, before the first step. */
+int wolfd2_b200_smallscale_init(wolfd2_ctx *ctx);
+/* One plane (1..3) of the saved map iterates of family 0/1/2 = umap/vmap/tmap: download (upload = 0) or upload. */
+int wolfd2_b200_smallscale_map(wolfd2_ctx *ctx, int32_t family, int32_t plane, double *host, int32_t upload);
+
+/* Lagrangian particles (tr->ntr > 0) on or off: x, y are the grid nodes as main.f holds them (REAL*8 (0:mnx,0:mny),
+ * src/grid.f), the particle arrays have tr->ntr entries (src/main.f:242-260); nTOutBnd may be NULL (all zero).
+ * Every following step ends with the block of src/main.f:1000-1024 (VelAvg, PTDAvg, Traject) on the device;
+ * wolfd2_b200_get_particles reads the particles back (any pointer may be NULL).  One GPU only. */
+int wolfd2_b200_set_trajectories(wolfd2_ctx *ctx, const wolfd2_traject *tr, const double *x, const double *y,
+                                 const double *cpartx, const double *cparty, const double *repc,
+                                 const double *xp, const double *yp, const double *up, const double *vp,
+                                 const int32_t *nTOutBnd);
+int wolfd2_b200_get_particles(wolfd2_ctx *ctx, double *xp, double *yp, double *up, double *vp, int32_t *nTOutBnd);
 
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
@@ -307,6 +356,42 @@ void thermenergy_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, con
 /* src/thermal.f:283-285 */
 void eqstate_(const int32_t *nx, const int32_t *ny, const double *uref, const double *densref,
     const double *tmax, const double *tref, const double *rconst, const double *p, const double *t, double *den);
+
+
+/* src/small_scale.f:31-49.  The maps, cell areas and work arrays are `save`d locals in the reference: the shim keeps
+ * them in the library's shim context between calls (initflg <= 0 re-seeds them). */
+void smallscale_(const int32_t *nx, const int32_t *ny, const int32_t *initflg, const int32_t *nthermen,
+    const int32_t *lCartesGrid, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nRegType, const int32_t *nTRgType, const int32_t *nMomBdTp, const int32_t *nTemBdTp,
+    const int32_t *nPpeSolver, const int32_t *msorit,
+    const double *dlref, const double *uref, const double *tref, const double *tmax,
+    const double *dka, const double *re, const double *pe, const double *sortol, const double *sorrel,
+    const double *fp, const double *cu0, const double *TsCoef, const double *HsCoef, const double *TemCoef,
+    const double *bnumc, const double *rmax, const double *rlc, const double *dTRgVal, const double *dBCVal,
+    const double *rau, const double *rbu, const double *rbv, const double *rgv,
+    const double *dju, const double *djv, const double *djc,
+    const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+    const double *xzu, const double *yzu, const double *xev, const double *yev,
+    const double *xec, const double *yec, const double *xzc, const double *yzc,
+    const double *u1, const double *v1, const double *t1,
+    double *uss, double *vss, double *pss, double *tss);
+/* src/bound_cond.f:1209-1213 */
+void smlsclbc_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nRegType, const int32_t *nMomBdTp, const int32_t *nTRgType, const int32_t *nTemBdTp,
+    const double *dBCVal, double *u, double *v, double *p, double *t);
+/* src/utility.f:512, 574 */
+void ptdavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nRegType, const double *p, double *pav);
+void velavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nRegType, const double *u, const double *v, double *util, double *vbar);
+/* src/traject.f:154-164.  HeunTrap's step is the sub-step size (the reference passes the INTEGER sub-step counter
+ * there). */
+void traject_(const int32_t *nx, const int32_t *ny, const int32_t *ntr, const int32_t *ntsubstp,
+    const int32_t *nTrMethod, const int32_t *nTrCdEq, const int32_t *mTrHTmit, int32_t *nTOutBnd,
+    const double *dkflow, const double *densref, const double *fr, const double *dTrHTtol, const double *dTrHTdel,
+    const double *cpartx, const double *cparty, const double *repc,
+    const double *x, const double *y, const double *u, const double *v, const double *un, const double *vn,
+    const double *dens, const double *densn, double *xp, double *yp, double *up, double *vp);
 
 #ifdef __cplusplus
 }

@@ -1813,6 +1813,8 @@ void orc_eqstate_(const int32_t *nx_, const int32_t *ny_, const double *uref_, c
         }
 }
 
+#include "wolfd2_oracle_atd.inc"
+
 /* ================================== main.f ======================================= */
 
 typedef struct orc_state {
@@ -1845,9 +1847,51 @@ void orc_coldstart(const wolfd2_params *par, const wolfd2_regions *reg, const wo
 /* Step body, src/main.f:690-981 with nsmallscl=0.  th == NULL (or th->nthermen == 0): cold flow;
  * otherwise the momentum-energy iterations with ThermEnergy / EqState (:736-880), Filter(_T_) (:890)
  * and TempBoundCond (:955).  t and d are passed in either case (copies/norms of :696-704, :857-870, :965). */
-int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
-                         const wolfd2_thermal *th, double *u, double *v, double *p, double *t, double *d,
-                         int32_t nsteps, wolfd2_step_log *logs) {
+/* particles of a trajectory run (src/main.f:242-260): what main.f passes to Traject at :1014-1024 */
+typedef struct orc_particles {
+    const wolfd2_traject *tr;
+    const double *gx, *gy;                 /* grid nodes x(0:mnx,0:mny), y */
+    const double *cpartx, *cparty, *repc;
+    double *xp, *yp, *up, *vp;
+    int32_t *nTOutBnd;
+} orc_particles;
+
+static void orc_call_smallscale(int32_t initflg, const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
+                                const wolfd2_thermal *th, const wolfd2_smallscale *ss, const double *u, const double *v,
+                                const double *t, double *uss, double *vss, double *pss, double *tss) {
+    const int32_t nx = par->nx, ny = par->ny, nthermen = th->nthermen;
+    orc_smallscale_(&nx, &ny, &initflg, &nthermen, &par->lCartesGrid, reg->nReg, reg->nRegBrd, reg->nRegType,
+                    th->nTRgType, reg->nMomBdTp, th->nTemBdTp, &ss->nssPpeSlvr, &ss->mssSorIt,
+                    &ss->dlref, &ss->uref, &ss->tref, &ss->tmax, &par->dk, &par->re, &ss->pe,
+                    &ss->ssSorTol, &ss->ssSorRel, ss->ssFiltPar,
+                    &ss->ssCu0, &ss->ssTsCoef, &ss->ssHsCoef, &ss->ssTemCoef, &ss->ssBnCrit, &ss->ssRMpMax, &ss->ssRMpExp,
+                    th->dTRgVal, reg->dBCVal, m->rau, m->rbu, m->rbv, m->rgv, m->dju, m->djv, m->djc,
+                    m->xeu, m->yeu, m->xzv, m->yzv, m->xzu, m->yzu, m->xev, m->yev, m->xec, m->yec, m->xzc, m->yzc,
+                    u, v, t, uss, vss, pss, tss);
+}
+/* src/main.f:643-665: SmallScale with initflg = 0 before the time loop */
+void orc_atd_init(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m, const wolfd2_thermal *th,
+                  const wolfd2_smallscale *ss, const double *u, const double *v, const double *t,
+                  double *uss, double *vss, double *pss, double *tss) {
+    orc_call_smallscale(0, par, reg, m, th, ss, u, v, t, uss, vss, pss, tss);
+}
+
+static double *S_usn, *S_vsn, *S_tsn;
+/* ss != NULL with nsmallscl == 1: the ATD blocks of :706-727 and :896-940 (th must carry the thermal tables);
+ * pt != NULL: the trajectory block of :997-1031 */
+int32_t orc_step_full(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
+                      const wolfd2_thermal *th, const wolfd2_smallscale *ss, const orc_particles *pt,
+                      double *u, double *v, double *p, double *t, double *d,
+                      double *uss, double *vss, double *pss, double *tss,
+                      int32_t nsteps, wolfd2_step_log *logs) {
+    const int nsmallscl = ss ? ss->nsmallscl : 0;
+    if (nsmallscl == 1 || pt) {
+        if (!S_usn || S_n != NFULL) {
+            free(S_usn); free(S_vsn); free(S_tsn);
+            S_usn = zalloc(NFULL); S_vsn = zalloc(NFULL); S_tsn = zalloc(NFULL);
+        }
+    }
+    double *usn = S_usn, *vsn = S_vsn, *tsn = S_tsn;
     const int32_t nx = par->nx, ny = par->ny;
     const int32_t cU = _U_, cV = _V_, cT = _T_;
     const int nthermen = th ? th->nthermen : 0, neqstate = th ? th->neqstate : 0;
@@ -1860,6 +1904,17 @@ int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, co
                 A(pn, i, j) = A(p, i, j); A(un, i, j) = A(u, i, j); A(vn, i, j) = A(v, i, j);
                 A(tn, i, j) = A(t, i, j); A(dn, i, j) = A(d, i, j);
             }
+        if (nsmallscl == 1) {                                          /* :706-727 */
+            for (j = 0; j <= ny + 1; ++j)
+                for (i = 0; i <= nx + 1; ++i) {
+                    A(usn, i, j) = A(uss, i, j); A(vsn, i, j) = A(vss, i, j); A(tsn, i, j) = A(tss, i, j);
+                }
+            for (j = 0; j <= ny + 1; ++j)
+                for (i = 0; i <= nx + 1; ++i) {
+                    A(un, i, j) = A(un, i, j) + A(uss, i, j); A(vn, i, j) = A(vn, i, j) + A(vss, i, j);
+                    A(tn, i, j) = A(tn, i, j) + A(tss, i, j);
+                }
+        }
         int nmeiter = par->nmeiter;
         if (nthermen != 1 && nmeiter > 0) nmeiter = 1;                 /* :736 */
         int32_t nQLiter = 0, nSorConv = 0;
@@ -1912,6 +1967,20 @@ int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, co
         }
         if (nthermen == 1 && th->nfiltt == 1)                          /* :890-894 */
             orc_filter_(&nx, &ny, &cT, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp, th->nTRgType, &th->fpt, t);
+        if (nsmallscl == 1) {                                          /* :896-940 */
+            for (j = 0; j <= ny + 1; ++j)
+                for (i = 0; i <= nx + 1; ++i) {
+                    A(u, i, j) = A(u, i, j) - A(usn, i, j); A(v, i, j) = A(v, i, j) - A(vsn, i, j);
+                    A(t, i, j) = A(t, i, j) - A(tsn, i, j);
+                }
+            orc_call_smallscale(1, par, reg, m, th, ss, u, v, t, uss, vss, pss, tss);
+            if (orc_errflag) return 1;
+            for (j = 0; j <= ny + 1; ++j)
+                for (i = 0; i <= nx + 1; ++i) {
+                    A(u, i, j) = A(u, i, j) + A(uss, i, j); A(v, i, j) = A(v, i, j) + A(vss, i, j);
+                    A(t, i, j) = A(t, i, j) + A(tss, i, j);
+                }
+        }
         orc_velboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nMomBdTp, reg->dBCVal, u, v);         /* :946 */
         orc_presboundcond_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp, reg->dBCVal, p);
         if (nthermen == 1)                                             /* :955 */
@@ -1931,8 +2000,25 @@ int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, co
             for (int q = 0; q < 4; ++q) logs[k].dif[q] = dif[q];
         }
         if (difmax > 1.e12) { fprintf(stderr, "* Solution diverged. Please reduce CFL number.\n"); return 2; } /* :969-972 */
+        if (pt) {                                                      /* :1000-1024 (averages go to the starred arrays) */
+            const wolfd2_traject *tr = pt->tr;
+            orc_velavg_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, u, v, us, vs);
+            orc_velavg_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, un, vn, usn, vsn);
+            orc_ptdavg_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, d, ts);
+            orc_ptdavg_(&nx, &ny, reg->nReg, reg->nRegBrd, reg->nRegType, dn, tsn);
+            orc_traject_(&nx, &ny, &tr->ntr, &tr->ntsubstp, &tr->nTrMethod, &tr->nTrCdEq, &tr->mTrHTmit, pt->nTOutBnd,
+                         &par->dk, &tr->densref, &par->fr, &tr->dTrHTtol, &tr->dTrHTdel, pt->cpartx, pt->cparty, pt->repc,
+                         pt->gx, pt->gy, us, vs, usn, vsn, ts, tsn, pt->xp, pt->yp, pt->up, pt->vp);
+            if (orc_errflag) return 1;
+        }
     }
     return 0;
+}
+
+int32_t orc_step_thermal(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
+                         const wolfd2_thermal *th, double *u, double *v, double *p, double *t, double *d,
+                         int32_t nsteps, wolfd2_step_log *logs) {
+    return orc_step_full(par, reg, m, th, NULL, NULL, u, v, p, t, d, NULL, NULL, NULL, NULL, nsteps, logs);
 }
 
 int32_t orc_step(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,

@@ -27,6 +27,14 @@ ORACLE_ONLY = {
 }
 
 
+class Particles(C.Structure):
+    """orc_particles of oracle/wolfd2_oracle.c."""
+    _fields_ = [("tr", C.POINTER(_abi.Traject)), ("gx", _abi.c_f64p), ("gy", _abi.c_f64p),
+                ("cpartx", _abi.c_f64p), ("cparty", _abi.c_f64p), ("repc", _abi.c_f64p),
+                ("xp", _abi.c_f64p), ("yp", _abi.c_f64p), ("up", _abi.c_f64p), ("vp", _abi.c_f64p),
+                ("nTOutBnd", _abi.c_i32p)]
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ODIR = os.path.join(ROOT, "oracle")
 
@@ -34,7 +42,8 @@ ODIR = os.path.join(ROOT, "oracle")
 def _build(target="liboracle.so"):
     path = os.path.join(ODIR, target)
     src = os.path.join(ODIR, "wolfd2_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    inc = os.path.join(ODIR, "wolfd2_oracle_atd.inc")
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(inc)):
         subprocess.check_call(["make", "-C", ODIR, target], stdout=subprocess.DEVNULL)
     return path
 
@@ -58,6 +67,15 @@ class Oracle:
                                               C.POINTER(_abi.Thermal)] + [_abi.c_f64p] * 5 + \
                                              [C.c_int32, C.POINTER(_abi.StepLog)]
         self.lib.orc_step_thermal.restype = C.c_int32
+        self.lib.orc_atd_init.argtypes = [C.POINTER(_abi.Params), C.POINTER(_abi.Regions), C.POINTER(_abi.Metrics),
+                                          C.POINTER(_abi.Thermal), C.POINTER(_abi.SmallScale)] + [_abi.c_f64p] * 7
+        self.lib.orc_step_full.argtypes = [C.POINTER(_abi.Params), C.POINTER(_abi.Regions), C.POINTER(_abi.Metrics),
+                                           C.POINTER(_abi.Thermal), C.POINTER(_abi.SmallScale), C.POINTER(Particles)] + \
+                                          [_abi.c_f64p] * 9 + [C.c_int32, C.POINTER(_abi.StepLog)]
+        self.lib.orc_step_full.restype = C.c_int32
+        self.lib.orc_ss_map.argtypes = [C.c_int32, C.c_int32]
+        self.lib.orc_ss_map.restype = _abi.c_f64p
+        self.lib.orc_ss_tarea.restype = C.c_double
         self.lib.orc_ppe_matrix.argtypes = [C.c_int32, C.c_int32, _abi.c_i32p, _abi.c_i32p, _abi.c_i32p,
                                             _abi.c_f64p, _abi.c_f64p, _abi.c_f64p, _abi.c_f64p]
         self.lib.orc_grid.argtypes = [C.c_int32, C.c_int32, C.c_double, _abi.c_f64p, _abi.c_f64p,
@@ -111,6 +129,43 @@ class Oracle:
             rc = self.lib.orc_step(C.byref(par), C.byref(reg), C.byref(met),
                                    *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)
         return rc, [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, dif=list(l.dif)) for l in logs]
+
+
+    def atd_init(self, deck, u, v, t, uss, vss, pss, tss):
+        """src/main.f:643-665: SmallScale(initflg=0)."""
+        self.config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        par, reg, met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
+        th, ss = deck.thermal_struct(), deck.smallscale_struct()
+        self.lib.orc_atd_init(C.byref(par), C.byref(reg), C.byref(met), C.byref(th), C.byref(ss),
+                              *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, t, uss, vss, pss, tss)])
+
+    def step_full(self, deck, u, v, p, t, d, ss_fields=None, particles=None, nsteps=1):
+        """Step body with the ATD blocks (ss_fields = (uss, vss, pss, tss)) and / or the trajectory block
+        (particles = dict(tr, gx, gy, cpartx, cparty, repc, xp, yp, up, vp, out))."""
+        self.config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        par, reg, met = deck.params(), deck.regions.as_struct(), deck.metrics_struct()
+        th = deck.thermal_struct()
+        ss = deck.smallscale_struct() if ss_fields is not None else None
+        pt = None
+        if particles is not None:
+            pt = Particles()
+            pt.tr = C.pointer(particles["tr"])
+            for k in ("gx", "gy", "cpartx", "cparty", "repc", "xp", "yp", "up", "vp"):
+                setattr(pt, k, particles[k].ctypes.data_as(_abi.c_f64p))
+            pt.nTOutBnd = particles["out"].ctypes.data_as(_abi.c_i32p)
+        f = list(ss_fields) if ss_fields is not None else [None] * 4
+        logs = (_abi.StepLog * nsteps)()
+        rc = self.lib.orc_step_full(C.byref(par), C.byref(reg), C.byref(met), C.byref(th),
+                                    C.byref(ss) if ss is not None else None, C.byref(pt) if pt is not None else None,
+                                    *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)],
+                                    *[a.ctypes.data_as(_abi.c_f64p) if a is not None else None for a in f], nsteps, logs)
+        return rc, [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, dif=list(l.dif)) for l in logs]
+
+    def ss_map(self, deck, family, plane):
+        """A copy of one plane of the oracle's saved map iterates."""
+        ptr = self.lib.orc_ss_map(family, plane)
+        n = (deck.mny + 1) * (deck.mnx + 1)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(deck.mny + 1, deck.mnx + 1).copy()
 
 
 _ORACLE = None

@@ -1,0 +1,313 @@
+"""GPU parity of the optional rows of SURVEY section 8f through the C ABI against the CPU oracle:
+N2 SmallScale / SmlSclBC (ATD small-scale model), N3 Traject (Lagrangian particles), N4 VelAvg / PTDAvg.
+
+Bit-exact: SmlSclBC, VelAvg, PTDAvg, the seeded chaotic maps and tArea, and Traject for the drag laws that need no
+pow() (Stokes, White) with either integrator.  SmallScale's amplitude model calls pow/tanh per cell (CUDA's <= 2 ulp
+against glibc's < 1 ulp) and the chaotic map amplifies that by up to 4.83 per iterate: its fields are held to 1e-9
+for the short sequences tested here."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import get_oracle
+from util import make_test_decks, rand_field, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_SS = 1e-9       # uss, vss, tss, pss of one SmallScale call (see module docstring)
+TOL_STEP = 1e-8     # u, v, p, t after a step with the ATD blocks on (the model's output feeds the next step)
+TOL_POW = 1e-12     # particle state with the Chein / Tilly drag laws (pow)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from wolfd2_b200 import api as a
+    a.lib()
+    return a
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return get_oracle()
+
+
+def _cfg(api, orc, d):
+    api.config(d.mnx, d.mny)
+    orc.config(d.mnx, d.mny)
+
+
+SS_KW = dict(smallscale=True, ss_cu0=1.0, ss_bncrit=2.0, ss_rmpmax=0.95, ss_ppe_solver="rb_sor", ss_msorit=300,
+             ss_sortol=1e-9, ss_sorrel=1.5, ss_filt=(4e2, 3e2, 0.0, 2e2))
+
+
+def _atd_decks():
+    from wolfd2_b200 import deck as dk
+    out = [dk.cavity(37, re=1000.0, dt=0.01, ny=29, **SS_KW),
+           dk.backward_step(44, re=800.0, dt=0.004, ny=36, **SS_KW)]
+    # thermal run: heat source, fixed-temperature block, temperature / flux faces; general (skewed) grid
+    x, y = dk.stretched_grid(40, 34)
+    reg = dk.RegionTables(40, 34, 2, 2, (18,), (16,))
+    reg.heat_generation(1, 1, 2.0).fixed_temperature_region(2, 2, 0.7)
+    reg.wall_temperature(1, 1, "w", 1.0).wall_heat_flux(1, 2, "w", 0.05).wall(1, 2, "n", tangent_vel=1.0)
+    out.append(dk._mk("atd_thermal_2x2", 40, 34, reg, 900.0, 0.004, x=x, y=y, cartesian=False, thermal=True, nmeiter=2,
+                      **SS_KW))
+    # inflow / both outlet types
+    reg = dk.RegionTables(42, 30, 2, 1, (20,), ())
+    reg.inlet(1, 1, "w", normal_vel=1.0).outlet(2, 1, "e", fully_dev=False).outlet(2, 1, "n", fully_dev=True)
+    out.append(dk._mk("atd_channel", 42, 30, reg, 700.0, 0.004, **SS_KW))
+    return out
+
+
+ATD_DECKS = _atd_decks()
+ATD_IDS = [d.name for d in ATD_DECKS]
+
+
+# ------------------------------------------------------------------------------------------ SmlSclBC, averages
+@pytest.mark.parametrize("d", make_test_decks(), ids=lambda d: d.name)
+def test_smlsclbc_bitwise(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(77)
+    r = d.regions
+    f = [rand_field(d, rng) for _ in range(4)]
+    g, o = [a.copy() for a in f], [a.copy() for a in f]
+    args = (d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.nTRgType, r.nTemBdTp, r.dBCVal)
+    for _ in range(2):     # second pass: corner cells read ghosts written by the first
+        api.SmlSclBC(*args, *g)
+        orc.smlsclbc(*args, *o)
+        for a, b in zip(g, o):
+            assert np.array_equal(a, b)
+
+
+def test_smlsclbc_thermal_tables_bitwise(api, orc):
+    d = ATD_DECKS[2]
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(78)
+    r = d.regions
+    f = [rand_field(d, rng) for _ in range(4)]
+    g, o = [a.copy() for a in f], [a.copy() for a in f]
+    args = (d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.nTRgType, r.nTemBdTp, r.dBCVal)
+    api.SmlSclBC(*args, *g)
+    orc.smlsclbc(*args, *o)
+    for a, b in zip(g, o):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("d", make_test_decks(), ids=lambda d: d.name)
+def test_node_averages_bitwise(api, orc, d):
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(79)
+    r = d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    p[3, 3:6] = 1e-21                      # the 1e-20 flush of PTDAvg (utility.f:560)
+    pre = [rand_field(d, rng) for _ in range(3)]   # nodes no loop covers keep the caller's values
+    g, o = [a.copy() for a in pre], [a.copy() for a in pre]
+    api.VelAvg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, u, v, g[0], g[1])
+    orc.velavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, u, v, o[0], o[1])
+    api.PTDAvg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, p, g[2])
+    orc.ptdavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, p, o[2])
+    for a, b in zip(g, o):
+        assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ SmallScale
+def _ss_args(d, initflg):
+    r, m = d.regions, d.metrics
+    fp = np.array(d.ss_filt, dtype=np.float64)
+    from wolfd2_b200.deck import PPE_SOLVERS
+    return (d.nx, d.ny, initflg, int(d.thermal), int(d.cartesian), r.nReg, r.nRegBrd, r.nRegType, r.nTRgType, r.nMomBdTp,
+            r.nTemBdTp, PPE_SOLVERS[d.ss_ppe_solver], d.ss_msorit, d.dlref, d.uref, d.tref, d.tmax, d.dk, d.re, d.pe,
+            d.ss_sortol, d.ss_sorrel, fp, d.ss_cu0, d.ss_tscoef, d.ss_hscoef, d.ss_temcoef, d.ss_bncrit, d.ss_rmpmax,
+            d.ss_rmpexp, r.dTRgVal, r.dBCVal, m["rau"], m["rbu"], m["rbv"], m["rgv"], m["dju"], m["djv"], m["djc"],
+            m["xeu"], m["yeu"], m["xzv"], m["yzv"], m["xzu"], m["yzu"], m["xev"], m["yev"], m["xec"], m["yec"],
+            m["xzc"], m["yzc"])
+
+
+@pytest.mark.parametrize("d", ATD_DECKS, ids=ATD_IDS)
+def test_smallscale_literal_calls(api, orc, d):
+    """SmallScale through its literal interface: initflg 0, then two more calls on changing fields (the maps are
+    `save`d between calls on both sides)."""
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(11)
+    g = [d.new_field() for _ in range(4)]
+    o = [d.new_field() for _ in range(4)]
+    for call, initflg in enumerate((0, 1, 1)):
+        u, v, t = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng, 0.0, 1.0)
+        api.SmallScale_(*_ss_args(d, initflg), u, v, t, *g)
+        orc.smallscale(*_ss_args(d, initflg), u, v, t, *o)
+        assert orc.lib.orc_get_errflag() == 0
+        for name, a, b in zip(("uss", "vss", "pss", "tss"), g, o):
+            assert np.all(np.isfinite(a)), (call, name)
+            assert rel_l2(a, b) <= TOL_SS, (call, name, rel_l2(a, b))
+        assert np.abs(o[0]).max() > 1e-4 and np.abs(o[1]).max() > 1e-4     # the model is active in this regime
+
+
+def test_smallscale_seeding_bitwise_and_initflg_negative(api, orc):
+    """initflg < 0 only seeds the maps, zeroes uss, vss, tss and forms the areas (small_scale.f:198-245)."""
+    d = ATD_DECKS[0]
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(12)
+    u, v, t = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng, 0.0, 1.0)
+    g = [rand_field(d, rng) for _ in range(4)]
+    o = [a.copy() for a in g]
+    api.SmallScale_(*_ss_args(d, -1), u, v, t, *g)
+    orc.smallscale(*_ss_args(d, -1), u, v, t, *o)
+    for a, b in zip(g, o):
+        assert np.array_equal(a, b)
+    assert not g[0][:d.ny + 2, :d.nx + 2].any() and g[2].any()    # uss zeroed, pss untouched
+
+
+# ------------------------------------------------------------------------------------------ step body with ATD
+@pytest.mark.parametrize("d", ATD_DECKS, ids=ATD_IDS)
+def test_steps_with_smallscale(api, orc, d):
+    """src/main.f:643-665 then 4 steps with the blocks of :706-727 and :896-940; the maps start bit-identical."""
+    _cfg(api, orc, d)
+    from wolfd2_b200.api import F_D, F_P, F_PSS, F_T, F_TSS, F_U, F_USS, F_V, F_VSS
+    u, v, p, t, dd = (d.new_field() for _ in range(5))
+    ss = [d.new_field() for _ in range(4)]
+    orc.coldstart(d, u, v, p)
+    # a developed flow is needed for the model to switch on (peh > 3): a few plain steps first
+    import dataclasses
+    d0 = dataclasses.replace(d, smallscale=False)
+    rc, _ = orc.step(d0, u, v, p, nsteps=6, t=t, d=dd)
+    assert rc == 0
+    with api.Context(d) as ctx:
+        for w, a in ((F_U, u), (F_V, v), (F_P, p), (F_T, t), (F_D, dd)):
+            ctx.upload(w, a)
+        ctx.smallscale_init()
+        orc.atd_init(d, u, v, t, *ss)
+        for fam in range(3):
+            for pl in (1, 2, 3):
+                assert np.array_equal(ctx.smallscale_map(fam, pl), orc.ss_map(d, fam, pl))
+        for w, a in ((F_USS, ss[0]), (F_VSS, ss[1]), (F_PSS, ss[2]), (F_TSS, ss[3])):
+            assert rel_l2(ctx.download(w), a) <= TOL_SS
+        active = False
+        for k in range(4):
+            logs = ctx.step(1)
+            rc, ol = orc.step_full(d, u, v, p, t, dd, ss_fields=ss, nsteps=1)
+            assert rc == 0
+            assert logs[0]["nQLiter"] == ol[0]["nQLiter"] and logs[0]["nSorConv"] == ol[0]["nSorConv"], (k, logs, ol)
+            for name, w, a in (("u", F_U, u), ("v", F_V, v), ("p", F_P, p), ("uss", F_USS, ss[0]), ("vss", F_VSS, ss[1]),
+                               ("pss", F_PSS, ss[2]), ("tss", F_TSS, ss[3]), ("t", F_T, t)):
+                e = rel_l2(ctx.download(w), a)
+                assert e <= TOL_STEP, (k, name, e)
+            np.testing.assert_allclose(logs[0]["dif"], ol[0]["dif"], rtol=1e-6, atol=1e-12)
+            active = active or np.abs(ss[0]).max() > 1e-6
+        assert active, "the small-scale model never switched on in this deck"
+
+
+# ------------------------------------------------------------------------------------------ trajectories
+def _particles(d, n, rng, spread=(0.05, 0.95)):
+    lx = d.x_nodes.max() / d.dlref
+    ly = d.y_nodes.max() / d.dlref
+    xp = rng.uniform(spread[0] * lx, spread[1] * lx, n)
+    yp = rng.uniform(spread[0] * ly, spread[1] * ly, n)
+    # some start outside or on the boundary cells: flagged 1, 2 or 3 by iFindPos
+    xp[:4] = (-0.01, 1.5 * lx, 0.3 * lx, 0.5 * lx)
+    yp[:4] = (0.4 * ly, 0.5 * ly, -0.2 * ly, 2.0 * ly)
+    up, vp = rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n)
+    cx, cy = rng.uniform(0.5, 3.0, n), rng.uniform(0.5, 3.0, n)
+    repc = rng.uniform(5.0, 50.0, n)
+    return cx, cy, repc, xp, yp, up, vp
+
+
+def _traj_deck(kind):
+    from wolfd2_b200 import deck as dk
+    if kind == "uniform":
+        return dk.cavity(41, re=100.0, dt=0.02, ny=33)
+    if kind == "blockage":
+        return dk.backward_step(44, re=100.0, dt=0.02, ny=36)
+    x, y = dk.stretched_grid(30, 26)                    # skewed: the literal O(nx*ny) search
+    return dk._mk("skewed", 30, 26, dk.RegionTables(30, 26), 100.0, 0.02, x=x, y=y, cartesian=False)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "blockage", "skewed"])
+@pytest.mark.parametrize("method,cdeq", [(2, 1), (2, 3), (1, 1), (1, 3), (2, 2), (1, 4)])
+def test_traject_literal(api, orc, kind, method, cdeq):
+    d = _traj_deck(kind)
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(100 * method + cdeq)
+    n = 300
+    cx, cy, repc, xp, yp, up, vp = _particles(d, n, rng)
+    gx, gy = d.node_arrays()
+    f = [rand_field(d, rng, -1.0, 1.0) for _ in range(4)] + [rand_field(d, rng, -0.1, 0.1) for _ in range(2)]
+    res = []
+    for call in (api.Traject_, orc.traject):
+        st = [a.copy() for a in (xp, yp, up, vp)]
+        out = np.zeros(n, dtype=np.int32)
+        out[7] = 2                                        # already out of bounds: never touched again
+        for _ in range(2):                                # two flow steps of 3 sub-steps each
+            call(d.nx, d.ny, n, 3, method, cdeq, 6, out, d.dk, 1.2, d.fr, 1e-10, 1.0, cx, cy, repc, gx, gy, *f, *st)
+        res.append((st, out))
+    (sg, og), (so, oo) = res
+    assert np.array_equal(og, oo)
+    assert set(oo[:4]) == {1, 2, 3} and (oo[8:] == 0).sum() > n // 2
+    exact = cdeq in (1, 3)
+    for name, a, b in zip(("xp", "yp", "up", "vp"), sg, so):
+        if exact:
+            assert np.array_equal(a, b), (name, np.abs(a - b).max())
+        else:
+            assert np.allclose(a, b, rtol=TOL_POW, atol=TOL_POW), (name, np.abs(a - b).max())
+    assert not np.array_equal(so[0][8:], xp[8:])          # the particles did move
+
+
+def test_steps_with_trajectories(api, orc):
+    """The block of src/main.f:1000-1024 inside the step: node averages of both time levels, then Traject."""
+    from wolfd2_b200 import _abi
+    from wolfd2_b200.api import F_P, F_U, F_V
+    d = _traj_deck("blockage")
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(5)
+    n = 500
+    cx, cy, repc, xp, yp, up, vp = _particles(d, n, rng)
+    gx, gy = d.node_arrays()
+    tr = _abi.Traject()
+    tr.ntr, tr.ntsubstp, tr.nTrMethod, tr.nTrCdEq, tr.mTrHTmit = n, 2, 1, 3, 5
+    tr.densref, tr.dTrHTtol, tr.dTrHTdel = 1.2, 1e-10, 1.0
+    u, v, p, t, dd = (d.new_field() for _ in range(5))
+    orc.coldstart(d, u, v, p)
+    out = np.zeros(n, dtype=np.int32)
+    part = dict(tr=tr, gx=gx, gy=gy, cpartx=cx, cparty=cy, repc=repc, xp=xp.copy(), yp=yp.copy(), up=up.copy(),
+                vp=vp.copy(), out=out)
+    with api.Context(d) as ctx:
+        for w, a in ((F_U, u), (F_V, v), (F_P, p)):
+            ctx.upload(w, a)
+        ctx.set_trajectories(tr, gx, gy, cx, cy, repc, xp, yp, up, vp)
+        for k in range(4):
+            ctx.step(1)
+            rc, _ = orc.step_full(d, u, v, p, t, dd, particles=part, nsteps=1)
+            assert rc == 0
+            gxp, gyp, gup, gvp, gout = ctx.particles()
+            assert np.array_equal(gout, part["out"]), k
+            # the fields differ at the 1e-12 level (tridiagonal elimination order): so do the interpolated velocities
+            for name, a, b in (("xp", gxp, part["xp"]), ("yp", gyp, part["yp"]), ("up", gup, part["up"]),
+                               ("vp", gvp, part["vp"])):
+                assert np.allclose(a, b, rtol=1e-9, atol=1e-11), (k, name, np.abs(a - b).max())
+        assert rel_l2(ctx.download(F_U), u) <= 1e-10
+
+
+def test_traject_many_particles_fast_search(api):
+    """10^6 particles on a 1024^2 rectilinear grid: one launch, O(log n) cell search (the reference's scan would be
+    10^12 comparisons).  Property check: in a uniform flow field every in-bounds particle relaxes towards the
+    fluid velocity and none is flagged."""
+    from wolfd2_b200 import deck as dk
+    n = 1024
+    d = dk.cavity(n, re=100.0, dt=1e-3)
+    api.config(d.mnx, d.mny)
+    rng = np.random.default_rng(9)
+    npart = 1_000_000
+    gx, gy = d.node_arrays()
+    uf = d.new_field(); uf[:] = 0.5
+    vf = d.new_field(); vf[:] = -0.25
+    z = d.new_field()
+    xp, yp = rng.uniform(0.2, 0.8, npart), rng.uniform(0.2, 0.8, npart)
+    up, vp = np.zeros(npart), np.zeros(npart)
+    cx = np.full(npart, 2.0); cy = np.full(npart, 2.0); repc = np.full(npart, 10.0)
+    out = np.zeros(npart, dtype=np.int32)
+    x0, y0 = xp.copy(), yp.copy()
+    api.Traject_(d.nx, d.ny, npart, 4, 2, 1, 1, out, d.dk, 1.0, 1e30, 1e-10, 1.0, cx, cy, repc, gx, gy, uf, vf, uf, vf, z, z,
+                 xp, yp, up, vp)
+    assert not out.any()
+    assert np.all(up > 0.0) and np.all(up < 0.5) and np.all(vp < 0.0) and np.all(vp > -0.25)
+    assert np.all(xp > x0) and np.all(yp < y0)
+    assert np.ptp(up) < 1e-12 and np.ptp(vp) < 1e-12      # same drag history for every particle

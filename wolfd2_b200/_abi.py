@@ -49,6 +49,16 @@ SIGNATURES = {
     "thermenergy_": (None, "ii" "II" "II" "dd" "DDD" "DDDDD" "DDDD" "DDDD" "DDDDDD"),
     # src/thermal.f:283-285
     "eqstate_": (None, "ii" "ddddd" "DDD"),
+    # src/small_scale.f:31-49
+    "smallscale_": (None, "iiii" "i" "II" "IIII" "ii" "dddd" "ddd" "dd" "D" "dddd" "ddd" "DD" "DDDD" "DDD"
+                          "DDDD" "DDDD" "DDDD" "DDD" "DDDD"),
+    # src/bound_cond.f:1209-1213
+    "smlsclbc_": (None, "ii" "II" "IIII" "D" "DDDD"),
+    # src/utility.f:512, 574
+    "ptdavg_": (None, "ii" "III" "DD"),
+    "velavg_": (None, "ii" "III" "DDDD"),
+    # src/traject.f:154-164
+    "traject_": (None, "ii" "ii" "iii" "I" "ddddd" "DDD" "DD" "DDDD" "DD" "DDDD"),
 }
 
 _KIND = {"i": c_i32p, "o": c_i32p, "d": c_f64p, "I": c_i32p, "D": c_f64p}
@@ -142,6 +152,23 @@ class Thermal(C.Structure):
                 ("uref", C.c_double), ("densref", C.c_double), ("tmax", C.c_double), ("tref", C.c_double),
                 ("rconst", C.c_double),
                 ("nTRgType", c_i32p), ("nTemBdTp", c_i32p), ("dTRgVal", c_f64p), ("dHGSTval", c_f64p)]
+
+
+class SmallScale(C.Structure):
+    """wolfd2_smallscale of include/wolfd2_b200.h."""
+    _fields_ = [("nsmallscl", C.c_int32), ("nssPpeSlvr", C.c_int32), ("mssSorIt", C.c_int32), ("reserved_", C.c_int32),
+                ("dlref", C.c_double), ("uref", C.c_double), ("tref", C.c_double), ("tmax", C.c_double),
+                ("pe", C.c_double), ("ssSorTol", C.c_double), ("ssSorRel", C.c_double),
+                ("ssFiltPar", C.c_double * 4),
+                ("ssCu0", C.c_double), ("ssTsCoef", C.c_double), ("ssHsCoef", C.c_double), ("ssTemCoef", C.c_double),
+                ("ssBnCrit", C.c_double), ("ssRMpMax", C.c_double), ("ssRMpExp", C.c_double)]
+
+
+class Traject(C.Structure):
+    """wolfd2_traject of include/wolfd2_b200.h."""
+    _fields_ = [("ntr", C.c_int32), ("ntsubstp", C.c_int32), ("nTrMethod", C.c_int32), ("nTrCdEq", C.c_int32),
+                ("mTrHTmit", C.c_int32), ("reserved_", C.c_int32),
+                ("densref", C.c_double), ("dTrHTtol", C.c_double), ("dTrHTdel", C.c_double)]
 
 
 class StepLog(C.Structure):

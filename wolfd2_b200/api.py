@@ -19,12 +19,12 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import Metrics, Params, Regions, StepLog, Thermal, c_f64p
+from ._abi import Metrics, Params, Regions, SmallScale, StepLog, Thermal, Traject, c_f64p, c_i32p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwolfd2_b200.so")
 
-F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B, F_T, F_TS, F_TN = range(14)
+F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B, F_T, F_TS, F_TN, F_USS, F_VSS, F_PSS, F_TSS = range(18)
 
 _lib = None
 _fn = None
@@ -57,6 +57,11 @@ def lib():
     L.wolfd2_b200_destroy.restype = None
     L.wolfd2_b200_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.wolfd2_b200_set_thermal.argtypes = [C.c_void_p, C.POINTER(Thermal)]
+    L.wolfd2_b200_set_smallscale.argtypes = [C.c_void_p, C.POINTER(SmallScale)]
+    L.wolfd2_b200_smallscale_init.argtypes = [C.c_void_p]
+    L.wolfd2_b200_smallscale_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_f64p, C.c_int32]
+    L.wolfd2_b200_set_trajectories.argtypes = [C.c_void_p, C.POINTER(Traject)] + [c_f64p] * 9 + [c_i32p]
+    L.wolfd2_b200_get_particles.argtypes = [C.c_void_p] + [c_f64p] * 4 + [c_i32p]
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_coldstart.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -115,6 +120,11 @@ Filter = _routine("filter")
 TempBoundCond = _routine("tempboundcond")
 ThermEnergy = _routine("thermenergy")
 EqState = _routine("eqstate")
+SmallScale_ = _routine("smallscale")     # `SmallScale` is the parameter block (ctypes struct)
+SmlSclBC = _routine("smlsclbc")
+PTDAvg = _routine("ptdavg")
+VelAvg = _routine("velavg")
+Traject_ = _routine("traject")           # `Traject` is the parameter block
 DiffMaxNorm = _routine("diffmaxnorm")
 DMaxNorm = _routine("dmaxnorm")
 
@@ -136,9 +146,12 @@ class Context:
             _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
                    "wolfd2_b200_create")
         self._h = h
-        if getattr(deck, "thermal", False):
-            self._th = deck.thermal_struct()
+        if getattr(deck, "thermal", False) or getattr(deck, "smallscale", False):
+            self._th = deck.thermal_struct()   # cold ATD runs still need the thermal region tables
             _check(L.wolfd2_b200_set_thermal(h, C.byref(self._th)), "wolfd2_b200_set_thermal")
+        if getattr(deck, "smallscale", False):
+            self._ss = deck.smallscale_struct()
+            _check(L.wolfd2_b200_set_smallscale(h, C.byref(self._ss)), "wolfd2_b200_set_smallscale")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -165,6 +178,34 @@ class Context:
         for k, v in kw.items():
             setattr(self._th, k, v)
         _check(lib().wolfd2_b200_set_thermal(self._h, C.byref(self._th)), "wolfd2_b200_set_thermal")
+
+    def smallscale_init(self):
+        """src/main.f:643-665: SmallScale(initflg=0) on the current u, v, t."""
+        _check(lib().wolfd2_b200_smallscale_init(self._h), "wolfd2_b200_smallscale_init")
+
+    def smallscale_map(self, family, plane, arr=None):
+        """Download (arr None) or upload one plane of the saved chaotic-map iterates."""
+        out = self.deck.new_field() if arr is None else arr
+        _check(lib().wolfd2_b200_smallscale_map(self._h, family, plane, out.ctypes.data_as(c_f64p), 0 if arr is None else 1),
+               "wolfd2_b200_smallscale_map")
+        return out
+
+    def set_trajectories(self, tr, x, y, cpartx, cparty, repc, xp, yp, up, vp, out=None):
+        """tr: _abi.Traject; x, y: grid nodes (0:mnx,0:mny); particle arrays of tr.ntr float64 (out: int32 or None)."""
+        a = [np.ascontiguousarray(q, dtype=np.float64) for q in (x, y, cpartx, cparty, repc, xp, yp, up, vp)]
+        o = None if out is None else np.ascontiguousarray(out, dtype=np.int32)
+        _check(lib().wolfd2_b200_set_trajectories(self._h, C.byref(tr), *[q.ctypes.data_as(c_f64p) for q in a],
+                                                  o.ctypes.data_as(c_i32p) if o is not None else None),
+               "wolfd2_b200_set_trajectories")
+        self._ntr = tr.ntr
+
+    def particles(self):
+        n = self._ntr
+        xp, yp, up, vp = (np.zeros(n) for _ in range(4))
+        out = np.zeros(n, dtype=np.int32)
+        _check(lib().wolfd2_b200_get_particles(self._h, *[q.ctypes.data_as(c_f64p) for q in (xp, yp, up, vp)],
+                                               out.ctypes.data_as(c_i32p)), "wolfd2_b200_get_particles")
+        return xp, yp, up, vp, out
 
     def upload(self, which, arr):
         assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]

@@ -203,7 +203,7 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     W2_CUDA(cudaMalloc((void **)&c->dreg, sizeof(W2Regions)));
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) W2_TRY(falloc(c, &mp[k]));
-    for (int k = 0; k < W2_F_COUNT; ++k) W2_TRY(falloc(c, &c->fld[k]));
+    for (int k = 0; k < W2_F_CORE; ++k) W2_TRY(falloc(c, &c->fld[k]));
     W2_TRY(falloc(c, &c->dus));
     W2_TRY(falloc(c, &c->dvs));
     W2_TRY(falloc(c, &c->div));
@@ -241,6 +241,8 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    w2_atd_release(c);
+    w2_traj_release(c);
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);
@@ -347,6 +349,7 @@ extern "C" int wolfd2_b200_create_slab(wolfd2_ctx **out, const wolfd2_params *pa
 
 extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const double *host) {
     if (!c || !host || which < 0 || which >= W2_F_COUNT) return W2_ERR_BAD_ARG;
+    if (!c->fld[which]) { w2_set_error("field %d does not exist in this context (small-scale model off)", which); return W2_ERR_BAD_ARG; }
     W2_CUDA(cudaSetDevice(c->device));
     W2_TRY(w2_upload2d(c, c->fld[which], host));
     if (which == W2_F_D || which == W2_F_DN) c->dn_valid = 0;
@@ -355,6 +358,7 @@ extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const doub
 }
 extern "C" int wolfd2_b200_download_field(wolfd2_ctx *c, int32_t which, double *host) {
     if (!c || !host || which < 0 || which >= W2_F_COUNT) return W2_ERR_BAD_ARG;
+    if (!c->fld[which]) { w2_set_error("field %d does not exist in this context (small-scale model off)", which); return W2_ERR_BAD_ARG; }
     W2_CUDA(cudaSetDevice(c->device));
     W2_TRY(w2_download2d(c, host, c->fld[which]));
     W2_CUDA(cudaStreamSynchronize(c->stream));

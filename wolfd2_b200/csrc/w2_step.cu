@@ -35,13 +35,22 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS], *ts = c->fld[W2_F_TS];
     double *un = c->fld[W2_F_UN], *vn = c->fld[W2_F_VN], *pn = c->fld[W2_F_PN], *tn = c->fld[W2_F_TN];
     const bool thermal = c->th.nthermen == 1;
+    const bool atd = c->atd && c->atd->ss.nsmallscl == 1;
     cudaStream_t s = c->stream;
     cudaEventRecord(c->ev[0], s);
     // :696-704  time-level n copies (without the thermal energy equation t is identically zero; d only
     // changes through EqState, so dn is refreshed only then)
     W2_TRY(w2_copy_field(c, un, u));
     W2_TRY(w2_copy_field(c, vn, v));
-    if (thermal) W2_TRY(w2_copy_field(c, tn, t));
+    if (thermal || atd) W2_TRY(w2_copy_field(c, tn, t));   // with the ATD model t carries tss even in cold flow
+    if (atd) {                                             // :706-727
+        W2Atd *a = c->atd;
+        double *uss = c->fld[W2_F_USS], *vss = c->fld[W2_F_VSS], *tss = c->fld[W2_F_TSS];
+        W2_TRY(w2_copy_field(c, a->usn, uss));
+        W2_TRY(w2_copy_field(c, a->vsn, vss));
+        W2_TRY(w2_copy_field(c, a->tsn, tss));
+        W2_TRY(w2_axpy3(c, +1.0, un, uss, vn, vss, tn, tss));
+    }
     if (thermal || !c->dn_valid) { W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D])); c->dn_valid = 1; }
     int nme = c->par.nmeiter;
     if (!thermal && nme > 0) nme = 1;                        // :736
@@ -51,9 +60,9 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         W2_TRY(w2_copy_field(c, us, u));
         W2_TRY(w2_copy_field(c, vs, v));
         if (thermal) W2_TRY(w2_copy_field(c, ts, t));
-        // us == un on the first pass, so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
+        // us == un on the first pass (not with the ATD model, where un carries uss: then the loop of :114-119 is real), so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
         // on later passes it resets us, vs to un, vn as the reference does
-        W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1, &nQL));   // :753
+        W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1 || atd, &nQL));   // :753
         if (l == 1) {
             // The momentum solve does not read p; step_host uploads p on a second stream meanwhile.  pn <- p
             // (:696) therefore happens here, after that upload has landed.
@@ -91,6 +100,12 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         if (l > 1 && dmemax < c->th.dmeittol) break;    // :873-877
     }
     if (thermal && c->th.nfiltt == 1) W2_TRY(w2_filter(c, W2_T, c->th.fpt, t));   // :890-894
+    if (atd) {                                      // :896-940
+        W2Atd *a = c->atd;
+        W2_TRY(w2_axpy3(c, -1.0, u, a->usn, v, a->vsn, t, a->tsn));
+        W2_TRY(w2_smallscale(c, 1, u, v, t));
+        W2_TRY(w2_axpy3(c, +1.0, u, c->fld[W2_F_USS], v, c->fld[W2_F_VSS], t, c->fld[W2_F_TSS]));
+    }
     W2_TRY(w2_vel_bc(c, u, v));                     // :946
     W2_TRY(w2_pres_bc(c, p));                       // :950
     if (thermal) W2_TRY(w2_temp_bc(c, t));          // :955
@@ -98,10 +113,10 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     W2_TRY(w2_diffmaxnorm_async(c, pn, p, 0));      // :962-965
     W2_TRY(w2_diffmaxnorm_async(c, un, u, 1));
     W2_TRY(w2_diffmaxnorm_async(c, vn, v, 2));
-    if (thermal) W2_TRY(w2_diffmaxnorm_async(c, tn, t, 3));
+    if (thermal || atd) W2_TRY(w2_diffmaxnorm_async(c, tn, t, 3));
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
-    W2_TRY(w2_norm_fetch(c, thermal ? 4 : 3, dif)); // syncs the stream
+    W2_TRY(w2_norm_fetch(c, thermal || atd ? 4 : 3, dif)); // syncs the stream
     float t_tot = 0, t_mom = 0, t_bc1 = 0, t_ppe = 0, t_tail = 0;
     if (nme > 0) {
         cudaEventElapsedTime(&t_tot, c->ev[0], c->ev[6]);
@@ -122,6 +137,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         w2_set_error("* Solution diverged. Please reduce CFL number.");   // :970
         return W2_ERR_DIVERGED;
     }
+    if (c->traj && c->traj->active) W2_TRY(w2_traject_step(c));   // :1000-1024
     return W2_OK;
 }
 
@@ -493,4 +509,113 @@ extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int
     down(c, us, c->fld[W2_F_US], who); down(c, vs, c->fld[W2_F_VS], who);
     sync(c, who);
     return nql;
+}
+
+// ---- optional paths
+static void shim_thermal(wolfd2_ctx *c, const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal, const char *who) {
+    SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nTemBdTp, dTRgVal, nullptr), who);
+}
+
+extern "C" void smlsclbc_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                          const int32_t *nRegType, const int32_t *nMomBdTp, const int32_t *nTRgType, const int32_t *nTemBdTp,
+                          const double *dBCVal, double *u, double *v, double *p, double *t) {
+    const char *who = "smlsclbc_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, dBCVal, nullptr, nullptr, nullptr, who);
+    shim_thermal(c, nTRgType, nTemBdTp, nullptr, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who); up(c, c->fld[W2_F_P], p, who); up(c, c->fld[W2_F_T], t, who);
+    SHIM_TRY(w2_smlscl_bc(c, c->fld[W2_F_U], c->fld[W2_F_V], c->fld[W2_F_P], c->fld[W2_F_T]), who);
+    down(c, u, c->fld[W2_F_U], who); down(c, v, c->fld[W2_F_V], who); down(c, p, c->fld[W2_F_P], who); down(c, t, c->fld[W2_F_T], who);
+    sync(c, who);
+}
+
+extern "C" void smallscale_(const int32_t *nx, const int32_t *ny, const int32_t *initflg, const int32_t *nthermen,
+    const int32_t *lCartesGrid, const int32_t *nReg, const int32_t *nRegBrd,
+    const int32_t *nRegType, const int32_t *nTRgType, const int32_t *nMomBdTp, const int32_t *nTemBdTp,
+    const int32_t *nPpeSolver, const int32_t *msorit,
+    const double *dlref, const double *uref, const double *tref, const double *tmax,
+    const double *dka, const double *re, const double *pe, const double *sortol, const double *sorrel,
+    const double *fp, const double *cu0, const double *TsCoef, const double *HsCoef, const double *TemCoef,
+    const double *bnumc, const double *rmax, const double *rlc, const double *dTRgVal, const double *dBCVal,
+    const double *rau, const double *rbu, const double *rbv, const double *rgv,
+    const double *dju, const double *djv, const double *djc,
+    const double *xeu, const double *yeu, const double *xzv, const double *yzv,
+    const double *xzu, const double *yzu, const double *xev, const double *yev,
+    const double *xec, const double *yec, const double *xzc, const double *yzc,
+    const double *u1, const double *v1, const double *t1,
+    double *uss, double *vss, double *pss, double *tss) {
+    const char *who = "smallscale_";
+    (void)nthermen; (void)xzu; (void)yev;
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nMomBdTp, dBCVal, nullptr, nullptr, nullptr, who);
+    shim_thermal(c, nTRgType, nTemBdTp, dTRgVal, who);
+    wolfd2_smallscale S;
+    memset(&S, 0, sizeof(S));
+    S.nsmallscl = 1; S.nssPpeSlvr = *nPpeSolver; S.mssSorIt = *msorit;
+    S.dlref = *dlref; S.uref = *uref; S.tref = *tref; S.tmax = *tmax; S.pe = *pe;
+    S.ssSorTol = *sortol; S.ssSorRel = *sorrel;
+    for (int k = 0; k < 4; ++k) S.ssFiltPar[k] = fp[k];
+    S.ssCu0 = *cu0; S.ssTsCoef = *TsCoef; S.ssHsCoef = *HsCoef; S.ssTemCoef = *TemCoef;
+    S.ssBnCrit = *bnumc; S.ssRMpMax = *rmax; S.ssRMpExp = *rlc;
+    c->par.lCartesGrid = *lCartesGrid; c->par.dk = *dka; c->par.re = *re;
+    c->par.nPpeSolver = *nPpeSolver; c->par.msorit = *msorit; c->par.sortol = *sortol; c->par.sorrel = *sorrel;
+    SHIM_TRY(wolfd2_b200_set_smallscale(c, &S), who);
+    W2Metrics &m = c->met;
+    up(c, m.rau, rau, who); up(c, m.rbu, rbu, who); up(c, m.rbv, rbv, who); up(c, m.rgv, rgv, who);
+    up(c, m.dju, dju, who); up(c, m.djv, djv, who); up(c, m.djc, djc, who);
+    up(c, m.xeu, xeu, who); up(c, m.yeu, yeu, who); up(c, m.xzv, xzv, who); up(c, m.yzv, yzv, who);
+    up(c, m.yzu, yzu, who); up(c, m.xev, xev, who);
+    up(c, m.xec, xec, who); up(c, m.yec, yec, who); up(c, m.xzc, xzc, who); up(c, m.yzc, yzc, who);
+    up(c, c->fld[W2_F_U], u1, who); up(c, c->fld[W2_F_V], v1, who); up(c, c->fld[W2_F_T], t1, who);
+    up(c, c->fld[W2_F_USS], uss, who); up(c, c->fld[W2_F_VSS], vss, who);
+    up(c, c->fld[W2_F_PSS], pss, who); up(c, c->fld[W2_F_TSS], tss, who);
+    SHIM_TRY(w2_smallscale(c, *initflg, c->fld[W2_F_U], c->fld[W2_F_V], c->fld[W2_F_T]), who);
+    down(c, uss, c->fld[W2_F_USS], who); down(c, vss, c->fld[W2_F_VSS], who);
+    down(c, pss, c->fld[W2_F_PSS], who); down(c, tss, c->fld[W2_F_TSS], who);
+    sync(c, who);
+}
+
+extern "C" void ptdavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                        const int32_t *nRegType, const double *p, double *pav) {
+    const char *who = "ptdavg_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nullptr, nullptr, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_P], p, who); up(c, c->fld[W2_F_PN], pav, who);
+    SHIM_TRY(w2_ptdavg(c, c->fld[W2_F_P], c->fld[W2_F_PN]), who);
+    down(c, pav, c->fld[W2_F_PN], who);
+    sync(c, who);
+}
+extern "C" void velavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
+                        const int32_t *nRegType, const double *u, const double *v, double *util, double *vbar) {
+    const char *who = "velavg_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nullptr, nullptr, nullptr, nullptr, nullptr, who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who);
+    up(c, c->fld[W2_F_US], util, who); up(c, c->fld[W2_F_VS], vbar, who);
+    SHIM_TRY(w2_velavg(c, c->fld[W2_F_U], c->fld[W2_F_V], c->fld[W2_F_US], c->fld[W2_F_VS]), who);
+    down(c, util, c->fld[W2_F_US], who); down(c, vbar, c->fld[W2_F_VS], who);
+    sync(c, who);
+}
+
+extern "C" void traject_(const int32_t *nx, const int32_t *ny, const int32_t *ntr, const int32_t *ntsubstp,
+    const int32_t *nTrMethod, const int32_t *nTrCdEq, const int32_t *mTrHTmit, int32_t *nTOutBnd,
+    const double *dkflow, const double *densref, const double *fr, const double *dTrHTtol, const double *dTrHTdel,
+    const double *cpartx, const double *cparty, const double *repc,
+    const double *x, const double *y, const double *u, const double *v, const double *un, const double *vn,
+    const double *dens, const double *densn, double *xp, double *yp, double *up_, double *vp) {
+    const char *who = "traject_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    wolfd2_traject T;
+    memset(&T, 0, sizeof(T));
+    T.ntr = *ntr; T.ntsubstp = *ntsubstp; T.nTrMethod = *nTrMethod; T.nTrCdEq = *nTrCdEq; T.mTrHTmit = *mTrHTmit;
+    T.densref = *densref; T.dTrHTtol = *dTrHTtol; T.dTrHTdel = *dTrHTdel;
+    if (T.ntr <= 0) return;
+    SHIM_TRY(w2_traj_set_grid(c, x, y), who);
+    SHIM_TRY(w2_traj_set_particles(c, &T, cpartx, cparty, repc, xp, yp, up_, vp, nTOutBnd), who);
+    up(c, c->fld[W2_F_U], u, who); up(c, c->fld[W2_F_V], v, who); up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
+    up(c, c->fld[W2_F_D], dens, who); up(c, c->fld[W2_F_DN], densn, who);
+    SHIM_TRY(w2_traject(c, *dkflow, *fr, c->fld[W2_F_U], c->fld[W2_F_V], c->fld[W2_F_UN], c->fld[W2_F_VN], c->fld[W2_F_D],
+                        c->fld[W2_F_DN]), who);
+    SHIM_TRY(wolfd2_b200_get_particles(c, xp, yp, up_, vp, nTOutBnd), who);
+    c->traj->active = 0;   // the shim context is shared: a later step through it must not move these particles
 }

@@ -92,6 +92,7 @@ int w2_set_thermal_tables(wolfd2_ctx *c, const int32_t *nTRgType, const int32_t 
             H.trgval[q] = dTRgVal ? dTRgVal[base] : 0.0;
             H.hgst[q] = dHGSTval ? dHGSTval[base] : 0.0;
         }
+    c->th_tables = nTRgType && nTemBdTp;
     W2_CUDA(cudaMemcpyAsync(c->dth, &c->hth, sizeof(W2Thermal), cudaMemcpyHostToDevice, c->stream));
     W2_CUDA(cudaStreamSynchronize(c->stream));
     dim3 grid((c->nx + 2 + 255) / 256, c->ny + 2);
@@ -110,6 +111,9 @@ extern "C" int wolfd2_b200_set_thermal(wolfd2_ctx *c, const wolfd2_thermal *th) 
             w2_set_error("set_thermal: region tables missing");
             return W2_ERR_BAD_ARG;
         }
+        W2_TRY(w2_set_thermal_tables(c, th->nTRgType, th->nTemBdTp, th->dTRgVal, th->dHGSTval));
+    } else if (th->nTRgType && th->nTemBdTp && th->dTRgVal) {
+        // cold flow, tables given all the same: the ATD model calls TempBoundCond and Filter(_T_) in any case
         W2_TRY(w2_set_thermal_tables(c, th->nTRgType, th->nTemBdTp, th->dTRgVal, th->dHGSTval));
     }
     c->th = *th;

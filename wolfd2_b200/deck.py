@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._abi import METRIC_NAMES, Metrics, Params, Regions, Thermal, c_f64p, c_i32p
+from ._abi import METRIC_NAMES, Metrics, Params, Regions, SmallScale, Thermal, c_f64p, c_i32p
 
 # include/wolfd2.h:15-59
 RM_BLOCKG, RM_INTERN, RM_POROUS = 0, 1, 2
@@ -394,6 +394,20 @@ class Deck:
     tmax: float = 310.0
     tref: float = 300.0
     rconst: float = 287.0
+    # ATD small-scale model (small_scale / atd_* of the reference's input deck; defaults src/parse.f:144-178)
+    smallscale: bool = False
+    ss_ppe_solver: str = "sor"
+    ss_msorit: int = 2000
+    ss_sortol: float = 1e-8
+    ss_sorrel: float = 1.0
+    ss_filt: tuple = (5e2, 5e2, 0.0, 5e2)
+    ss_cu0: float = 0.0
+    ss_tscoef: float = 1.0
+    ss_hscoef: float = 1.0
+    ss_temcoef: float = 1.0
+    ss_bncrit: float = 2e2
+    ss_rmpmax: float = 0.95
+    ss_rmpexp: float = 5.0
     # one rank's share of a multi-GPU run: (rank, world, J0, J1, A0, A1, HG), wolfd2_b200/slab.py.  nx, ny,
     # regions and params stay global; metrics and fields hold rows A0..A1 only (row 0 = global row A0)
     slab: tuple = None
@@ -433,6 +447,25 @@ class Deck:
         t.dTRgVal = r.dTRgVal.ctypes.data_as(c_f64p)
         t.dHGSTval = r.dHGSTval.ctypes.data_as(c_f64p)
         return t
+
+    def smallscale_struct(self) -> SmallScale:
+        q = SmallScale()
+        q.nsmallscl = int(self.smallscale)
+        q.nssPpeSlvr, q.mssSorIt = PPE_SOLVERS[self.ss_ppe_solver], self.ss_msorit
+        q.dlref, q.uref, q.tref, q.tmax, q.pe = self.dlref, self.uref, self.tref, self.tmax, self.pe
+        q.ssSorTol, q.ssSorRel = self.ss_sortol, self.ss_sorrel
+        for k in range(4):
+            q.ssFiltPar[k] = self.ss_filt[k]
+        q.ssCu0, q.ssTsCoef, q.ssHsCoef, q.ssTemCoef = self.ss_cu0, self.ss_tscoef, self.ss_hscoef, self.ss_temcoef
+        q.ssBnCrit, q.ssRMpMax, q.ssRMpExp = self.ss_bncrit, self.ss_rmpmax, self.ss_rmpexp
+        return q
+
+    def node_arrays(self):
+        """Grid nodes as main.f holds them: x(0:mnx,0:mny), y, nodes at 1..nx, 1..ny (src/grid.f)."""
+        gx, gy = self.new_field(), self.new_field()
+        gx[1:self.ny + 1, 1:self.nx + 1] = self.x_nodes / self.dlref
+        gy[1:self.ny + 1, 1:self.nx + 1] = self.y_nodes / self.dlref
+        return gx, gy
 
     def metrics_struct(self) -> Metrics:
         m = Metrics()
