@@ -1877,6 +1877,7 @@ void orc_atd_init(const wolfd2_params *par, const wolfd2_regions *reg, const wol
 }
 
 static double *S_usn, *S_vsn, *S_tsn;
+static size_t S_usn_n;
 /* ss != NULL with nsmallscl == 1: the ATD blocks of :706-727 and :896-940 (th must carry the thermal tables);
  * pt != NULL: the trajectory block of :997-1031 */
 int32_t orc_step_full(const wolfd2_params *par, const wolfd2_regions *reg, const wolfd2_metrics *m,
@@ -1886,9 +1887,10 @@ int32_t orc_step_full(const wolfd2_params *par, const wolfd2_regions *reg, const
                       int32_t nsteps, wolfd2_step_log *logs) {
     const int nsmallscl = ss ? ss->nsmallscl : 0;
     if (nsmallscl == 1 || pt) {
-        if (!S_usn || S_n != NFULL) {
+        if (!S_usn || S_usn_n != NFULL) {
             free(S_usn); free(S_vsn); free(S_tsn);
             S_usn = zalloc(NFULL); S_vsn = zalloc(NFULL); S_tsn = zalloc(NFULL);
+            S_usn_n = NFULL;
         }
     }
     double *usn = S_usn, *vsn = S_vsn, *tsn = S_tsn;

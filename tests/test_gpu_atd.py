@@ -161,16 +161,20 @@ def test_smallscale_seeding_bitwise_and_initflg_negative(api, orc):
 @pytest.mark.parametrize("d", ATD_DECKS, ids=ATD_IDS)
 def test_steps_with_smallscale(api, orc, d):
     """src/main.f:643-665 then 4 steps with the blocks of :706-727 and :896-940; the maps start bit-identical."""
-    _cfg(api, orc, d)
+    import dataclasses
     from wolfd2_b200.api import F_D, F_P, F_PSS, F_T, F_TSS, F_U, F_USS, F_V, F_VSS
+    # cu0 = 0.05 keeps the fluctuations at a few per cent of the flow while the maps grow from their seeds
+    d = dataclasses.replace(d, ss_cu0=0.05, sorrel=1.7)
+    _cfg(api, orc, d)
+    # a developed flow is needed for the model to switch on (peh > 3): one vortex filling the box, made
+    # solenoidal by the cold-start projection
+    gx, gy = d.node_arrays()
+    X, Y = gx / gx.max(), gy / gy.max()
     u, v, p, t, dd = (d.new_field() for _ in range(5))
+    u[:] = np.sin(np.pi * X) ** 2 * np.sin(2 * np.pi * Y)
+    v[:] = -np.sin(2 * np.pi * X) * np.sin(np.pi * Y) ** 2
     ss = [d.new_field() for _ in range(4)]
     orc.coldstart(d, u, v, p)
-    # a developed flow is needed for the model to switch on (peh > 3): a few plain steps first
-    import dataclasses
-    d0 = dataclasses.replace(d, smallscale=False)
-    rc, _ = orc.step(d0, u, v, p, nsteps=6, t=t, d=dd)
-    assert rc == 0
     with api.Context(d) as ctx:
         for w, a in ((F_U, u), (F_V, v), (F_P, p), (F_T, t), (F_D, dd)):
             ctx.upload(w, a)
