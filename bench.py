@@ -41,10 +41,13 @@ def global_ny(args, world):
     return args.n * world if args.scaling == "weak" else args.n
 
 
-def make_deck(workload, n, fixed_work, q_iters, s_iters, ny=None, slab=None):
+def make_deck(workload, n, fixed_work, q_iters, s_iters, ny=None, slab=None, atd=False):
     from wolfd2_b200 import deck as dk
     ny = ny or n
     kw = {"ny": ny}
+    if atd:   # BASELINE.json configs[4]: ATD small-scale model on; its own Ppe does the same fixed work
+        kw.update(smallscale=True, ss_cu0=0.02, ss_bncrit=2.0, ss_ppe_solver="rb_sor",
+                  ss_msorit=s_iters if fixed_work else 2000, ss_sortol=0.0 if fixed_work else 1e-8)
     if slab is not None:
         kw["slab"] = slab          # (rank, world): this rank's rows only
     nmax = max(n, ny)
@@ -269,13 +272,29 @@ def run_gpu(args):
         slab.init_comm(dist, local)     # the library's own NCCL communicator; torch only carries the id
         d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters, ny=nyg, slab=(rank, world))
     else:
-        d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters)
+        d = make_deck(args.workload, args.n, args.fixed_work, args.q_iters, args.s_iters, atd=args.atd)
+    if world > 1 and (args.atd or args.particles):
+        raise SystemExit("bench: --atd / --particles run on one GPU (SURVEY 8f N2/N3 are single-GPU rows)")
     cells = (d.nx - 1) * (d.ny - 1)          # pressure unknowns of the whole grid
     cells_local = (d.nx - 1) * (d.slab[3] - d.slab[2] + 1) if d.slab else cells
     ctx = api.Context(d)
     for w, f in zip((api.F_U, api.F_V, api.F_P), developed_state(d)):
         ctx.upload(w, f)
     ctx.coldstart()
+    if args.atd:
+        ctx.smallscale_init()                # src/main.f:643-665
+    if args.particles:                       # configs[4]: particles on a uniform lattice, FwdEuler, Stokes drag
+        from wolfd2_b200 import _abi
+        side = max(1, int(round(args.particles ** 0.5)))
+        gx, gy = d.node_arrays()
+        lat = (np.arange(side) + 0.5) / side * 0.8 + 0.1
+        xp, yp = [a.ravel().copy() for a in np.meshgrid(lat, lat)]
+        npart = xp.size
+        tr = _abi.Traject()
+        tr.ntr, tr.ntsubstp, tr.nTrMethod, tr.nTrCdEq, tr.mTrHTmit = npart, 1, 2, 1, 1
+        tr.densref, tr.dTrHTtol, tr.dTrHTdel = 1.2, 1e-8, 1.0
+        ctx.set_trajectories(tr, gx, gy, np.full(npart, 2.0), np.full(npart, 2.0), np.full(npart, 10.0),
+                             xp, yp, np.zeros(npart), np.zeros(npart))
 
     def barrier():
         ctx.sync()
@@ -321,6 +340,12 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     e2e_s = slab.max_over_ranks(e2e_s, dist, "cuda" if dist is not None else None)
     e2e = cells * args.steps / e2e_s / 1e9
+    part_info = None
+    if args.particles:
+        gxp, gyp, gup, gvp, gout = ctx.particles()
+        part_info = {"particles": int(gxp.size), "in_bounds": int((gout == 0).sum()),
+                     "finite": bool(np.isfinite(gxp).all() and np.isfinite(gup).all()),
+                     "mean_speed": float(np.hypot(gup, gvp)[gout == 0].mean()) if (gout == 0).any() else 0.0}
     for nm, f in (("u", hu), ("v", hv), ("p", hp)):   # the timed run must have produced a sane flow
         if not np.isfinite(f).all() or np.abs(f).max() > 1.0e3:
             raise SystemExit(f"bench: field {nm} is not finite/bounded after the run (max {np.abs(f).max()})")
@@ -370,7 +395,12 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu:
+    if args.atd or args.particles:   # BASELINE.json configs[4]; a parity-test configuration, not the headline line
+        line["config"]["optional_paths"] = {
+            "small_scale": bool(args.atd), "trajectories": part_info,
+            "note": "SmallScale (own Ppe of the same fixed work) and/or Traject run inside every step on the device; "
+                    "step_roofline counts the large-scale step's algorithmic bytes only"}
+    if world == 1 and not args.no_cpu and not (args.atd or args.particles):
         try:
             n, _ = cpu_sample_size(args, budget_s=20.0, nsteps=1)
             dc = make_deck(args.workload, n, args.fixed_work, args.q_iters, args.s_iters)
@@ -396,6 +426,8 @@ def main():
     ap.add_argument("--q-iters", type=int, default=2)
     ap.add_argument("--s-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--atd", action="store_true", help="ATD small-scale model on (BASELINE.json configs[4])")
+    ap.add_argument("--particles", type=int, default=0, help="Lagrangian particles (configs[4]: 1000000)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = n x (n*N) grid, n rows per GPU; strong = the n x n grid cut into N slabs")
     args = ap.parse_args()

@@ -245,7 +245,9 @@ def test_traject_literal(api, orc, kind, method, cdeq):
         res.append((st, out))
     (sg, og), (so, oo) = res
     assert np.array_equal(og, oo)
-    assert set(oo[:4]) == {1, 2, 3} and (oo[8:] == 0).sum() > n // 2
+    if kind != "skewed":   # (on the skewed grid the first match of the scan need not be the containing cell)
+        assert set(oo[:4]) == {1, 2, 3}
+    assert (oo[8:] == 0).sum() > n // 2
     exact = cdeq in (1, 3)
     for name, a, b in zip(("xp", "yp", "up", "vp"), sg, so):
         if exact:
