@@ -342,6 +342,31 @@ double diffmaxnorm_(const int32_t *nx, const int32_t *ny, const double *un,
                     const double *u);
 double dmaxnorm_(const int32_t *nx, const int32_t *ny, const double *u);
 
+/* Routines below XMomentum / YMomentum / Ppe in the reference's call tree, exported for unit parity.
+ * On the production path they are evaluated per unknown inside the momentum kernels; these entry points run
+ * the same device functions one operator at a time.  Output arrays are in/out: only the reference's loop
+ * ranges are written.
+ * ConvCoef src/momentum.f:864-866; DConvU :987; DDiffU :1015; DConvV :1051; DDiffV :1079; PorosCoef :1115-1118;
+ * RhsPpe src/pressure.f:329-330 (b is the vector b(mn), entries 1..(nx-1)(ny-1)).
+ * Not exported: Sor, SorRB, SorRBP, Slor, SlorRB, SlorRBP (src/pressure.f:384-1138) take the assembled matrix
+ * a(mn,5), which this implementation never forms (coefficients are re-formed from rau, rgv); they are reached
+ * through ppe_ with nPpeSolver = 1..6. */
+void convcoef_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *njacob,
+               const double *xzi, const double *xet, const double *yzi, const double *yet,
+               const double *u, const double *v, double *cc1, double *cc2);
+void dconvu_(const int32_t *nx, const int32_t *ny, const double *c1, const double *c2, const double *u, double *c);
+void ddiffu_(const int32_t *nx, const int32_t *ny, const double *ac, const double *bc, const double *bn,
+             const double *gn, const double *u, double *d);
+void dconvv_(const int32_t *nx, const int32_t *ny, const double *c1, const double *c2, const double *v, double *c);
+void ddiffv_(const int32_t *nx, const int32_t *ny, const double *an, const double *bc, const double *bn,
+             const double *gc, const double *v, double *d);
+void poroscoef_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *njacob,
+                const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType,
+                const double *dPRporos, const double *dPRporc1, const double *dPRporc2,
+                const double *u, const double *v, double *cp);
+void rhsppe_(const int32_t *nx, const int32_t *ny, const int32_t *lCartesGrid, const double *dk,
+             const double *rbu, const double *rbv, const double *div, const double *p, double *b);
+
 /* src/bound_cond.f:1030-1034 */
 void tempboundcond_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
     const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal, const double *dBCVal, double *t);

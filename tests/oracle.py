@@ -10,14 +10,7 @@ from wolfd2_b200 import _abi
 
 # Routines only the oracle exposes individually (internal to the reference's call tree).
 ORACLE_ONLY = {
-    # src/momentum.f:864
-    "convcoef_": (None, "iiii" "DDDD" "DD" "DD"),
-    "dconvu_": (None, "ii" "DDD" "D"),
-    "ddiffu_": (None, "ii" "DDDD" "D" "D"),
-    "dconvv_": (None, "ii" "DDD" "D"),
-    "ddiffv_": (None, "ii" "DDDD" "D" "D"),
-    # src/pressure.f:329, 384, 457, 548, 673, 819, 976
-    "rhsppe_": (None, "ii" "i" "d" "DD" "D" "D" "D"),
+    # src/pressure.f:384, 457, 548, 673, 819, 976 (they take the assembled matrix a(mn,5))
     "sor_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
     "sorrb_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),
     "sorrbp_": (None, "ii" "i" "io" "ddd" "DD" "DD" "D" "D"),

@@ -43,6 +43,15 @@ SIGNATURES = {
     # src/utility.f:446, 479
     "diffmaxnorm_": (C.c_double, "ii" "DD"),
     "dmaxnorm_": (C.c_double, "ii" "D"),
+    # routines below XMomentum/YMomentum/Ppe, exported for unit parity:
+    # src/momentum.f:864-866, 987, 1015, 1051, 1079, 1115-1118; src/pressure.f:329-330
+    "convcoef_": (None, "iiii" "DDDD" "DD" "DD"),
+    "dconvu_": (None, "ii" "DDD" "D"),
+    "ddiffu_": (None, "ii" "DDDD" "D" "D"),
+    "dconvv_": (None, "ii" "DDD" "D"),
+    "ddiffv_": (None, "ii" "DDDD" "D" "D"),
+    "poroscoef_": (None, "iiii" "III" "DDD" "DD" "D"),
+    "rhsppe_": (None, "ii" "i" "d" "DD" "D" "D" "D"),
     # src/bound_cond.f:1030-1034
     "tempboundcond_": (None, "ii" "II" "II" "DD" "D"),
     # src/thermal.f:24-33

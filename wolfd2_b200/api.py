@@ -127,6 +127,14 @@ VelAvg = _routine("velavg")
 Traject_ = _routine("traject")           # `Traject` is the parameter block
 DiffMaxNorm = _routine("diffmaxnorm")
 DMaxNorm = _routine("dmaxnorm")
+# the operators below XMomentum / YMomentum / Ppe, one at a time (unit parity)
+ConvCoef = _routine("convcoef")
+DConvU = _routine("dconvu")
+DDiffU = _routine("ddiffu")
+DConvV = _routine("dconvv")
+DDiffV = _routine("ddiffv")
+PorosCoef = _routine("poroscoef")
+RhsPpe = _routine("rhsppe")
 
 
 class Context:

@@ -513,3 +513,157 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
     }
     return W2_OK;
 }
+
+// ---- unit-parity entry points ("internal but worth exporting") -------------------------
+// ConvCoef, DConvU/V, DDiffU/V and PorosCoef are never materialised on the production path: mom_row evaluates
+// them per unknown.  These kernels run THE SAME device functions (x_c1_raw ... por_coef of w2_mom_rows.inc) one
+// operator at a time over the reference's loop ranges and store the result, so that each stencil can be compared
+// with the oracle bit for bit (convcoef_, dconvu_, ... in w2_step.cu).  Argument combinations the reference
+// never uses (e.g. ncomp 1 with njacob 1, commented out at momentum.f:279) go through the written-out formula.
+__global__ void __launch_bounds__(256) unit_convcoef_kernel(MomArgs m, int ncomp, int njacob, const double *__restrict__ xzi,
+                                                            const double *__restrict__ xet, const double *__restrict__ yzi,
+                                                            const double *__restrict__ yet, const double *__restrict__ u,
+                                                            const double *__restrict__ v, double *__restrict__ cc1,
+                                                            double *__restrict__ cc2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int nx = m.nx, ny = m.ny, pitch = m.pitch;
+    if (i > nx + 1 || j > ny + 1) return;
+    const double djac = njacob == 1 ? 2.0 : 1.0;   // :895-896
+    const bool in1 = i >= 1 && j >= 1;              // 1..nx+1, 1..ny+1
+    const bool in0 = in1 && i <= nx && j <= ny;     // 1..nx, 1..ny
+    using namespace mom_np;
+    switch (ncomp) {
+    case 1:   // :901-913
+        if (in1) cc1[IDX(i, j)] = njacob == 0 ? x_c1_raw(m, u, v, i, j)
+                                              : (djac * F(yet, i, j) * (F(u, i, j) + F(u, i - 1, j)) - F(xet, i, j) * (F(v, i, j) + F(v, i, j - 1))) * 0.5;
+        if (in0) cc2[IDX(i, j)] = njacob == 0 ? x_c2_raw(m, u, v, i, j)
+                                              : (F(xzi, i, j) * (F(v, i + 1, j) + F(v, i, j)) - djac * F(yzi, i, j) * (F(u, i, j + 1) + F(u, i, j))) * 0.5;
+        break;
+    case 2:   // :916-928
+        if (in0) cc1[IDX(i, j)] = njacob == 0 ? y_c1_raw(m, u, v, i, j)
+                                              : (F(yet, i, j) * (F(u, i, j + 1) + F(u, i, j)) - djac * F(xet, i, j) * (F(v, i + 1, j) + F(v, i, j))) * 0.5;
+        if (in1) cc2[IDX(i, j)] = njacob == 0 ? y_c2_raw(m, u, v, i, j)
+                                              : (djac * F(xzi, i, j) * (F(v, i, j) + F(v, i, j - 1)) - F(yzi, i, j) * (F(u, i, j) + F(u, i - 1, j))) * 0.5;
+        break;
+    case 3:   // :931-939
+        if (in0) { cc1[IDX(i, j)] = t_cun(m, u, v, i, j); cc2[IDX(i, j)] = t_cvn(m, u, v, i, j); }
+        break;
+    case 4:   // :942-950, i = 0..nx, j = 1..ny
+        if (i <= nx && j >= 1 && j <= ny) {
+            if (njacob == 1) { cc1[IDX(i, j)] = x_cj1_raw(m, i, j); cc2[IDX(i, j)] = x_cj2_raw(m, i, j); }
+            else {
+                const double s4 = F(v, i + 1, j) + F(v, i, j) + F(v, i + 1, j - 1) + F(v, i, j - 1);
+                cc1[IDX(i, j)] = djac * F(yet, i, j) * F(u, i, j) - F(xet, i, j) * s4 / 4.0;
+                cc2[IDX(i, j)] = F(xzi, i, j) * s4 / 4.0 - djac * F(yzi, i, j) * F(u, i, j);
+            }
+        }
+        break;
+    case 5:   // :953-961, i = 1..nx, j = 0..ny
+        if (i >= 1 && i <= nx && j <= ny) {
+            if (njacob == 1) { cc1[IDX(i, j)] = y_cj1_raw(m, i, j); cc2[IDX(i, j)] = y_cj2_raw(m, i, j); }
+            else {
+                const double s4 = F(u, i, j + 1) + F(u, i - 1, j + 1) + F(u, i, j) + F(u, i - 1, j);
+                cc1[IDX(i, j)] = F(yet, i, j) * s4 / 4.0 - djac * F(xet, i, j) * F(v, i, j);
+                cc2[IDX(i, j)] = djac * F(xzi, i, j) * F(v, i, j) - F(yzi, i, j) * s4 / 4.0;
+            }
+        }
+        break;
+    case 6:   // :964-972
+        if (in1) { cc1[IDX(i, j)] = t_cu1(m, u, v, i, j); cc2[IDX(i, j)] = t_cv1(m, u, v, i, j); }
+        break;
+    }
+}
+
+// DConvU (:1000-1006) / DConvV (:1064-1070) on given coefficient arrays; DDiffU (:1028-1042) / DDiffV (:1092-1106)
+template <int COMP>
+__global__ void __launch_bounds__(256) unit_dconv_kernel(int nx, int ny, int pitch, const double *__restrict__ c1,
+                                                         const double *__restrict__ c2, const double *__restrict__ q,
+                                                         double *__restrict__ out) {
+    const int i = CH_I0(COMP) + blockIdx.x * blockDim.x + threadIdx.x, j = CH_J0(COMP) + blockIdx.y;
+    if (i > nx || j > ny) return;
+    if (COMP == 0) out[IDX(i, j)] = mom_np::x_conv_sum(F(c1, i, j), F(c1, i + 1, j), F(c2, i, j), F(c2, i, j - 1), q, pitch, i, j);
+    else out[IDX(i, j)] = mom_np::y_conv_sum(F(c1, i, j), F(c1, i - 1, j), F(c2, i, j), F(c2, i, j + 1), q, pitch, i, j);
+}
+template <int COMP>
+__global__ void __launch_bounds__(256) unit_ddiff_kernel(MomArgs m, const double *__restrict__ q, double *__restrict__ out) {
+    const int i = CH_I0(COMP) + blockIdx.x * blockDim.x + threadIdx.x, j = CH_J0(COMP) + blockIdx.y;
+    const int pitch = m.pitch;
+    if (i > m.nx || j > m.ny) return;
+    out[IDX(i, j)] = COMP == 0 ? mom_np::x_diff(m, q, i, j) : mom_np::y_diff(m, q, i, j);
+}
+// PorosCoef (:1115-1226): cells no region assignment reaches keep their value
+template <int COMP>
+__global__ void __launch_bounds__(256) unit_poroscoef_kernel(MomArgs m, int njacob, const double *__restrict__ u,
+                                                             const double *__restrict__ v, double *__restrict__ cp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int pitch = m.pitch;
+    if (i > m.nx + 1 || j > m.ny + 1) return;
+    if ((COMP == 0 ? m.xcp : m.ycp)[IDX(i, j)] == 0) return;
+    cp[IDX(i, j)] = mom_po::por_coef<COMP>(m, u, v, njacob, i, j);
+}
+
+int w2_unit_convcoef(wolfd2_ctx *c, int ncomp, int njacob, const double *xzi, const double *xet, const double *yzi,
+                     const double *yet, const double *u, const double *v, double *cc1, double *cc2) {
+    if (ncomp < 1 || ncomp > 6) {
+        w2_set_error("Error: Wrong component flag passed to ConvCoef: %d", ncomp);   // :975-977
+        return W2_ERR_BAD_ARG;
+    }
+    MomArgs m;
+    fill_args(c, m);
+    // the metric names mom_row's operators read, bound to this call's arguments (call sites: momentum.f:282-290,
+    // :607-615, thermal.f:111-116)
+    switch (ncomp) {
+    case 1: m.xzn = xzi; m.xec = xet; m.yzn = yzi; m.yec = yet; break;
+    case 2: m.xzc = xzi; m.xen = xet; m.yzc = yzi; m.yen = yet; break;
+    case 3: m.xzv = xzi; m.xeu = xet; m.yzv = yzi; m.yeu = yet; break;
+    case 4: m.xzu = xzi; m.xeu = xet; m.yzu = yzi; m.yeu = yet; m.us = u; m.vs = v; break;
+    case 5: m.xzv = xzi; m.xev = xet; m.yzv = yzi; m.yev = yet; m.us = u; m.vs = v; break;
+    case 6: m.xzc = xzi; m.xec = xet; m.yzc = yzi; m.yec = yet; break;
+    }
+    dim3 g((c->nx + 2 + 255) / 256, c->ny + 2);
+    unit_convcoef_kernel<<<g, 256, 0, c->stream>>>(m, ncomp, njacob, xzi, xet, yzi, yet, u, v, cc1, cc2);
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+int w2_unit_dconv(wolfd2_ctx *c, int comp, const double *c1, const double *c2, const double *q, double *out) {
+    const int w = comp == 0 ? c->nx : c->nx - 1, h = comp == 0 ? c->ny - 1 : c->ny;
+    dim3 g((w + 255) / 256, h);
+    if (comp == 0) unit_dconv_kernel<0><<<g, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, c1, c2, q, out);
+    else unit_dconv_kernel<1><<<g, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, c1, c2, q, out);
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+// comp 0: (ac, bc, bn, gn) of DDiffU; comp 1: (an, bc, bn, gc) of DDiffV
+int w2_unit_ddiff(wolfd2_ctx *c, int comp, const double *a, const double *bc, const double *bn, const double *g_, const double *q,
+                  double *out) {
+    MomArgs m;
+    fill_args(c, m);
+    m.rbc = bc; m.rbn = bn;
+    if (comp == 0) { m.rac = a; m.rgn = g_; } else { m.ran = a; m.rgc = g_; }
+    const int w = comp == 0 ? c->nx : c->nx - 1, h = comp == 0 ? c->ny - 1 : c->ny;
+    dim3 g((w + 255) / 256, h);
+    if (comp == 0) unit_ddiff_kernel<0><<<g, 256, 0, c->stream>>>(m, q, out);
+    else unit_ddiff_kernel<1><<<g, 256, 0, c->stream>>>(m, q, out);
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+int w2_unit_poroscoef(wolfd2_ctx *c, int ncomp, int njacob, const double *u, const double *v, double *cp) {
+    if (ncomp != 1 && ncomp != 2) {
+        w2_set_error("Error: Wrong ncomp flag passed to PorosCoef: %d", ncomp);   // :1216-1218
+        return W2_ERR_BAD_ARG;
+    }
+    // the last-assignment maps are built with the momentum masks when the deck has a porous region; without one
+    // every region assigns zero on its full index range (:1166-1172)
+    if (!c->hreg.has_porous) {
+        W2_TRY(w2_alloc_pormap(c));
+        dim3 gm((c->nx + 2 + 255) / 256, c->rows);
+        por_map_kernel<<<gm, 256, 0, c->stream>>>(c->dreg, c->nx, c->A0, c->A1, c->pitch, c->nelem, c->pormap);
+    }
+    MomArgs m;
+    fill_args(c, m);
+    dim3 g((c->nx + 2 + 255) / 256, c->ny + 2);
+    if (ncomp == 1) unit_poroscoef_kernel<0><<<g, 256, 0, c->stream>>>(m, njacob, u, v, cp);
+    else unit_poroscoef_kernel<1><<<g, 256, 0, c->stream>>>(m, njacob, u, v, cp);
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}

@@ -150,6 +150,26 @@ __global__ void __launch_bounds__(256) rhs_cross_kernel(int nx, int ny, int pitc
     }
 }
 
+// RhsPpe as a unit (rhsppe_ shim): b(ind), ind = (j-2)*(nx-1)+i-1 (:347-352), from a given div.  The non-Cartesian
+// branch is the production rhs_cross_kernel; this kernel only gathers its field-layout result into the
+// reference's vector ordering (Cartesian grids: b = div/dk, the statement div_rhs_kernel fuses with Divergence).
+__global__ void __launch_bounds__(256) unit_rhs_gather_kernel(int nx, int ny, int pitch, int cartes, double dk,
+                                                              const double *__restrict__ div, const double *__restrict__ bf,
+                                                              double *__restrict__ bvec) {
+    const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x, j = 2 + blockIdx.y;
+    if (i > nx || j > ny) return;
+    const size_t ind = (size_t)(j - 2) * (size_t)(nx - 1) + (size_t)(i - 2);
+    bvec[ind] = cartes ? div[IDX(i, j)] / dk : bf[IDX(i, j)];
+}
+int w2_unit_rhsppe(wolfd2_ctx *c, int cartes, double dk, const double *rbu, const double *rbv, const double *div, const double *p,
+                   double *bfield, double *bvec) {
+    dim3 g((c->nx - 1 + 255) / 256, c->ny - 1);
+    if (!cartes) rhs_cross_kernel<<<g, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, dk, rbu, rbv, div, p, bfield, nullptr);
+    unit_rhs_gather_kernel<<<g, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, cartes, dk, div, bfield, bvec);
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
+
 // ------------------------------------------------------------------ SOR control block
 // ctl[0]=done, ctl[1]=iterations completed (m), ctl[2]=nConv, ctl[3]=CTA ticket counter
 // slot: running max |sum| of the current iteration (bit pattern of a non-negative double).

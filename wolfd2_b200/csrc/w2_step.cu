@@ -511,6 +511,80 @@ extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int
     return nql;
 }
 
+// ---- unit-parity shims of the routines below XMomentum / YMomentum / Ppe in the reference's call tree
+// ("internal but worth exporting").  Output arrays are in/out as in the reference: cells
+// outside the loop ranges keep the caller's values.
+extern "C" void convcoef_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *njacob,
+                          const double *xzi, const double *xet, const double *yzi, const double *yet, const double *u,
+                          const double *v, double *cc1, double *cc2) {
+    const char *who = "convcoef_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    W2Metrics &t = c->met;
+    up(c, t.xzn, xzi, who); up(c, t.xec, xet, who); up(c, t.yzn, yzi, who); up(c, t.yec, yet, who);
+    up(c, c->fld[W2_F_US], u, who); up(c, c->fld[W2_F_VS], v, who);
+    up(c, c->dus, cc1, who); up(c, c->dvs, cc2, who);
+    SHIM_TRY(w2_unit_convcoef(c, *ncomp, *njacob, t.xzn, t.xec, t.yzn, t.yec, c->fld[W2_F_US], c->fld[W2_F_VS], c->dus, c->dvs), who);
+    down(c, cc1, c->dus, who); down(c, cc2, c->dvs, who);
+    sync(c, who);
+}
+static void shim_dconv(int comp, const int32_t *nx, const int32_t *ny, const double *c1, const double *c2, const double *q,
+                       double *out, const char *who) {
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    up(c, c->dus, c1, who); up(c, c->dvs, c2, who); up(c, c->fld[W2_F_US], q, who); up(c, c->x1, out, who);
+    SHIM_TRY(w2_unit_dconv(c, comp, c->dus, c->dvs, c->fld[W2_F_US], c->x1), who);
+    down(c, out, c->x1, who);
+    sync(c, who);
+}
+extern "C" void dconvu_(const int32_t *nx, const int32_t *ny, const double *c1, const double *c2, const double *u, double *cv) {
+    shim_dconv(0, nx, ny, c1, c2, u, cv, "dconvu_");
+}
+extern "C" void dconvv_(const int32_t *nx, const int32_t *ny, const double *c1, const double *c2, const double *v, double *cv) {
+    shim_dconv(1, nx, ny, c1, c2, v, cv, "dconvv_");
+}
+static void shim_ddiff(int comp, const int32_t *nx, const int32_t *ny, const double *a, const double *bc, const double *bn,
+                       const double *g, const double *q, double *out, const char *who) {
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    W2Metrics &t = c->met;
+    double *da = comp == 0 ? t.rac : t.ran, *dg = comp == 0 ? t.rgn : t.rgc;
+    up(c, da, a, who); up(c, t.rbc, bc, who); up(c, t.rbn, bn, who); up(c, dg, g, who);
+    up(c, c->fld[W2_F_US], q, who); up(c, c->x1, out, who);
+    SHIM_TRY(w2_unit_ddiff(c, comp, da, t.rbc, t.rbn, dg, c->fld[W2_F_US], c->x1), who);
+    down(c, out, c->x1, who);
+    sync(c, who);
+}
+extern "C" void ddiffu_(const int32_t *nx, const int32_t *ny, const double *ac, const double *bc, const double *bn,
+                        const double *gn, const double *u, double *d) {
+    shim_ddiff(0, nx, ny, ac, bc, bn, gn, u, d, "ddiffu_");
+}
+extern "C" void ddiffv_(const int32_t *nx, const int32_t *ny, const double *an, const double *bc, const double *bn,
+                        const double *gc, const double *v, double *d) {
+    shim_ddiff(1, nx, ny, an, bc, bn, gc, v, d, "ddiffv_");
+}
+extern "C" void poroscoef_(const int32_t *nx, const int32_t *ny, const int32_t *ncomp, const int32_t *njacob,
+                           const int32_t *nReg, const int32_t *nRegBrd, const int32_t *nRegType, const double *dPRporos,
+                           const double *dPRporc1, const double *dPRporc2, const double *u, const double *v, double *cp) {
+    const char *who = "poroscoef_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nRegType, nullptr, nullptr, dPRporos, dPRporc1, dPRporc2, who);
+    up(c, c->fld[W2_F_US], u, who); up(c, c->fld[W2_F_VS], v, who); up(c, c->x1, cp, who);
+    SHIM_TRY(w2_unit_poroscoef(c, *ncomp, *njacob, c->fld[W2_F_US], c->fld[W2_F_VS], c->x1), who);
+    down(c, cp, c->x1, who);
+    sync(c, who);
+}
+// b is the reference's vector b(mn): entries 1..(nx-1)(ny-1) are written (pressure.f:347-352)
+extern "C" void rhsppe_(const int32_t *nx, const int32_t *ny, const int32_t *lCartesGrid, const double *dk, const double *rbu,
+                        const double *rbv, const double *div, const double *p, double *b) {
+    const char *who = "rhsppe_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    up(c, c->met.rbu, rbu, who); up(c, c->met.rbv, rbv, who); up(c, c->div, div, who); up(c, c->fld[W2_F_P], p, who);
+    SHIM_TRY(w2_unit_rhsppe(c, *lCartesGrid != 0, *dk, c->met.rbu, c->met.rbv, c->div, c->fld[W2_F_P], c->fld[W2_F_B], c->tb), who);
+    const size_t n = (size_t)(*nx - 1) * (size_t)(*ny - 1);
+    if (cudaMemcpyAsync(b, c->tb, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+        w2_set_error("rhsppe_: copy back failed"); die(who);
+    }
+    sync(c, who);
+}
+
 // ---- optional paths
 static void shim_thermal(wolfd2_ctx *c, const int32_t *nTRgType, const int32_t *nTemBdTp, const double *dTRgVal, const char *who) {
     SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nTemBdTp, dTRgVal, nullptr), who);
