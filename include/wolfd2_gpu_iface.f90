@@ -52,7 +52,24 @@ module wolfd2_gpu
     type(c_ptr)        :: nTRgType, nTemBdTp, dTRgVal, dHGSTval
   end type w2_thermal
 
+  ! struct wolfd2_smallscale: ATD small-scale model (small_scale.f:31-49, main.f:647-665)
+  type, bind(C) :: w2_smallscale
+    integer(c_int32_t) :: nsmallscl, nssPpeSlvr, mssSorIt, reserved
+    real(c_double)     :: dlref, uref, tref, tmax
+    real(c_double)     :: pe
+    real(c_double)     :: ssSorTol, ssSorRel
+    real(c_double)     :: ssFiltPar(4)
+    real(c_double)     :: ssCu0, ssTsCoef, ssHsCoef, ssTemCoef, ssBnCrit, ssRMpMax, ssRMpExp
+  end type w2_smallscale
+
+  ! struct wolfd2_traject: scalar arguments of Traject (traject.f:154-164)
+  type, bind(C) :: w2_traject
+    integer(c_int32_t) :: ntr, ntsubstp, nTrMethod, nTrCdEq, mTrHTmit, reserved
+    real(c_double)     :: densref, dTrHTtol, dTrHTdel
+  end type w2_traject
+
   integer(c_int32_t), parameter :: W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_D = 8, W2_F_T = 11
+  integer(c_int32_t), parameter :: W2_F_USS = 14, W2_F_VSS = 15, W2_F_PSS = 16, W2_F_TSS = 17
 
   interface
     ! replaces the compile-time include/config.f:19-26
@@ -118,6 +135,43 @@ module wolfd2_gpu
       import :: c_int, c_ptr, w2_thermal
       type(c_ptr), value :: ctx
       type(w2_thermal), intent(in) :: th
+    end function
+
+    ! ATD small-scale model on / off (main.f:706-727, :896-940 then run inside wolfd2_b200_step)
+    integer(c_int) function wolfd2_b200_set_smallscale(ctx, ss) bind(C, name='wolfd2_b200_set_smallscale')
+      import :: c_int, c_ptr, w2_smallscale
+      type(c_ptr), value :: ctx
+      type(w2_smallscale), intent(in) :: ss
+    end function
+    ! main.f:643-665 (SmallScale with initflg = 0 on the uploaded fields)
+    integer(c_int) function wolfd2_b200_smallscale_init(ctx) bind(C, name='wolfd2_b200_smallscale_init')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function
+    ! one plane (1..3) of the saved chaotic-map iterates, family 0/1/2 = umap/vmap/tmap (restart files)
+    integer(c_int) function wolfd2_b200_smallscale_map(ctx, family, plane, host, upload) &
+        bind(C, name='wolfd2_b200_smallscale_map')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: family, plane, upload
+      real(c_double), intent(inout) :: host(*)
+    end function
+
+    ! Lagrangian particles: main.f:1000-1024 (VelAvg, PTDAvg, Traject) then ends every step on the device
+    integer(c_int) function wolfd2_b200_set_trajectories(ctx, tr, x, y, cpartx, cparty, repc, xp, yp, up, vp, nTOutBnd) &
+        bind(C, name='wolfd2_b200_set_trajectories')
+      import :: c_int, c_int32_t, c_ptr, c_double, w2_traject
+      type(c_ptr), value :: ctx
+      type(w2_traject), intent(in) :: tr
+      real(c_double), intent(in) :: x(*), y(*), cpartx(*), cparty(*), repc(*), xp(*), yp(*), up(*), vp(*)
+      integer(c_int32_t), intent(in) :: nTOutBnd(*)
+    end function
+    integer(c_int) function wolfd2_b200_get_particles(ctx, xp, yp, up, vp, nTOutBnd) &
+        bind(C, name='wolfd2_b200_get_particles')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: xp(*), yp(*), up(*), vp(*)
+      integer(c_int32_t), intent(out) :: nTOutBnd(*)
     end function
 
     ! several GPUs (one process each): slab layout, NCCL communicator, slab context
