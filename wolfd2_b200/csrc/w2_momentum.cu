@@ -72,6 +72,13 @@ struct ChainWalk {
         pos += d;
         while (pos >= w) { pos -= w; ++j; }
     }
+    // advance by a fixed stride without a loop (a loop is a branch region, and ptxas moves no load across one):
+    // stride = sq*w + sr with sr < w, so one conditional wrap, compiled to selects
+    __device__ __forceinline__ void advance_split(int sq, int sr) {
+        pos += sr; j += sq;
+        const bool wrap = pos >= w;
+        pos = wrap ? pos - w : pos; j = wrap ? j + 1 : j;
+    }
     __device__ __forceinline__ void advance_far(int d) {   // any d >= 0 (one 32-bit division)
         pos += d;
         const int k = pos / w;
@@ -107,30 +114,38 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     constexpr int L = TRI_M - 2;
     if (t == 0) { s_ext[0] = 0; s_ext[1] = 0; }
 
-    // ---- phase A: assemble rows, coalesced (the cheap second-step rows are unrolled for more loads in flight)
-    ChainWalk<COMP> wa(m, ebase + t);
+    // ---- phase A: assemble rows, coalesced (the cheap second-step rows are unrolled for more loads in flight).
+    // The loop body is straight-line code: a branch region (chain end, first-row quirk) would stop ptxas from
+    // issuing the loads of the next unrolled unknown before the current one is finished.  Elements past the end
+    // of the chain (last segment only) assemble the row of the last valid point and are then replaced by the
+    // identity; the first-row quirk is patched in after the loop.
+    const long long e0 = ebase + t;
+    ChainWalk<COMP> wa(m, e0 < n ? e0 : n - 1);
+    int ci = wa.i(), cj = wa.j;
+    const int sq = TRI_T / wa.w, sr = TRI_T - sq * wa.w;
 #pragma unroll(STEP == 2 ? 4 : 2)
     for (int q = 0; q < TRI_M; ++q) {
         const int el = t + TRI_T * q;
         const long long e = ebase + el;
-        double a1 = 0.0, a2 = 1.0, a3 = 0.0, b = 0.0;
-        if (e < n) {
-            const int i = wa.i(), j = wa.j;
-            wa.advance(TRI_T);
-            if (POR) mom_po::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
-            else mom_np::mom_row<COMP, STEP>(m, i, j, a1, a2, a3, b);
-            if (e == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
-                a1 = 0.0;
-                int i2, j2; double b1, b2, b3, bb;
-                chain_ij<COMP>(m, 1, i2, j2);
-                if (POR) mom_po::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
-                else mom_np::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
-                a3 = a3 * a2 / b2;
-            }
-            if (e == n - 1) a3 = 0.0;
+        const bool live = e < n;
+        if (q > 0) {
+            wa.advance_split(sq, sr);
+            ci = live ? wa.i() : ci; cj = live ? wa.j : cj;
         }
+        double a1, a2, a3, b;
+        if (POR) mom_po::mom_row<COMP, STEP>(m, ci, cj, a1, a2, a3, b);
+        else mom_np::mom_row<COMP, STEP>(m, ci, cj, a1, a2, a3, b);
+        a3 = (e == n - 1) ? 0.0 : a3;
         const int p = MR_PAD(el);
-        s0[p] = a1; s1[p] = a2; s2[p] = a3; s3[p] = b;
+        s0[p] = live ? a1 : 0.0; s1[p] = live ? a2 : 1.0; s2[p] = live ? a3 : 0.0; s3[p] = live ? b : 0.0;
+    }
+    if (ebase == 0 && t == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
+        int i2, j2; double b1, b2, b3, bb;
+        chain_ij<COMP>(m, 1, i2, j2);
+        if (POR) mom_po::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+        else mom_np::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+        s0[0] = 0.0;
+        s2[0] = s2[0] * s1[0] / b2;
     }
     __syncthreads();
     // ---- phase B: chunk mapping
