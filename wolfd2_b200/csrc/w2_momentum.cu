@@ -94,9 +94,19 @@ struct ChainWalk {
 // spikes V/W go to chain-layout arrays only over the prefix/suffix where they are not exactly zero.
 #define MR_PAD(x) ((x) + ((x) >> 3))
 #define MR_LEN (TRI_S + TRI_S / 8)
+// Resident CTAs per SM and unroll depth, swept on B200 after phase A became straight-line code (momentum ms/step at
+// 4096^2, Q=2): MINB/U1/U2 = 5/2/4 5.64, 4/2/4 5.15, 4/2/2 5.11, 4/1/4 5.33, 4/4/4 5.33, 4/2/8 5.71, 3/2/4 5.66, 6/2/4 7.08
+// (80 registers: spills).  128 registers per thread hold more loads in flight than a fifth CTA hides.
 #ifndef MOM_MINB
-#define MOM_MINB (640 / TRI_T)
+#define MOM_MINB (512 / TRI_T)
 #endif
+#ifndef MOM_U1
+#define MOM_U1 2   /* unknowns of the first split step assembled per unrolled loop body */
+#endif
+#ifndef MOM_U2
+#define MOM_U2 2   /* same, second split step */
+#endif
+static constexpr int kMomU1 = MOM_U1, kMomU2 = MOM_U2;   // (#pragma unroll does not expand macros)
 
 template <int COMP, int STEP, bool POR>
 __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     ChainWalk<COMP> wa(m, e0 < n ? e0 : n - 1);
     int ci = wa.i(), cj = wa.j;
     const int sq = TRI_T / wa.w, sr = TRI_T - sq * wa.w;
-#pragma unroll(STEP == 2 ? 4 : 2)
+#pragma unroll(STEP == 2 ? kMomU2 : kMomU1)
     for (int q = 0; q < TRI_M; ++q) {
         const int el = t + TRI_T * q;
         const long long e = ebase + el;
