@@ -279,16 +279,14 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
                                iw = off_q + hw8 + u * PAIRB;
                 const double bb = lds_f64(aB + iq);
                 const double pc = lds_f64(aP + iq);
-                double sum;
-                if (bb != bb) {               // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
-                    sum = 0.0 - pc;
-                } else {
-                    const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
-                    const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
-                    const double a3 = -a4 - a2 - a5 - a1;
-                    sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
-                    sum = w2_div_exact(sum, a3) - pc;
-                }
+                // all ten operands are read before anything is decided: with the loads inside an else-branch the
+                // warp pays two shared-memory round trips per update instead of one
+                const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
+                const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
+                const double a3 = -a4 - a2 - a5 - a1;
+                double sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
+                sum = w2_div_exact(sum, a3) - pc;
+                if (bb != bb) sum = 0.0 - pc;   // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
                 sts_f64(aP + iq, pc + sorrel * sum);
                 if (row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
             }
