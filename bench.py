@@ -356,6 +356,8 @@ def run_gpu(args):
     ctx.close()
     if world > 1:
         api.comm_finalize()
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return

@@ -266,6 +266,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
 // Host (0:mnx,0:mny) <-> device pitched copies of the (0..nx+1, 0..ny+1) window.  In a slab context the
 // host array holds this rank's rows only: host row 0 is global row A0 (wolfd2_b200_slab_layout).
 int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host, cudaStream_t stream) {
+    if (dev == c->met.rau || dev == c->met.rgv) c->sorf_met_valid = 0;   // the fused SOR keeps colour-split copies
     W2_CUDA(cudaMemcpy2DAsync(dev + c->row_off, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
                               (size_t)(c->nx + 2) * 8, (size_t)c->rows, cudaMemcpyHostToDevice,
                               stream ? stream : c->stream));

@@ -483,8 +483,8 @@ static int fused_occupancy(int *per_sm) {
 
 // Runs the whole SOR loop of SorRB on p (Cartesian grids).  b (W2_F_B) must already hold div/dk in the
 // colour-split layout with the NaN sentinel at identity rows.  p is packed into the split layout, iterated
-// between two split buffers, and unpacked at the end; rau and rgv are re-packed on every call (0.1 ms at
-// 4096^2) so that shims which re-upload metrics need no invalidation logic.
+// between two split buffers, and unpacked at the end; the colour-split copies of rau and rgv are kept until
+// something is uploaded into those arrays (w2_upload2d clears sorf_met_valid).
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done) {
     for (int k = 0; k < 4; ++k)
@@ -492,8 +492,11 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     double *pA = c->sorf_buf[0], *pB = c->sorf_buf[1], *rauS = c->sorf_buf[2], *rgvS = c->sorf_buf[3];
     (void)scratch;
     W2_TRY(w2_sorf_pack(c, p, pA, true));
-    W2_TRY(w2_sorf_pack(c, c->met.rau, rauS, true));
-    W2_TRY(w2_sorf_pack(c, c->met.rgv, rgvS, true));
+    if (!c->sorf_met_valid) {   // metric-only: repacked after an upload into rau / rgv (w2_upload2d), not per solve
+        W2_TRY(w2_sorf_pack(c, c->met.rau, rauS, true));
+        W2_TRY(w2_sorf_pack(c, c->met.rgv, rgvS, true));
+        c->sorf_met_valid = 1;
+    }
     const wolfd2_params &par = c->par;
     const int nx = c->nx, ny = c->ny;
     SorFCtl *ctl = (SorFCtl *)c->d_flags;
