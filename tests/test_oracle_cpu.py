@@ -225,6 +225,50 @@ def test_cavity_matches_ghia_at_doubled_reynolds(orc):
     assert err[100.0] > 5e-2
 
 
+@pytest.mark.slow
+def test_poiseuille_channel_converges_to_the_discrete_parabola(orc):
+    """Plane channel 6 x 1, uniform inlet (`inlet 1 1 w normal_vel 1`), `outlet 1 1 e mass_cons`, no-slip walls, Re = 1.
+    Far from both ends the flow is fully developed: convection vanishes (so the doubled convection of DConvU does
+    not matter), v = 0, and the discrete steady x-momentum balance is  (1/Re) d2u/dy2 = dp/dx  with the mirrored
+    wall ghosts u_g = -u_1.  Its exact solution on this staggered grid is
+        u_j = C (y_j (1 - y_j) + h^2/4),  C = 1 / (1/6 + h^2/3)  (unit flux),   Re dp/dx = -2 C.
+    The steady state the REFERENCE SCHEME reaches depends on the time step: the second split step carries no
+    j-coupling, which leaves an O(dt) splitting error (3.1e-3, 1.5e-3, 7.7e-4 for dt = 0.2,
+    0.1, 0.05 Re h^2: ratios 2.00).  Extrapolated to dt = 0 the profile matches the formula to 1.2e-8 and the
+    pressure gradient to 7e-8.  Pins the inlet and mass-conserving outlet fills, the no-slip ghosts, the
+    y-diffusion operator, the PPE / projection scaling and global mass conservation physically."""
+    nx, ny, length, re = 49, 13, 6.0, 1.0
+    x, y = dk.uniform_grid(nx, ny, length, 1.0)
+    h, hx = 1.0 / (ny - 1), length / (nx - 1)
+    yc = (np.arange(ny + 2) - 1.5) * h
+    c = 1.0 / (1.0 / 6.0 + h * h / 3.0)
+    exact = (c * (yc * (1.0 - yc) + h * h / 4.0))[2:ny + 1]
+    i = nx // 2
+    prof, grad = {}, {}
+    for dtf in (0.2, 0.1, 0.05):
+        reg = dk.RegionTables(nx, ny).inlet(1, 1, "w", normal_vel=1.0).outlet(1, 1, "e", fully_dev=False)
+        d = dk._mk("poiseuille", nx, ny, reg, re, dtf * re * h * h, x=x, y=y)
+        d.sorrel, d.sortol, d.msorit, d.qtol = 1.7, 1e-13, 20000, 1e-11
+        u, v, p = d.new_field(), d.new_field(), d.new_field()
+        orc.coldstart(d, u, v, p)
+        for _ in range(200):
+            rc, lg = orc.step(d, u, v, p, 100)
+            assert rc == 0
+            if max(lg[-1]["dif"][1:3]) < 2e-14:
+                break
+        assert abs(u[2:ny + 1, i].sum() * h - 1.0) < 1e-11          # every section carries the inlet flux
+        assert abs(u[2:ny + 1, nx].sum() * h - 1.0) < 1e-11         # ... the outlet face too (mass_cons)
+        assert np.abs(v[1:ny + 1, i]).max() < 1e-7 and np.abs(u[1, i] + u[2, i]) == 0.0
+        prof[dtf] = u[2:ny + 1, i].copy()
+        grad[dtf] = re * (p[ny // 2, i + 1] - p[ny // 2, i]) / hx
+    err = {k: np.abs(prof[k] - exact).max() for k in prof}
+    assert 1.9 < err[0.2] / err[0.1] < 2.1 and 1.9 < err[0.1] / err[0.05] < 2.1     # first order in dt
+    u0 = (prof[0.2] - 6.0 * prof[0.1] + 8.0 * prof[0.05]) / 3.0                     # quadratic extrapolation to dt = 0
+    g0 = (grad[0.2] - 6.0 * grad[0.1] + 8.0 * grad[0.05]) / 3.0
+    assert np.abs(u0 - exact).max() < 1e-7
+    assert abs(g0 + 2.0 * c) < 1e-6
+
+
 # ------------------------------------------------------------------ regression fixtures
 @pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20", "heated_cavity26x22"])
 def test_oracle_reproduces_golden_fixtures(orc, name):
