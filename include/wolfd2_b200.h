@@ -206,6 +206,12 @@ int wolfd2_b200_set_trajectories(wolfd2_ctx *ctx, const wolfd2_traject *tr, cons
                                  const int32_t *nTOutBnd);
 int wolfd2_b200_get_particles(wolfd2_ctx *ctx, double *xp, double *yp, double *up, double *vp, int32_t *nTOutBnd);
 
+/* Node averages of the resident fields for output dumps: VelAvg and PTDAvg (src/utility.f:513-647) as main.f calls
+ * them before SaveStdVarsP3D / SaveTimeSrs (src/main.f:1053-1062), computed on the device; only the averaged arrays
+ * come back, in the host layout (0:mnx,0:mny), zero outside the nodes 1..nx, 1..ny.  set 0: (u, v, p); set 1: the
+ * small-scale fields (uss, vss, pss).  Any output pointer may be NULL.  One GPU only. */
+int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double *vbar, double *pav);
+
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
 int wolfd2_b200_download_field(wolfd2_ctx *ctx, int32_t which, double *host);

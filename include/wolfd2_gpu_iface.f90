@@ -174,6 +174,14 @@ module wolfd2_gpu
       integer(c_int32_t), intent(out) :: nTOutBnd(*)
     end function
 
+    ! VelAvg / PTDAvg of the resident fields (set 0: u,v,p; set 1: uss,vss,pss) for output dumps, main.f:1053-1062
+    integer(c_int) function wolfd2_b200_node_averages(ctx, set, util, vbar, pav) bind(C, name='wolfd2_b200_node_averages')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: set
+      real(c_double), intent(out) :: util(*), vbar(*), pav(*)
+    end function
+
     ! several GPUs (one process each): slab layout, NCCL communicator, slab context
     integer(c_int) function wolfd2_b200_slab_layout(nx, ny, world, rank, lay) bind(C, name='wolfd2_b200_slab_layout')
       import :: c_int, c_int32_t

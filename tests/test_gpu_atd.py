@@ -110,6 +110,45 @@ def test_node_averages_bitwise(api, orc, d):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("k", [0, 3])
+def test_resident_node_averages_and_plot3d_dump(api, orc, k, tmp_path):
+    """Output dump without moving the staggered fields: steps on the device, VelAvg / PTDAvg on the device
+    (wolfd2_b200_node_averages), `.qqq` file in the reference's layout, and the run continues unperturbed."""
+    from wolfd2_b200 import plot3d
+    d = make_test_decks()[k]
+    d.msorit = 200
+    _cfg(api, orc, d)
+    r = d.regions
+    uo, vo, po = d.new_field(), d.new_field(), d.new_field()
+    orc.coldstart(d, uo, vo, po)
+    orc.step(d, uo, vo, po, 3)
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        ctx.coldstart()
+        ctx.step(3)
+        ug, vg, pg = ctx.download(api.F_U), ctx.download(api.F_V), ctx.download(api.F_P)
+        util, vbar, pav = ctx.node_averages()
+        # the averages are those of the reference routines applied to the device's own fields, bit for bit
+        ref = [d.new_field() for _ in range(3)]
+        orc.velavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, ug, vg, ref[0], ref[1])
+        orc.ptdavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, pg, ref[2])
+        for a, b in zip((util, vbar, pav), ref):
+            assert np.array_equal(a, b)
+        pre = str(tmp_path / "snap")
+        assert plot3d.save_std_vars_p3d(pre, d.nx, d.ny, util, vbar, pav, grid=d.node_arrays()) == 4
+        nx, ny, planes = plot3d.read_std_vars_p3d(pre + ".qqq")
+        W = (slice(1, d.ny + 1), slice(1, d.nx + 1))
+        assert np.array_equal(planes[0], ref[2][W]) and np.array_equal(planes[1], ref[0][W])
+        # the dump used scratch arrays only: the next steps match the oracle as if nothing had happened
+        lg = ctx.step(2)
+        rc, lo = orc.step(d, uo, vo, po, 2)
+        assert [g["nSorConv"] for g in lg] == [o_["nSorConv"] for o_ in lo]
+        for w, a in ((api.F_U, uo), (api.F_V, vo), (api.F_P, po)):
+            assert rel_l2(ctx.download(w), a) <= 1e-10
+
+
 # ------------------------------------------------------------------------------------------ SmallScale
 def _ss_args(d, initflg):
     r, m = d.regions, d.metrics

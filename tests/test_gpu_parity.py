@@ -206,6 +206,40 @@ def test_time_steps(api, orc, k):
     print(f"{d.name}: worst rel-L2 over 8 steps = {worst:.2e}")
 
 
+RAGGED = [(6, 6), (7, 131), (131, 7), (1025, 9), (9, 1030), (129, 33), (2049, 6)]
+
+
+@pytest.mark.parametrize("size", RAGGED, ids=[f"{a}x{b}" for a, b in RAGGED])
+@pytest.mark.parametrize("kind", ["cavity", "channel_mc"])
+def test_ragged_and_minimal_grids(api, orc, size, kind):
+    """Smallest legal grid (6x6, CheckGridSize), one-cell-wide extremes and row lengths around the solver's
+    thread-block stride (128) and segment size (1024): chain segments then cover many grid rows or straddle
+    them at every offset, the chain walker takes its multi-row stride, the last segment is mostly padding."""
+    from wolfd2_b200 import deck as dk
+    nx, ny = size
+    h = 1.0 / (max(nx, ny) - 1)
+    if kind == "cavity":
+        d = dk.cavity(nx, re=100.0, dt=min(0.01, 20.0 * h * h), ny=ny)
+    else:
+        d = dk.channel(nx, re=100.0, dt=min(0.01, 20.0 * h * h), ny=ny, fully_dev=False)
+    d.msorit = 60
+    orc.config(d.mnx, d.mny)
+    uo, vo, po = d.new_field(), d.new_field(), d.new_field()
+    nso = orc.coldstart(d, uo, vo, po)
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P):
+            ctx.upload(w, z)
+        assert ctx.coldstart() == nso
+        for step in range(3):
+            lg = ctx.step(1)[0]
+            rc, lo = orc.step(d, uo, vo, po, 1)
+            assert rc == 0
+            assert lg["nQLiter"] == lo[0]["nQLiter"] and lg["nSorConv"] == lo[0]["nSorConv"]
+            for w, ref in ((api.F_U, uo), (api.F_V, vo), (api.F_P, po)):
+                assert rel_l2(ctx.download(w), ref) <= TOL_STEP, (size, kind, step, w)
+
+
 def test_step_host_equals_resident(api):
     """The host-buffer entry point (e2e path) gives the same fields as the resident one."""
     from wolfd2_b200 import deck as dk

@@ -511,6 +511,34 @@ extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int
     return nql;
 }
 
+// Node averages of the resident fields for output dumps (src/main.f:1053-1062, :1300-1330: VelAvg and PTDAvg before
+// SaveStdVarsP3D / SaveTimeSrs): computed on the device into scratch arrays, only the three averaged arrays cross
+// the bus.  set 0: (u, v, p) -> (util, vbar, pav); set 1: the small-scale fields (uss, vss, pss).  Cells outside the
+// node range 1..nx, 1..ny come back as zero.  TAveraged (temperature) stays on the host.
+extern "C" int wolfd2_b200_node_averages(wolfd2_ctx *c, int32_t set, double *util, double *vbar, double *pav) {
+    if (!c || set < 0 || set > 1) return W2_ERR_BAD_ARG;
+    if (c->world > 1) { w2_set_error("node averages are not supported on a row slab"); return W2_ERR_UNSUPPORTED; }
+    const double *u = c->fld[set ? W2_F_USS : W2_F_U], *v = c->fld[set ? W2_F_VSS : W2_F_V], *p = c->fld[set ? W2_F_PSS : W2_F_P];
+    if (!u || !v || !p) { w2_set_error("the small-scale fields do not exist in this context"); return W2_ERR_BAD_ARG; }
+    W2_CUDA(cudaSetDevice(c->device));
+    double *a = c->x1, *b = c->div, *q = c->fld[W2_F_B];   // scratch: rebuilt by their producers before every use
+    const size_t bytes = c->nelem * sizeof(double);
+    if (util || vbar) {
+        W2_CUDA(cudaMemsetAsync(a, 0, bytes, c->stream));
+        W2_CUDA(cudaMemsetAsync(b, 0, bytes, c->stream));
+        W2_TRY(w2_velavg(c, u, v, a, b));
+        if (util) W2_TRY(w2_download2d(c, util, a));
+        if (vbar) W2_TRY(w2_download2d(c, vbar, b));
+    }
+    if (pav) {
+        W2_CUDA(cudaMemsetAsync(q, 0, bytes, c->stream));
+        W2_TRY(w2_ptdavg(c, p, q));
+        W2_TRY(w2_download2d(c, pav, q));
+    }
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    return W2_OK;
+}
+
 // ---- unit-parity shims of the routines below XMomentum / YMomentum / Ppe in the reference's call tree
 // ("internal but worth exporting").  Output arrays are in/out as in the reference: cells
 // outside the loop ranges keep the caller's values.
