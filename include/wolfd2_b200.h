@@ -209,8 +209,9 @@ int wolfd2_b200_get_particles(wolfd2_ctx *ctx, double *xp, double *yp, double *u
 /* Node averages of the resident fields for output dumps: VelAvg and PTDAvg (src/utility.f:513-647) as main.f calls
  * them before SaveStdVarsP3D / SaveTimeSrs (src/main.f:1053-1062), computed on the device; only the averaged arrays
  * come back, in the host layout (0:mnx,0:mny), zero outside the nodes 1..nx, 1..ny.  set 0: (u, v, p); set 1: the
- * small-scale fields (uss, vss, pss).  Any output pointer may be NULL.  One GPU only. */
-int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double *vbar, double *pav);
+ * small-scale fields (uss, vss, pss).  tav: TAveraged (src/utility.f:668-740) of t (set 0) or tss (set 1, nScale = 1);
+ * it needs the thermal region tables (wolfd2_b200_set_thermal).  Any output pointer may be NULL.  One GPU only. */
+int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double *vbar, double *pav, double *tav);
 
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
@@ -413,6 +414,9 @@ void smlsclbc_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const 
 /* src/utility.f:512, 574 */
 void ptdavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
     const int32_t *nRegType, const double *p, double *pav);
+/* src/utility.f:668-671 */
+void taveraged_(const int32_t *nx, const int32_t *ny, const int32_t *nScale, const int32_t *nReg,
+    const int32_t *nRegBrd, const int32_t *nTRgType, const double *dTRgVal, const double *t, double *tav);
 void velavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,
     const int32_t *nRegType, const double *u, const double *v, double *util, double *vbar);
 /* src/traject.f:154-164.  HeunTrap's step is the sub-step size (the reference passes the INTEGER sub-step counter

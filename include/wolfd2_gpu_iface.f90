@@ -175,11 +175,12 @@ module wolfd2_gpu
     end function
 
     ! VelAvg / PTDAvg of the resident fields (set 0: u,v,p; set 1: uss,vss,pss) for output dumps, main.f:1053-1062
-    integer(c_int) function wolfd2_b200_node_averages(ctx, set, util, vbar, pav) bind(C, name='wolfd2_b200_node_averages')
+    integer(c_int) function wolfd2_b200_node_averages(ctx, set, util, vbar, pav, tav) &
+        bind(C, name='wolfd2_b200_node_averages')
       import :: c_int, c_int32_t, c_ptr, c_double
       type(c_ptr), value :: ctx
       integer(c_int32_t), value :: set
-      real(c_double), intent(out) :: util(*), vbar(*), pav(*)
+      real(c_double), intent(out) :: util(*), vbar(*), pav(*), tav(*)   ! TAveraged of t / tss in tav
     end function
 
     ! several GPUs (one process each): slab layout, NCCL communicator, slab context

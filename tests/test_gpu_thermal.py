@@ -139,6 +139,42 @@ def test_thermal_time_steps(api, orc, d):
     print(f"{d.name}: worst rel-L2 over 6 steps = {worst:.2e}")
 
 
+@pytest.mark.parametrize("d", DECKS, ids=IDS)
+def test_taveraged_bitwise_and_resident_dump(api, orc, d, tmp_path):
+    """TAveraged (utility.f:668-740) through the shim, both scales, sentinel values outside the loops; then the
+    resident variant after a few thermal steps and the 5-variable `.qqq` dump."""
+    from wolfd2_b200 import plot3d
+    _cfg(api, orc, d)
+    rng = np.random.default_rng(11)
+    r = d.regions
+    t = rand_field(d, rng)
+    for nscale in (0, 1):
+        s = rand_field(d, rng)
+        g, o = s.copy(), s.copy()
+        api.TAveraged(d.nx, d.ny, nscale, r.nReg, r.nRegBrd, r.nTRgType, r.dTRgVal, t, g)
+        orc.taveraged(d.nx, d.ny, nscale, r.nReg, r.nRegBrd, r.nTRgType, r.dTRgVal, t, o)
+        assert np.array_equal(g, o) and not np.array_equal(g, s)
+    d.msorit = 200
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P, api.F_D):
+            ctx.upload(w, z)
+        t0 = d.new_field()
+        t0[:d.ny + 2, :d.nx + 2] = 0.5
+        ctx.upload(api.F_T, t0)
+        ctx.coldstart()
+        ctx.step(2)
+        tg = ctx.download(api.F_T)
+        util, vbar, pav, tav = ctx.node_averages(temperature=True)
+        ref = d.new_field()
+        orc.taveraged(d.nx, d.ny, 0, r.nReg, r.nRegBrd, r.nTRgType, r.dTRgVal, tg, ref)
+        assert np.array_equal(tav, ref)
+        pre = str(tmp_path / "hot")
+        assert plot3d.save_std_vars_p3d(pre, d.nx, d.ny, util, vbar, pav, t=tav) == 5
+        _, _, pl = plot3d.read_std_vars_p3d(pre + ".qqq")
+        assert np.array_equal(pl[4], ref[1:d.ny + 1, 1:d.nx + 1])
+
+
 def test_thermal_off_is_the_cold_path(api, orc):
     """A context whose thermal switch was set and cleared again steps exactly like a cold one."""
     from wolfd2_b200 import deck as dk

@@ -66,6 +66,8 @@ SIGNATURES = {
     # src/utility.f:512, 574
     "ptdavg_": (None, "ii" "III" "DD"),
     "velavg_": (None, "ii" "III" "DDDD"),
+    # src/utility.f:668-671
+    "taveraged_": (None, "iii" "II" "I" "D" "DD"),
     # src/traject.f:154-164
     "traject_": (None, "ii" "ii" "iii" "I" "ddddd" "DDD" "DD" "DDDD" "DD" "DDDD"),
 }

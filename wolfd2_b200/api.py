@@ -62,7 +62,7 @@ def lib():
     L.wolfd2_b200_smallscale_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_f64p, C.c_int32]
     L.wolfd2_b200_set_trajectories.argtypes = [C.c_void_p, C.POINTER(Traject)] + [c_f64p] * 9 + [c_i32p]
     L.wolfd2_b200_get_particles.argtypes = [C.c_void_p] + [c_f64p] * 4 + [c_i32p]
-    L.wolfd2_b200_node_averages.argtypes = [C.c_void_p, C.c_int32] + [c_f64p] * 3
+    L.wolfd2_b200_node_averages.argtypes = [C.c_void_p, C.c_int32] + [c_f64p] * 4
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_coldstart.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -125,6 +125,7 @@ SmallScale_ = _routine("smallscale")     # `SmallScale` is the parameter block (
 SmlSclBC = _routine("smlsclbc")
 PTDAvg = _routine("ptdavg")
 VelAvg = _routine("velavg")
+TAveraged = _routine("taveraged")
 Traject_ = _routine("traject")           # `Traject` is the parameter block
 DiffMaxNorm = _routine("diffmaxnorm")
 DMaxNorm = _routine("dmaxnorm")
@@ -216,11 +217,12 @@ class Context:
                                                out.ctypes.data_as(c_i32p)), "wolfd2_b200_get_particles")
         return xp, yp, up, vp, out
 
-    def node_averages(self, small_scale=False):
-        """(util, vbar, pav): VelAvg / PTDAvg of the resident fields, computed on the device (output dumps)."""
-        out = [self.deck.new_field() for _ in range(3)]
-        _check(lib().wolfd2_b200_node_averages(self._h, 1 if small_scale else 0, *[q.ctypes.data_as(c_f64p) for q in out]),
-               "wolfd2_b200_node_averages")
+    def node_averages(self, small_scale=False, temperature=False):
+        """(util, vbar, pav[, tav]): VelAvg / PTDAvg / TAveraged of the resident fields, computed on the device
+        (output dumps)."""
+        out = [self.deck.new_field() for _ in range(4 if temperature else 3)]
+        ptr = [q.ctypes.data_as(c_f64p) for q in out] + ([] if temperature else [None])
+        _check(lib().wolfd2_b200_node_averages(self._h, 1 if small_scale else 0, *ptr), "wolfd2_b200_node_averages")
         return tuple(out)
 
     def upload(self, which, arr):

@@ -514,8 +514,8 @@ extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int
 // Node averages of the resident fields for output dumps (src/main.f:1053-1062, :1300-1330: VelAvg and PTDAvg before
 // SaveStdVarsP3D / SaveTimeSrs): computed on the device into scratch arrays, only the three averaged arrays cross
 // the bus.  set 0: (u, v, p) -> (util, vbar, pav); set 1: the small-scale fields (uss, vss, pss).  Cells outside the
-// node range 1..nx, 1..ny come back as zero.  TAveraged (temperature) stays on the host.
-extern "C" int wolfd2_b200_node_averages(wolfd2_ctx *c, int32_t set, double *util, double *vbar, double *pav) {
+// node range 1..nx, 1..ny come back as zero.  tav: TAveraged of t (set 0) or tss (set 1).
+extern "C" int wolfd2_b200_node_averages(wolfd2_ctx *c, int32_t set, double *util, double *vbar, double *pav, double *tav) {
     if (!c || set < 0 || set > 1) return W2_ERR_BAD_ARG;
     if (c->world > 1) { w2_set_error("node averages are not supported on a row slab"); return W2_ERR_UNSUPPORTED; }
     const double *u = c->fld[set ? W2_F_USS : W2_F_U], *v = c->fld[set ? W2_F_VSS : W2_F_V], *p = c->fld[set ? W2_F_PSS : W2_F_P];
@@ -534,6 +534,13 @@ extern "C" int wolfd2_b200_node_averages(wolfd2_ctx *c, int32_t set, double *uti
         W2_CUDA(cudaMemsetAsync(q, 0, bytes, c->stream));
         W2_TRY(w2_ptdavg(c, p, q));
         W2_TRY(w2_download2d(c, pav, q));
+    }
+    if (tav) {   // TAveraged with nScale = set (src/main.f:1057-1066); needs the thermal region tables
+        const double *t = c->fld[set ? W2_F_TSS : W2_F_T];
+        if (!t || !c->th_tables) { w2_set_error("node average of t: no thermal tables (wolfd2_b200_set_thermal) or no such field"); return W2_ERR_BAD_ARG; }
+        W2_CUDA(cudaMemsetAsync(a, 0, bytes, c->stream));
+        W2_TRY(w2_taveraged(c, set, t, a));
+        W2_TRY(w2_download2d(c, tav, a));
     }
     W2_CUDA(cudaStreamSynchronize(c->stream));
     return W2_OK;
@@ -685,6 +692,17 @@ extern "C" void ptdavg_(const int32_t *nx, const int32_t *ny, const int32_t *nRe
     up(c, c->fld[W2_F_P], p, who); up(c, c->fld[W2_F_PN], pav, who);
     SHIM_TRY(w2_ptdavg(c, c->fld[W2_F_P], c->fld[W2_F_PN]), who);
     down(c, pav, c->fld[W2_F_PN], who);
+    sync(c, who);
+}
+extern "C" void taveraged_(const int32_t *nx, const int32_t *ny, const int32_t *nScale, const int32_t *nReg,
+                           const int32_t *nRegBrd, const int32_t *nTRgType, const double *dTRgVal, const double *t, double *tav) {
+    const char *who = "taveraged_";
+    wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    shim_regions(c, nReg, nRegBrd, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, who);
+    SHIM_TRY(w2_set_thermal_tables(c, nTRgType, nullptr, dTRgVal, nullptr), who);
+    up(c, c->fld[W2_F_T], t, who); up(c, c->fld[W2_F_TN], tav, who);
+    SHIM_TRY(w2_taveraged(c, *nScale, c->fld[W2_F_T], c->fld[W2_F_TN]), who);
+    down(c, tav, c->fld[W2_F_TN], who);
     sync(c, who);
 }
 extern "C" void velavg_(const int32_t *nx, const int32_t *ny, const int32_t *nReg, const int32_t *nRegBrd,

@@ -59,6 +59,28 @@ __global__ void __launch_bounds__(256) ptdavg_kernel(const W2Regions *__restrict
         }
     }
 }
+// TAveraged (src/utility.f:668-740): RT_TEMPER regions take dTRgVal (nScale 0) or zero (small scales)
+__global__ void __launch_bounds__(256) taveraged_kernel(const W2Regions *__restrict__ R, const W2Thermal *__restrict__ H, int nscale,
+                                                        int nx, int ny, int pitch, const double *__restrict__ t,
+                                                        double *__restrict__ tav) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nx + 1) return;
+    for (int j = blockIdx.y; j <= ny + 1; j += gridDim.y) {
+        int hit = -1;
+        for (int q = 0; q < R->nreg; ++q)
+            if (i >= R->iW[q] && i <= R->iE[q] && j >= R->jS[q] && j <= R->jN[q]) hit = q;
+        if (hit < 0) continue;
+        if (H->ttype[hit] == W2_RT_TEMPER) tav[IDX(i, j)] = nscale == 0 ? H->trgval[hit] : 0.0;
+        else tav[IDX(i, j)] = (t[IDX(i, j)] + t[IDX(i, j + 1)] + t[IDX(i + 1, j + 1)] + t[IDX(i + 1, j)]) / 4.0;
+    }
+}
+int w2_taveraged(wolfd2_ctx *c, int nscale, const double *t, double *tav) {
+    dim3 g((c->nx + 2 + 255) / 256, c->ny + 2 < 2048 ? c->ny + 2 : 2048);
+    taveraged_kernel<<<g, 256, 0, c->stream>>>(c->dreg, c->dth, nscale, c->nx, c->ny, c->pitch, t, tav);
+    c->launches[3]++;
+    W2_CUDA(cudaGetLastError());
+    return W2_OK;
+}
 int w2_velavg(wolfd2_ctx *c, const double *u, const double *v, double *util, double *vbar) {
     dim3 g((c->nx + 2 + 255) / 256, c->ny + 2 < 2048 ? c->ny + 2 : 2048);
     velavg_kernel<<<g, 256, 0, c->stream>>>(c->dreg, c->nx, c->ny, c->pitch, u, v, util, vbar);
