@@ -40,6 +40,27 @@ def test_signature_table_matches_header():
         assert len([a for a in m.group(1).split(",") if a.strip()]) == len(kinds), name
 
 
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: the header compiles on its own as C99 and as C++17, warnings as errors, and a
+    C program can link the library with nothing but the header (no torch, no CUDA headers)."""
+    import subprocess
+    from wolfd2_b200 import build
+    lib = build.build()
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "wolfd2_b200.h"\n'
+                   'int main(void) { printf("%s %d\\n", wolfd2_b200_version(), wolfd2_b200_config(302, 302, 20, 10)); return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    cxx = tmp_path / "use.cpp"
+    cxx.write_text(src.read_text())
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(cxx)])
+    exe = tmp_path / "use"
+    d = os.path.dirname(lib)
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, "-o", str(exe), str(src), "-L" + d, "-lwolfd2_b200", "-Wl,-rpath," + d])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.split()[-1] == "0", (out.stdout, out.stderr)   # config needs no device
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
