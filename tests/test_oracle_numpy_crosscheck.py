@@ -1,0 +1,503 @@
+"""A SECOND, independent restatement of the streaming operators, vectorised in numpy straight from the Fortran text,
+cross-checked against the C oracle.  The reference ships no vectors and cannot be compiled here ("parity unpinned",
+DESIGN.md 1c); two restatements written separately (C loops, statement by statement; numpy slices, loop nest by loop
+nest) that agree bit for bit make a transcription slip in either one visible.  Arrays are f[j, i] (row-major
+(0:mny, 0:mnx)); `W(f, di, dj)` is the operand f(i+di, j+dj) over the loop range."""
+import numpy as np
+import pytest
+
+from oracle import get_oracle
+from util import make_test_decks, rand_field
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return get_oracle()
+
+
+def _deck(k=0, nx=37, ny=29):
+    d = make_test_decks(nx, ny)[k]
+    return d
+
+
+class Rng:
+    """f(i+di, j+dj) for i in i0..i1, j in j0..j1 (inclusive, Fortran indices)."""
+    def __init__(self, i0, i1, j0, j1):
+        self.i0, self.i1, self.j0, self.j1 = i0, i1, j0, j1
+
+    def __call__(self, f, di=0, dj=0):
+        return f[self.j0 + dj:self.j1 + dj + 1, self.i0 + di:self.i1 + di + 1]
+
+    def put(self, f, val):
+        f[self.j0:self.j1 + 1, self.i0:self.i1 + 1] = val
+
+
+def np_convcoef(nx, ny, ncomp, njacob, xzi, xet, yzi, yet, u, v, cc1, cc2):
+    """src/momentum.f:895-972."""
+    djac = 2.0 if njacob == 1 else 1.0
+    big, small = Rng(1, nx + 1, 1, ny + 1), Rng(1, nx, 1, ny)
+    if ncomp == 1:
+        W = big
+        W.put(cc1, (djac * W(yet) * (W(u) + W(u, -1, 0)) - W(xet) * (W(v) + W(v, 0, -1))) * 0.5)
+        W = small
+        W.put(cc2, (W(xzi) * (W(v, 1, 0) + W(v)) - djac * W(yzi) * (W(u, 0, 1) + W(u))) * 0.5)
+    elif ncomp == 2:
+        W = small
+        W.put(cc1, (W(yet) * (W(u, 0, 1) + W(u)) - djac * W(xet) * (W(v, 1, 0) + W(v))) * 0.5)
+        W = big
+        W.put(cc2, (djac * W(xzi) * (W(v) + W(v, 0, -1)) - W(yzi) * (W(u) + W(u, -1, 0))) * 0.5)
+    elif ncomp == 3:
+        W = small
+        W.put(cc1, (W(yet) * W(u) - W(xet) * (W(v, 1, 0) + W(v) + W(v, 1, -1) + W(v, 0, -1)) / 4.0) * 0.5)
+        W.put(cc2, (W(xzi) * W(v) - W(yzi) * (W(u, 0, 1) + W(u, -1, 1) + W(u) + W(u, -1, 0)) / 4.0) * 0.5)
+    elif ncomp == 4:
+        W = Rng(0, nx, 1, ny)
+        s4 = W(v, 1, 0) + W(v) + W(v, 1, -1) + W(v, 0, -1)
+        W.put(cc1, djac * W(yet) * W(u) - W(xet) * s4 / 4.0)
+        W.put(cc2, W(xzi) * s4 / 4.0 - djac * W(yzi) * W(u))
+    elif ncomp == 5:
+        W = Rng(1, nx, 0, ny)
+        s4 = W(u, 0, 1) + W(u, -1, 1) + W(u) + W(u, -1, 0)
+        W.put(cc1, W(yet) * s4 / 4.0 - djac * W(xet) * W(v))
+        W.put(cc2, djac * W(xzi) * W(v) - W(yzi) * s4 / 4.0)
+    elif ncomp == 6:
+        W = big
+        W.put(cc1, (W(yet) * (W(u) + W(u, -1, 0)) - W(xet) * (W(v) + W(v, 0, -1))) * 0.5)
+        W.put(cc2, (W(xzi) * (W(v) + W(v, 0, -1)) - W(yzi) * (W(u) + W(u, -1, 0))) * 0.5)
+
+
+def np_dconvu(nx, ny, c1, c2, u, c):
+    """src/momentum.f:1000-1006."""
+    W = Rng(1, nx, 2, ny)
+    W.put(c, -W(c2, 0, -1) * W(u, 0, -1) - W(c1) * W(u, -1, 0)
+          + (W(c1, 1, 0) - W(c1) + W(c2) - W(c2, 0, -1)) * W(u)
+          + W(c1, 1, 0) * W(u, 1, 0) + W(c2) * W(u, 0, 1))
+
+
+def np_dconvv(nx, ny, c1, c2, v, c):
+    """src/momentum.f:1064-1070."""
+    W = Rng(2, nx, 1, ny)
+    W.put(c, -W(c2) * W(v, 0, -1) - W(c1, -1, 0) * W(v, -1, 0)
+          + (W(c1) - W(c1, -1, 0) + W(c2, 0, 1) - W(c2)) * W(v)
+          + W(c1) * W(v, 1, 0) + W(c2, 0, 1) * W(v, 0, 1))
+
+
+def np_ddiffu(nx, ny, ac, bc, bn, gn, u, d):
+    """src/momentum.f:1028-1042."""
+    W = Rng(1, nx, 2, ny)
+    s1 = (W(ac, 1, 0) * (W(u, 1, 0) - W(u)) - W(ac) * (W(u) - W(u, -1, 0))
+          + W(bc, 1, 0) * (W(u, 1, 1) + W(u, 0, 1) - W(u, 1, -1) - W(u, 0, -1))
+          - W(bc) * (W(u, 0, 1) + W(u, -1, 1) - W(u, 0, -1) - W(u, -1, -1)))
+    s2 = (W(bn) * (W(u, 1, 1) + W(u, 1, 0) - W(u, -1, 1) - W(u, -1, 0))
+          - W(bn, 0, -1) * (W(u, 1, 0) + W(u, 1, -1) - W(u, -1, 0) - W(u, -1, -1))
+          + W(gn) * (W(u, 0, 1) - W(u)) - W(gn, 0, -1) * (W(u) - W(u, 0, -1)))
+    W.put(d, s1 + s2)
+
+
+def np_ddiffv(nx, ny, an, bc, bn, gc, v, d):
+    """src/momentum.f:1092-1106."""
+    W = Rng(2, nx, 1, ny)
+    s1 = (W(an) * (W(v, 1, 0) - W(v)) - W(an, -1, 0) * (W(v) - W(v, -1, 0))
+          + W(bn) * (W(v, 1, 1) + W(v, 0, 1) - W(v, 1, -1) - W(v, 0, -1))
+          - W(bn, -1, 0) * (W(v, 0, 1) + W(v, -1, 1) - W(v, 0, -1) - W(v, -1, -1)))
+    s2 = (W(bc, 0, 1) * (W(v, 1, 1) + W(v, 1, 0) - W(v, -1, 1) - W(v, -1, 0))
+          - W(bc) * (W(v, 1, 0) + W(v, 1, -1) - W(v, -1, 0) - W(v, -1, -1))
+          + W(gc, 0, 1) * (W(v, 0, 1) - W(v)) - W(gc) * (W(v) - W(v, 0, -1)))
+    W.put(d, s1 + s2)
+
+
+def np_divergence(nx, ny, nloc, xet, yet, xzi, yzi, u, v, div):
+    """src/pressure.f:284-315."""
+    W = Rng(1, nx, 1, ny)
+    if nloc == 1:
+        ucij = W(yet) * W(u) - W(xet) * (W(v, 1, 0) + W(v) + W(v, 1, -1) + W(v, 0, -1)) / 4.0
+        uci1j = W(yet, -1, 0) * W(u, -1, 0) - W(xet, -1, 0) * (W(v) + W(v, -1, 0) + W(v, 0, -1) + W(v, -1, -1)) / 4.0
+        vcij = W(xzi) * W(v) - W(yzi) * (W(u, 0, 1) + W(u, -1, 1) + W(u) + W(u, -1, 0)) / 4.0
+        vcij1 = W(xzi, 0, -1) * W(v, 0, -1) - W(yzi, 0, -1) * (W(u) + W(u, -1, 0) + W(u, 0, -1) + W(u, -1, -1)) / 4.0
+        W.put(div, ucij - uci1j + vcij - vcij1)
+    else:
+        uci1j = W(yet, 1, 0) * (W(u, 0, 1) + W(u, 1, 1) + W(u) + W(u, 1, 0)) / 4.0 - W(xet, 1, 0) * W(v, 1, 0)
+        ucij = W(yet) * (W(u, -1, 1) + W(u, 0, 1) + W(u, -1, 0) + W(u)) / 4.0 - W(xet) * W(v)
+        vcij1 = W(xzi, 0, 1) * (W(v, 0, 1) + W(v, 1, 1) + W(v) + W(v, 1, 0)) / 4.0 - W(yzi, 0, 1) * W(u, 0, 1)
+        vcij = W(xzi) * (W(v) + W(v, 1, 0) + W(v, 0, -1) + W(v, 1, -1)) / 4.0 - W(yzi) * W(u)
+        W.put(div, uci1j - ucij + vcij1 - vcij)
+
+
+def np_rhsppe(nx, ny, cartes, dk, rbu, rbv, div, p, b):
+    """src/pressure.f:347-375; b is the vector b(ind), ind = (j-2)*(nx-1)+i-1."""
+    W = Rng(2, nx, 2, ny)
+    bb = W(div) / dk
+    if not cartes:
+        bb = bb - (W(rbu) * (W(p, 1, 1) + W(p, 0, 1) - W(p, 1, -1) - W(p, 0, -1))
+                   - W(rbu, -1, 0) * (W(p, 0, 1) + W(p, -1, 1) - W(p, 0, -1) - W(p, -1, -1))
+                   + W(rbv) * (W(p, 1, 1) + W(p, 1, 0) - W(p, -1, 1) - W(p, -1, 0))
+                   - W(rbv, 0, -1) * (W(p, 1, 0) + W(p, 1, -1) - W(p, -1, 0) - W(p, -1, -1)))
+    b[:(nx - 1) * (ny - 1)] = bb.ravel()
+
+
+def np_sorrb_iteration(nx, ny, sorrel, rau, rgv, b, p):
+    """One iteration of SorRB on a one-region grid without blockage: matrix of src/pressure.f:97-106, colour
+    sweeps :505-531 (black: i starts at 2+mod(j,2)); each colour is a vector update because a colour's points
+    only read the other colour.  Returns dif = max |sum|."""
+    W = Rng(2, nx, 2, ny)
+    a1, a2, a4, a5 = W(rgv, 0, -1), W(rau, -1, 0), W(rau), W(rgv)
+    a3 = -W(rau) - W(rau, -1, 0) - W(rgv) - W(rgv, 0, -1)
+    bb = b[:(nx - 1) * (ny - 1)].reshape(ny - 1, nx - 1)
+    jj, ii = np.meshgrid(np.arange(2, ny + 1), np.arange(2, nx + 1), indexing="ij")
+    dif = 0.0
+    for colour in (0, 1):          # black: (i - 2 - mod(j,2)) even  <=>  (i + j) even
+        mask = ((ii + jj) % 2) == colour
+        s = bb - a1 * W(p, 0, -1) - a2 * W(p, -1, 0) - a4 * W(p, 1, 0) - a5 * W(p, 0, 1)
+        s = s / a3 - W(p)
+        new = W(p) + sorrel * s
+        W(p)[mask] = new[mask]
+        dif = max(dif, np.abs(s[mask]).max())
+    return dif
+
+
+SIZES = [(37, 29), (64, 64)]
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_convcoef_all_cases(orc, size):
+    d = _deck(0, *size)
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(1)
+    ms = [rand_field(d, rng) for _ in range(4)]
+    u, v = rand_field(d, rng), rand_field(d, rng)
+    for ncomp in range(1, 7):
+        for njacob in (0, 1):
+            s1, s2 = rand_field(d, rng), rand_field(d, rng)
+            a, b, c, e = s1.copy(), s2.copy(), s1.copy(), s2.copy()
+            np_convcoef(d.nx, d.ny, ncomp, njacob, *ms, u, v, a, b)
+            orc.convcoef(d.nx, d.ny, ncomp, njacob, *ms, u, v, c, e)
+            assert np.array_equal(a, c) and np.array_equal(b, e), (ncomp, njacob)
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_conv_diff_divergence_rhs(orc, size):
+    d = _deck(0, *size)
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(2)
+    f = [rand_field(d, rng) for _ in range(8)]
+    for mine, theirs, nargs in ((np_dconvu, orc.dconvu, 3), (np_dconvv, orc.dconvv, 3), (np_ddiffu, orc.ddiffu, 5),
+                                (np_ddiffv, orc.ddiffv, 5)):
+        s = rand_field(d, rng)
+        a, b = s.copy(), s.copy()
+        mine(d.nx, d.ny, *f[:nargs], a)
+        theirs(d.nx, d.ny, *f[:nargs], b)
+        assert np.array_equal(a, b), mine.__name__
+    for nloc in (1, 2):
+        s = rand_field(d, rng)
+        a, b = s.copy(), s.copy()
+        np_divergence(d.nx, d.ny, nloc, *f[:6], a)
+        orc.divergence(d.nx, d.ny, nloc, *f[:6], b)
+        assert np.array_equal(a, b), nloc
+    for cartes in (1, 0):
+        a = rng.uniform(-1, 1, d.mnx * d.mny)
+        b = a.copy()
+        np_rhsppe(d.nx, d.ny, cartes, d.dk, f[0], f[1], f[2], f[3], a)
+        orc.rhsppe(d.nx, d.ny, cartes, d.dk, f[0], f[1], f[2], f[3], b)
+        assert np.array_equal(a, b), cartes
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_one_red_black_sor_iteration_through_ppe(orc, size):
+    """Ppe with max_sor_iter = 1 on the cavity deck == Divergence + RhsPpe + one SorRB iteration, restated in numpy."""
+    d = _deck(0, *size)
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(3)
+    m, r = d.metrics, d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    po = p.copy()
+    nconv = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 5, 1, d.dk, 0.0, 1.7, m["rau"], m["rbu"], m["rbv"],
+                    m["rgv"], m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, po)
+    div = d.new_field()
+    np_divergence(d.nx, d.ny, 1, m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, div)
+    b = np.zeros(d.mnx * d.mny)
+    np_rhsppe(d.nx, d.ny, 1, d.dk, m["rbu"], m["rbv"], div, p, b)
+    pn = p.copy()
+    np_sorrb_iteration(d.nx, d.ny, 1.7, m["rau"], m["rgv"], b, pn)
+    assert nconv == 1 and np.array_equal(pn, po)
+    assert not np.array_equal(pn, p)
+
+
+# ------------------------------------------------------------------ XMomentum / YMomentum, non-porous decks
+def py_alttridlu(a, b):
+    """src/momentum.f:1307-1339 (a is (n, 3): a(1,i), a(2,i), a(3,i); both modified in place)."""
+    n = len(b)
+    a[0][2] = a[0][2] / a[1][1]
+    b[0] = b[0] / a[0][1]
+    for i in range(1, n - 1):
+        a[i][1] = a[i][1] - (a[i][0] * a[i - 1][2])
+        a[i][2] = a[i][2] / a[i][1]
+        b[i] = (b[i] - a[i][0] * b[i - 1]) / a[i][1]
+    a[n - 1][1] = a[n - 1][1] - (a[n - 1][0] * a[n - 2][2])
+    b[n - 1] = (b[n - 1] - a[n - 1][0] * b[n - 2]) / a[n - 1][1]
+    for i in range(n - 2, -1, -1):
+        b[i] = b[i] - (a[i][2] * b[i + 1])
+
+
+def _regions(d):
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            brd = {k: int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH)}
+            bd = {k: int(r.nMomBdTp[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH)}
+            yield brd[dk.WEST], brd[dk.EAST], brd[dk.SOUTH], brd[dk.NORTH], int(r.nRegType[jr, ir]), bd
+
+
+def _upwind_rows(W, rkj, cj, cjm, cjp, re1, dm, dp, diag_first):
+    """The two branches of the implicit operators (momentum.f:365-375, :411-421, :689-699, :737-747): cj is the
+    local coefficient that switches, cjm / cjp the neighbours' coefficients on the side the flow comes from,
+    dm / dp the diffusion coefficients towards the previous / next unknown."""
+    up = cj >= 0.0
+    a1 = np.where(up, rkj * (-cjm - re1 * dm), rkj * (-re1 * dm))
+    if diag_first:   # XMomentum: dOne + rkj*(...) + dk2*cpj
+        a2 = np.where(up, 1.0 + rkj * (cj + re1 * (dp + dm)), 1.0 + rkj * (-cj + re1 * (dp + dm)))
+    else:            # YMomentum: rkj*(...) + dk2*cpj + dOne
+        a2 = np.where(up, rkj * (cj + re1 * (dp + dm)) + 1.0, rkj * (-cj + re1 * (dp + dm)) + 1.0)
+    a3 = np.where(up, rkj * (-re1 * dp), rkj * (cjp - re1 * dp))
+    return a1, a2, a3
+
+
+def np_xmomentum(d, us, vs, un, vn):
+    """src/momentum.f:278-510 for decks without porous regions (cpj = cps = cpn = 0)."""
+    from wolfd2_b200 import deck as dk
+    nx, ny, m = d.nx, d.ny, d.metrics
+    re1, dk2 = 1.0 / d.re, d.dk * 0.5
+    z = d.new_field
+    cj1, cj2, c1s, c2s, c1n, c2n, cnvs, cnvn, difs, difn = (z() for _ in range(10))
+    np_convcoef(nx, ny, 4, 1, m["xzu"], m["xeu"], m["yzu"], m["yeu"], us, vs, cj1, cj2)
+    np_convcoef(nx, ny, 1, 0, m["xzn"], m["xec"], m["yzn"], m["yec"], us, vs, c1s, c2s)
+    np_convcoef(nx, ny, 1, 0, m["xzn"], m["xec"], m["yzn"], m["yec"], un, vn, c1n, c2n)
+    np_dconvu(nx, ny, c1s, c2s, us, cnvs)
+    np_dconvu(nx, ny, c1n, c2n, un, cnvn)
+    np_ddiffu(nx, ny, m["rac"], m["rbc"], m["rbn"], m["rgn"], us, difs)
+    np_ddiffu(nx, ny, m["rac"], m["rbc"], m["rbn"], m["rgn"], un, difn)
+    W = Rng(1, nx, 2, ny)
+    rkj = dk2 * W(m["dju"])
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj1), W(cj1, -1, 0), W(cj1, 1, 0), re1, W(m["rac"]), W(m["rac"], 1, 0), True)
+    b = W(un) - W(us) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn))
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1).tolist()
+    b = b.ravel().tolist()
+    py_alttridlu(a, b)
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj2), W(cj2, 0, -1), W(cj2, 0, 1), re1, W(m["rgn"], 0, -1), W(m["rgn"]), True)
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1)
+    b = np.array(b)
+    ind = lambda i, j: (j - 2) * nx + i - 1          # 0-based ind of (i, j)
+    ident = []
+    for iW, iE, jS, jN, typ, bd in _regions(d):
+        if typ == dk.RM_BLOCKG:
+            ident += [ind(i, j) for j in range(jS + 1, jN + 1) for i in range(iW, iE + 1)]
+        for face, col in ((dk.WEST, iW), (dk.EAST, iE)):
+            if bd[face] in (dk.BM_WALL1, dk.BM_WALL2, dk.BM_INLET):
+                ident += [ind(col, j) for j in range(jS + 1, jN + 1)]
+    if ident:
+        a[ident] = (0.0, 1.0, 0.0)
+        b[ident] = 0.0
+    a, b = a.tolist(), b.tolist()
+    py_alttridlu(a, b)
+    dus = d.new_field()
+    W.put(dus, np.array(b).reshape(ny - 1, nx))
+    return dus
+
+
+def np_ymomentum(d, us, vs, un, vn, dens, densn):
+    """src/momentum.f:603-834 for decks without porous regions."""
+    from wolfd2_b200 import deck as dk
+    nx, ny, m = d.nx, d.ny, d.metrics
+    re1, dk2 = 1.0 / d.re, d.dk * 0.5
+    z = d.new_field
+    cj1, cj2, c1s, c2s, c1n, c2n, cnvs, cnvn, difs, difn = (z() for _ in range(10))
+    np_convcoef(nx, ny, 5, 1, m["xzv"], m["xev"], m["yzv"], m["yev"], us, vs, cj1, cj2)
+    np_convcoef(nx, ny, 2, 0, m["xzc"], m["xen"], m["yzc"], m["yen"], us, vs, c1s, c2s)
+    np_convcoef(nx, ny, 2, 0, m["xzc"], m["xen"], m["yzc"], m["yen"], un, vn, c1n, c2n)
+    np_dconvv(nx, ny, c1s, c2s, vs, cnvs)
+    np_dconvv(nx, ny, c1n, c2n, vn, cnvn)
+    np_ddiffv(nx, ny, m["ran"], m["rbc"], m["rbn"], m["rgc"], vs, difs)
+    np_ddiffv(nx, ny, m["ran"], m["rbc"], m["rbn"], m["rgc"], vn, difn)
+    W = Rng(2, nx, 1, ny)
+    rkj = dk2 * W(m["djv"])
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj1), W(cj1, -1, 0), W(cj1, 1, 0), re1, W(m["ran"], -1, 0), W(m["ran"]), False)
+    buoy = d.dk * (W(dens, 0, 1) + W(dens) + W(densn, 0, 1) + W(densn)) / (4.0 * d.fr)
+    b = W(vn) - W(vs) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn)) - buoy
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1).tolist()
+    b = b.ravel().tolist()
+    py_alttridlu(a, b)
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj2), W(cj2, 0, -1), W(cj2, 0, 1), re1, W(m["rgc"]), W(m["rgc"], 0, 1), False)
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1)
+    b = np.array(b)
+    ind = lambda i, j: (j - 1) * (nx - 1) + i - 2    # 0-based ind of (i, j)
+    ident = []
+    for iW, iE, jS, jN, typ, bd in _regions(d):
+        if typ == dk.RM_BLOCKG:
+            ident += [ind(i, j) for j in range(jS, jN + 1) for i in range(iW + 1, iE + 1)]
+        for face, row in ((dk.SOUTH, jS), (dk.NORTH, jN)):
+            if bd[face] in (dk.BM_WALL1, dk.BM_WALL2, dk.BM_INLET):
+                ident += [ind(i, row) for i in range(iW + 1, iE + 1)]
+    if ident:
+        a[ident] = (0.0, 1.0, 0.0)
+        b[ident] = 0.0
+    a, b = a.tolist(), b.tolist()
+    py_alttridlu(a, b)
+    dvs = d.new_field()
+    W.put(dvs, np.array(b).reshape(ny, nx - 1))
+    return dvs
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_xmomentum_ymomentum_second_restatement(orc, k):
+    """The whole of XMomentum and YMomentum (coefficients, both split steps, identity rows per region and face type,
+    AltTridLU with its first-row quirk) on the six small decks: cavity, channels with both outlet types, backward
+    step with a blockage, the mixed-face 2x2 deck, outlets on south/east.  Bit for bit."""
+    d = make_test_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(40 + k)
+    r, m = d.regions, d.metrics
+    us, vs, un, vn = (rand_field(d, rng, -0.5, 0.5) for _ in range(4))
+    dens, densn = rand_field(d, rng, 0.9, 1.1), rand_field(d, rng, 0.9, 1.1)
+    xm = [m[n] for n in "rbn rgn rac rbc dju xec yec xzn yzn xeu yeu xzu yzu".split()]
+    do = d.new_field()
+    orc.xmomentum(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, d.re, r.dPRporos, r.dPRporc1, r.dPRporc2,
+                  *xm, us, vs, un, vn, do)
+    assert np.array_equal(np_xmomentum(d, us, vs, un, vn), do)
+    ym = [m[n] for n in "ran rbn rbc rgc djv xen yen xzc yzc xev yev xzv yzv".split()]
+    do = d.new_field()
+    orc.ymomentum(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, d.re, d.fr, r.dPRporos, r.dPRporc1,
+                  r.dPRporc2, *ym, dens, densn, us, vs, un, vn, do)
+    assert np.array_equal(np_ymomentum(d, us, vs, un, vn, dens, densn), do)
+    assert np.abs(do).max() > 1e-6
+
+
+# ------------------------------------------------------------------ a whole time step of the lid-driven cavity
+def np_dmaxnorm(nx, ny, u):
+    """src/utility.f:479-507 (seed |u(5,5)|, scan 2..nx-1, 2..ny-1)."""
+    return max(abs(u[5, 5]), np.abs(u[2:ny, 2:nx]).max())
+
+
+def np_diffmaxnorm(nx, ny, un, u):
+    """src/utility.f:446-473 (seed (2,2), same scan)."""
+    return max(abs(un[2, 2] - u[2, 2]), np.abs(un[2:ny, 2:nx] - u[2:ny, 2:nx]).max())
+
+
+def np_velboundcond_walls(d, u, v):
+    """src/bound_cond.f:555-847, one region whose four faces are no-slip walls (BM_WALL1): W, E, S, N in that order."""
+    from wolfd2_b200 import deck as dk
+    nx, ny, bc = d.nx, d.ny, d.regions.dBCVal
+    val = lambda face, var: bc[var - 1, face - 1, 0, 0]        # dBCVal(1,1,face,var); _U_ = 1, _V_ = 2
+    iW, iE, jS, jN = 1, nx, 1, ny
+    u[jS:jN + 1, iW] = 0.0
+    v[jS + 1:jN + 1, iW] = 2.0 * val(dk.WEST, 2) - v[jS + 1:jN + 1, iW + 1]
+    u[jS:jN + 1, iE] = 0.0
+    v[jS + 1:jN + 1, iE + 1] = 2.0 * val(dk.EAST, 2) - v[jS + 1:jN + 1, iE]
+    u[jS, iW + 1:iE + 1] = 2.0 * val(dk.SOUTH, 1) - u[jS + 1, iW + 1:iE + 1]
+    v[jS, iW:iE + 1] = 0.0
+    u[jN + 1, iW + 1:iE + 1] = 2.0 * val(dk.NORTH, 1) - u[jN, iW + 1:iE + 1]
+    v[jN, iW:iE + 1] = 0.0
+
+
+def np_presboundcond_walls(d, p):
+    """src/bound_cond.f:940-1015, walls on all four faces: Neumann ghosts val + inner."""
+    from wolfd2_b200 import deck as dk
+    nx, ny, bc = d.nx, d.ny, d.regions.dBCVal
+    val = lambda face: bc[2, face - 1, 0, 0]                   # _P_ = 3
+    iW, iE, jS, jN = 1, nx, 1, ny
+    p[jS + 1:jN + 1, iW] = val(dk.WEST) + p[jS + 1:jN + 1, iW + 1]
+    p[jS + 1:jN + 1, iE + 1] = val(dk.EAST) + p[jS + 1:jN + 1, iE]
+    p[jS, iW + 1:iE + 1] = val(dk.SOUTH) + p[jS + 1, iW + 1:iE + 1]
+    p[jN + 1, iW + 1:iE + 1] = val(dk.NORTH) + p[jN, iW + 1:iE + 1]
+
+
+def np_project_walls(d, p, u, v):
+    """src/utility.f:305-392, one flow region with wall faces: interior points only."""
+    nx, ny, m = d.nx, d.ny, d.metrics
+    W = Rng(2, nx - 1, 2, ny)                                  # u: j = jS+1..jN, i = iW+1..iE-1
+    pzi = W(p, 1, 0) - W(p)
+    pet = (W(p, 1, 1) + W(p, 0, 1) - W(p, 1, -1) - W(p, 0, -1)) / 4.0
+    W.put(u, W(u) - W(m["dju"]) * d.dk * (W(m["yeu"]) * pzi - W(m["yzu"]) * pet))
+    W = Rng(2, nx, 2, ny - 1)                                  # v: j = jS+1..jN-1, i = iW+1..iE
+    pzi = (W(p, 1, 1) + W(p, 1, 0) - W(p, -1, 1) - W(p, -1, 0)) / 4.0
+    pet = W(p, 0, 1) - W(p)
+    W.put(v, W(v) - W(m["djv"]) * d.dk * (-W(m["xev"]) * pzi + W(m["xzv"]) * pet))
+
+
+def np_ppe_rb(d, u, v, p):
+    """Ppe with nPpeSolver = 5 on a Cartesian one-region grid (src/pressure.f:90-106, :197-246, :478-541)."""
+    nx, ny, m = d.nx, d.ny, d.metrics
+    div = d.new_field()
+    np_divergence(nx, ny, 1, m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, div)
+    b = np.zeros(d.mnx * d.mny)
+    np_rhsppe(nx, ny, 1, d.dk, m["rbu"], m["rbv"], div, p, b)
+    for it in range(1, d.msorit + 1):
+        dif = np_sorrb_iteration(nx, ny, d.sorrel, m["rau"], m["rgv"], b, p)
+        if it > 1 and dif < d.sortol:
+            return it
+    return d.msorit          # "did not converge": nSorConv = msorit (:242-246)
+
+
+def np_nauxmomentum(d, un, vn, us, vs, dens, densn):
+    """src/momentum.f:111-190 (no outlets on this deck: VelOutflowBCs does nothing)."""
+    nx, ny = d.nx, d.ny
+    us[1:ny + 2, 1:nx + 2] = un[1:ny + 2, 1:nx + 2]
+    vs[1:ny + 2, 1:nx + 2] = vn[1:ny + 2, 1:nx + 2]
+    for it in range(1, d.mqiter + 1):
+        dus = np_xmomentum(d, us, vs, un, vn)
+        dvs = np_ymomentum(d, us, vs, un, vn, dens, densn)
+        us[1:ny + 1, 1:nx + 1] += dus[1:ny + 1, 1:nx + 1]
+        vs[1:ny + 1, 1:nx + 1] += dvs[1:ny + 1, 1:nx + 1]
+        if max(np_dmaxnorm(nx, ny, dus), np_dmaxnorm(nx, ny, dvs)) <= d.qtol:
+            return it
+    return -1
+
+
+def np_cavity_step(d, u, v, p):
+    """src/main.f:690-972, cold flow (one momentum-energy iteration), no filter, no small scales."""
+    nx, ny = d.nx, d.ny
+    pn, un, vn = p.copy(), u.copy(), v.copy()
+    us, vs = u.copy(), v.copy()
+    zero = d.new_field()
+    nql = np_nauxmomentum(d, un, vn, us, vs, zero, zero)
+    np_velboundcond_walls(d, us, vs)
+    np_presboundcond_walls(d, p)
+    nsor = np_ppe_rb(d, us, vs, p)
+    np_presboundcond_walls(d, p)
+    np_project_walls(d, p, us, vs)
+    np_velboundcond_walls(d, us, vs)
+    np_presboundcond_walls(d, p)
+    u[:ny + 2, :nx + 2] = us[:ny + 2, :nx + 2]
+    v[:ny + 2, :nx + 2] = vs[:ny + 2, :nx + 2]
+    np_velboundcond_walls(d, u, v)
+    np_presboundcond_walls(d, p)
+    dif = [np_diffmaxnorm(nx, ny, pn, p), np_diffmaxnorm(nx, ny, un, u), np_diffmaxnorm(nx, ny, vn, v)]
+    return nql, nsor, dif
+
+
+@pytest.mark.parametrize("size", [(20, 16), (33, 24)])
+def test_cavity_time_steps_second_restatement(orc, size):
+    """Four time steps of the lid-driven cavity (the bench workload's deck family) through the numpy restatement of the
+    whole step body -- QL loop with both momentum solves, wall ghost fills in the reference's call order, Ppe with
+    the red/black solver and its convergence rule, projection, the PrintDiff norms -- against orc.step: fields bit
+    for bit, identical QL and SOR counts, identical norms."""
+    from wolfd2_b200 import deck as dk
+    nx, ny = size
+    d = dk.cavity(nx, re=100.0, dt=0.01, ny=ny)
+    d.msorit, d.sortol, d.sorrel, d.mqiter, d.qtol = 80, 1e-6, 1.6, 6, 1e-5
+    d.ppe_solver = "rb_sor"
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(8)
+    u, v, p = (0.05 * rand_field(d, rng) for _ in range(3))
+    np_velboundcond_walls(d, u, v)
+    np_presboundcond_walls(d, p)
+    uo, vo, po = u.copy(), v.copy(), p.copy()
+    seen = set()
+    for step in range(4):
+        nql, nsor, dif = np_cavity_step(d, u, v, p)
+        rc, lg = orc.step(d, uo, vo, po, 1)
+        assert rc == 0
+        assert (nql, nsor) == (lg[0]["nQLiter"], lg[0]["nSorConv"]), step
+        assert np.array_equal(u, uo) and np.array_equal(v, vo) and np.array_equal(p, po), step
+        assert dif == list(lg[0]["dif"][:3]), step
+        seen.add(nsor < d.msorit)
+    assert nql >= 1
