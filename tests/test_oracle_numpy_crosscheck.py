@@ -814,3 +814,115 @@ def test_time_steps_second_restatement_all_decks(orc, k):
         assert dif == list(lg[0]["dif"][:3]), step
         compared += 1
     assert compared >= 1
+
+
+# ------------------------------------------------------------------ Filter, the lexicographic Sor, the cold start
+def py_filter(d, ncomp, fp, qu):
+    """Filter for u (ncomp 1) and v (ncomp 2), src/utility.f:72-203, :238-243: a full copy is filtered per
+    non-blockage region -- interior, then the east / north face when interface or fully-developed outlet, the
+    west / south face only when fully-developed outlet -- and copied back whole."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    nx, ny = d.nx, d.ny
+    qh = qu.copy()
+
+    def f(i, j):
+        qh[j, i] = (qu[j - 1, i] + qu[j, i - 1] + qu[j + 1, i] + qu[j, i + 1] + fp * qu[j, i]) / (fp + 4.0)
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            if int(r.nRegType[jr, ir]) == dk.RM_BLOCKG:
+                continue
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            bd = lambda face: int(r.nMomBdTp[face - 1, jr, ir])
+            if ncomp == 1:
+                for j in range(jS + 1, jN + 1):
+                    for i in range(iW + 1, iE):
+                        f(i, j)
+                if bd(dk.WEST) == dk.BM_OUTLT1:
+                    for j in range(jS + 1, jN + 1): f(iW, j)
+                if bd(dk.EAST) in (dk.BM_INTERN, dk.BM_OUTLT1):
+                    for j in range(jS + 1, jN + 1): f(iE, j)
+            else:
+                for j in range(jS + 1, jN):
+                    for i in range(iW + 1, iE + 1):
+                        f(i, j)
+                if bd(dk.SOUTH) == dk.BM_OUTLT1:
+                    for i in range(iW + 1, iE + 1): f(i, jS)
+                if bd(dk.NORTH) in (dk.BM_INTERN, dk.BM_OUTLT1):
+                    for i in range(iW + 1, iE + 1): f(i, jN)
+    qu[:ny + 2, :nx + 2] = qh[:ny + 2, :nx + 2]
+
+
+def py_sor_lex(d, rau, rgv, b, p, msorit):
+    """Sor, the reference's default solver (src/pressure.f:411-446): lexicographic Gauss-Seidel sweeps with
+    relaxation, one-region grid without blockage (matrix of :97-106)."""
+    nx, ny = d.nx, d.ny
+    for it in range(1, msorit + 1):
+        dif = 0.0
+        for j in range(2, ny + 1):
+            for i in range(2, nx + 1):
+                ind = (j - 2) * (nx - 1) + i - 2
+                a1, a2, a4, a5 = rgv[j - 1, i], rau[j, i - 1], rau[j, i], rgv[j, i]
+                a3 = -rau[j, i] - rau[j, i - 1] - rgv[j, i] - rgv[j - 1, i]
+                s = b[ind] - a1 * p[j - 1, i] - a2 * p[j, i - 1] - a4 * p[j, i + 1] - a5 * p[j + 1, i]
+                s = s / a3 - p[j, i]
+                p[j, i] = p[j, i] + d.sorrel * s
+                dif = max(dif, abs(s))
+        if it > 1 and dif < d.sortol:
+            return it
+    return msorit
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_filter_second_restatement(orc, k):
+    d = make_test_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(90 + k)
+    r = d.regions
+    q = rand_field(d, rng)
+    ntr = np.zeros(200, np.int32)
+    for ncomp in (1, 2):
+        a, b = q.copy(), q.copy()
+        py_filter(d, ncomp, 5.0, a)
+        orc.filter(d.nx, d.ny, ncomp, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, ntr, 5.0, b)
+        assert np.array_equal(a, b) and not np.array_equal(a, q), ncomp
+
+
+def test_default_lexicographic_sor_second_restatement(orc):
+    """Ppe with ppe_solver sor (id 1) on the cavity deck: Divergence + RhsPpe + lexicographic sweeps in plain loops."""
+    d = _deck(0, 24, 20)
+    d.sorrel, d.sortol = 1.5, 1e-7
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(5)
+    m, r = d.metrics, d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    for msorit in (1, 7, 400):
+        po = p.copy()
+        nconv = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 1, msorit, d.dk, d.sortol, d.sorrel, m["rau"], m["rbu"],
+                        m["rbv"], m["rgv"], m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, po)
+        div = d.new_field()
+        np_divergence(d.nx, d.ny, 1, m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, div)
+        b = np.zeros(d.mnx * d.mny)
+        np_rhsppe(d.nx, d.ny, 1, d.dk, m["rbu"], m["rbv"], div, p, b)
+        pn = p.copy()
+        n = py_sor_lex(d, m["rau"], m["rgv"], b, pn, msorit)
+        assert n == nconv and np.array_equal(pn, po), msorit
+    assert nconv < 400       # the last call converged before the cap
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_cold_start_second_restatement(orc, k):
+    """src/main.f:606-641: VelBoundCond, Ppe, PresBoundCond, Project, VelBoundCond on the quiescent initial field."""
+    d = make_test_decks()[k]
+    d.msorit, d.sortol, d.sorrel = 80, 1e-7, 1.5
+    orc.config(d.mnx, d.mny)
+    u, v, p = d.new_field(), d.new_field(), d.new_field()
+    uo, vo, po = d.new_field(), d.new_field(), d.new_field()
+    nso = orc.coldstart(d, uo, vo, po)
+    py_velbc(d, u, v, False)
+    ns = np_ppe_general(d, u, v, p)
+    py_presbc(d, p)
+    py_project(d, p, u, v)
+    py_velbc(d, u, v, False)
+    assert ns == nso
+    assert np.array_equal(u, uo) and np.array_equal(v, vo) and np.array_equal(p, po)
