@@ -926,3 +926,144 @@ def test_cold_start_second_restatement(orc, k):
     py_velbc(d, u, v, False)
     assert ns == nso
     assert np.array_equal(u, uo) and np.array_equal(v, vo) and np.array_equal(p, po)
+
+
+# ------------------------------------------------------------------ thermal energy row
+def _thermal_decks():
+    from wolfd2_b200 import deck as dk
+    out = [dk.heated_cavity(29, re=100.0, dt=0.005, ny=23)]
+    reg = dk.RegionTables(34, 28, 2, 2, (16,), (12,))
+    reg.heat_generation(1, 1, 2.5).fixed_temperature_region(2, 2, 0.8)
+    reg.wall_temperature(1, 1, "w", 1.0).wall_heat_flux(1, 2, "w", 0.05).wall_temperature(2, 1, "s", 0.2)
+    reg.wall_heat_flux(1, 2, "n", -0.02).wall(1, 2, "n", tangent_vel=1.0)
+    out.append(dk._mk("thermal_2x2", 34, 28, reg, 100.0, 0.004, thermal=True, eqstate=True, nmeiter=2))
+    return out
+
+
+def py_tempbc(d, t):
+    """TempBoundCond, src/bound_cond.f:1067-1204."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            val = lambda face: r.dBCVal[3, face - 1, jr, ir]              # _T_ = 4
+            if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                for j in range(jS + 1, jN + 1):
+                    for i in range(iW + 1, iE + 1):
+                        t[j, i] = r.dTRgVal[jr, ir]
+                for j in range(jS + 1, jN + 1):
+                    t[j, iW + 1] = 2.0 * val(dk.WEST) - t[j, iW]
+                for j in range(jS + 1, jN + 1):
+                    t[j, iE] = 2.0 * val(dk.EAST) - t[j, iE + 1]
+                for i in range(iW + 1, iE + 1):
+                    t[jS + 1, i] = 2.0 * val(dk.SOUTH) - t[jS, i]
+                for i in range(iW + 1, iE + 1):
+                    t[jN, i] = 2.0 * val(dk.NORTH) - t[jN + 1, i]
+                continue
+            bt = lambda face: int(r.nTemBdTp[face - 1, jr, ir])
+            for face, rng_, ghost, inner in (
+                    (dk.WEST, range(jS + 1, jN + 1), lambda q: (q, iW), lambda q: (q, iW + 1)),
+                    (dk.EAST, range(jS + 1, jN + 1), lambda q: (q, iE + 1), lambda q: (q, iE)),
+                    (dk.SOUTH, range(iW + 1, iE + 1), lambda q: (jS, q), lambda q: (jS + 1, q)),
+                    (dk.NORTH, range(iW + 1, iE + 1), lambda q: (jN + 1, q), lambda q: (jN, q))):
+                if bt(face) == 1:       # BT_TEMPER: fixed temperature
+                    for q in rng_:
+                        t[ghost(q)] = 2.0 * val(face) - t[inner(q)]
+                elif bt(face) == 2:     # BT_HTFLUX
+                    for q in rng_:
+                        t[ghost(q)] = val(face) + t[inner(q)]
+
+
+def np_eqstate(d, p, t, den):
+    """EqState, src/thermal.f:313-322."""
+    W = Rng(2, d.nx, 2, d.ny)
+    pref = d.densref * d.rconst * d.tref
+    c1 = W(p) * d.densref * d.uref ** 2 + pref
+    c2 = d.densref * d.rconst * (W(t) * (d.tmax - d.tref) + d.tref)
+    r = c1 / c2 - 1.0
+    r[np.abs(r) < 1.0e-10] = 0.0
+    W.put(den, r)
+
+
+def np_thermenergy(d, un, vn, u, v, tn, t):
+    """ThermEnergy, src/thermal.f:97-272."""
+    from wolfd2_b200 import deck as dk
+    nx, ny, m, r = d.nx, d.ny, d.metrics, d.regions
+    pe1 = 1.0 / d.pe
+    py_tempbc(d, t)
+    cu1, cv1, cun, cvn, s = (d.new_field() for _ in range(5))
+    np_convcoef(nx, ny, 6, 0, m["xzc"], m["xec"], m["yzc"], m["yec"], u, v, cu1, cv1)
+    np_convcoef(nx, ny, 3, 0, m["xzv"], m["xeu"], m["yzv"], m["yeu"], un, vn, cun, cvn)
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            s[jS + 1:jN + 1, iW + 1:iE + 1] = r.dHGSTval[jr, ir] if int(r.nTRgType[jr, ir]) == dk.RT_HEATGN else 0.0
+    W = Rng(2, nx, 2, ny)
+    rau, rbu, rbv, rgv = (m[n] for n in "rau rbu rbv rgv".split())
+    rkj = d.dk * W(m["djc"]) * 0.5
+    up = W(cu1) >= 0.0
+    a1 = np.where(up, rkj * (-W(cu1, -1, 0) - pe1 * W(rau, -1, 0)), rkj * (-pe1 * W(rau, -1, 0)))
+    a2 = np.where(up, 1.0 + rkj * (W(cu1) + pe1 * (W(rau) + W(rau, -1, 0))), 1.0 + rkj * (-W(cu1) + pe1 * (W(rau) + W(rau, -1, 0))))
+    a3 = np.where(up, rkj * (-pe1 * W(rau)), rkj * (W(cu1, 1, 0) - pe1 * W(rau)))
+    c = (-W(cvn, 0, -1) * W(tn, 0, -1) - W(cun, -1, 0) * W(tn, -1, 0)
+         + (W(cun) - W(cun, -1, 0) + W(cvn) - W(cvn, 0, -1)) * W(tn)
+         + W(cun) * W(tn, 1, 0) + W(cvn) * W(tn, 0, 1))
+    dd = (W(rau) * (W(tn, 1, 0) - W(tn)) - W(rau, -1, 0) * (W(tn) - W(tn, -1, 0))
+          + W(rbu) * (W(tn, 1, 1) + W(tn, 0, 1) - W(tn, 1, -1) - W(tn, 0, -1))
+          - W(rbu, -1, 0) * (W(tn, 0, 1) + W(tn, -1, 1) - W(tn, 0, -1) - W(tn, -1, -1))
+          + W(rbv) * (W(tn, 1, 1) + W(tn, 1, 0) - W(tn, -1, 1) - W(tn, -1, 0))
+          - W(rbv, 0, -1) * (W(tn, 1, 0) + W(tn, 1, -1) - W(tn, -1, 0) - W(tn, -1, -1))
+          + W(rgv) * (W(tn, 0, 1) - W(tn)) - W(rgv, 0, -1) * (W(tn) - W(tn, 0, -1)))
+    b = d.dk * W(s) * 0.5 + 2.0 * rkj * (-c + pe1 * dd)
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1).tolist()
+    b = b.ravel().tolist()
+    py_alttridlu(a, b)
+    up = W(cv1) >= 0.0
+    a1 = np.where(up, rkj * (-W(cv1, 0, -1) - pe1 * W(rgv, 0, -1)), rkj * (-pe1 * W(rgv, 0, -1)))
+    a2 = np.where(up, 1.0 + rkj * (W(cv1) + pe1 * (W(rgv) + W(rgv, 0, -1))), 1.0 + rkj * (-W(cv1) + pe1 * (W(rgv) + W(rgv, 0, -1))))
+    a3 = np.where(up, rkj * (-pe1 * W(rgv)), rkj * (W(cv1, 0, 1) - pe1 * W(rgv)))
+    a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1)
+    b = np.array(b)
+    ind = lambda i, j: (j - 2) * (nx - 1) + i - 2
+    ident = []
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+                ident += [ind(i, j) for j in range(jS + 1, jN + 1) for i in range(iW + 1, iE + 1)]
+    if ident:
+        a[ident] = (0.0, 1.0, 0.0)
+        b[ident] = 0.0
+    a, b = a.tolist(), b.tolist()
+    py_alttridlu(a, b)
+    W.put(t, W(t) + np.array(b).reshape(ny - 1, nx - 1))
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_thermal_row_second_restatement(orc, k):
+    """TempBoundCond (fixed-temperature blocks, temperature and flux faces), EqState with its 1e-10 clip, and
+    ThermEnergy (case 3 / 6 coefficients, heat sources, both split steps, fixed-T identity rows), bit for bit."""
+    d = _thermal_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(300 + k)
+    r, m = d.regions, d.metrics
+    t = rand_field(d, rng, 0.0, 1.0)
+    a, b = t.copy(), t.copy()
+    py_tempbc(d, a)
+    orc.tempboundcond(d.nx, d.ny, r.nReg, r.nRegBrd, r.nTRgType, r.nTemBdTp, r.dTRgVal, r.dBCVal, b)
+    assert np.array_equal(a, b) and not np.array_equal(a, t)
+    p = rand_field(d, rng, -0.3, 0.3)
+    s = rand_field(d, rng)
+    a, b = s.copy(), s.copy()
+    np_eqstate(d, p, t, a)
+    orc.eqstate(d.nx, d.ny, d.uref, d.densref, d.tmax, d.tref, d.rconst, p, t, b)
+    assert np.array_equal(a, b)
+    un, vn, u, v = (rand_field(d, rng, -0.5, 0.5) for _ in range(4))
+    tn = rand_field(d, rng, 0.0, 1.0)
+    mm = [m[n] for n in "rau rbu rbv rgv djc xeu yeu xzv yzv xec yec xzc yzc".split()]
+    a, b = t.copy(), t.copy()
+    np_thermenergy(d, un, vn, u, v, tn, a)
+    orc.thermenergy(d.nx, d.ny, r.nReg, r.nRegBrd, r.nTRgType, r.nTemBdTp, d.dk, d.pe, r.dTRgVal, r.dHGSTval, r.dBCVal,
+                    *mm, un, vn, u, v, tn, b)
+    assert np.array_equal(a, b) and not np.array_equal(a, t)
