@@ -248,7 +248,7 @@ def _regions(d):
             yield brd[dk.WEST], brd[dk.EAST], brd[dk.SOUTH], brd[dk.NORTH], int(r.nRegType[jr, ir]), bd
 
 
-def _upwind_rows(W, rkj, cj, cjm, cjp, re1, dm, dp, diag_first):
+def _upwind_rows(W, rkj, cj, cjm, cjp, re1, dm, dp, diag_first, por=0.0):
     """The two branches of the implicit operators (momentum.f:365-375, :411-421, :689-699, :737-747): cj is the
     local coefficient that switches, cjm / cjp the neighbours' coefficients on the side the flow comes from,
     dm / dp the diffusion coefficients towards the previous / next unknown."""
@@ -257,13 +257,60 @@ def _upwind_rows(W, rkj, cj, cjm, cjp, re1, dm, dp, diag_first):
     if diag_first:   # XMomentum: dOne + rkj*(...) + dk2*cpj
         a2 = np.where(up, 1.0 + rkj * (cj + re1 * (dp + dm)), 1.0 + rkj * (-cj + re1 * (dp + dm)))
     else:            # YMomentum: rkj*(...) + dk2*cpj + dOne
-        a2 = np.where(up, rkj * (cj + re1 * (dp + dm)) + 1.0, rkj * (-cj + re1 * (dp + dm)) + 1.0)
+        a2 = np.where(up, rkj * (cj + re1 * (dp + dm)) + por + 1.0, rkj * (-cj + re1 * (dp + dm)) + por + 1.0)
     a3 = np.where(up, rkj * (-re1 * dp), rkj * (cjp - re1 * dp))
     return a1, a2, a3
 
 
+def _porous_divide(d, ncomp, arrays):
+    """"Divide convective terms by porosity" (src/momentum.f:296-324, :621-649): region after region, so a point on
+    a border shared by two porous regions is divided twice."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            if int(r.nRegType[jr, ir]) != dk.RM_POROUS:
+                continue
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            sl = (slice(jS + 1, jN + 1), slice(iW, iE + 1)) if ncomp == 1 else (slice(jS, jN + 1), slice(iW + 1, iE + 1))
+            for f in arrays:
+                f[sl] = f[sl] / r.dPRporos[jr, ir]
+
+
+def py_poroscoef(d, ncomp, njacob, u, v):
+    """PorosCoef, src/momentum.f:1152-1222 (the x case keeps the reference's `/dFour` on the last v only)."""
+    from wolfd2_b200 import deck as dk
+    import math
+    r = d.regions
+    cp = d.new_field()
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            if int(r.nRegType[jr, ir]) != dk.RM_POROUS:
+                cp[jS:jN + 1, iW:iE + 1] = 0.0
+                continue
+            porc1, porc2 = r.dPRporc1[jr, ir], r.dPRporc2[jr, ir]
+            if ncomp == 1:
+                for j in range(jS + 1, jN + 1):
+                    for i in range(iW, iE + 1):
+                        unorm = math.sqrt(u[j, i] ** 2 + (v[j, i] + v[j, i + 1] + v[j - 1, i] + v[j - 1, i + 1] / 4.0) ** 2)
+                        unrm1 = (u[j, i] ** 2) / unorm if unorm > 1.0e-8 else 0.0
+                        if njacob == 1:
+                            unorm = unrm1 + unorm
+                        cp[j, i] = porc1 + porc2 * unorm
+            else:
+                for j in range(jS, jN + 1):
+                    for i in range(iW + 1, iE + 1):
+                        unorm = math.sqrt(((u[j + 1, i - 1] + u[j + 1, i] + u[j, i - 1] + u[j, i]) / 4.0) ** 2 + v[j, i] ** 2)
+                        unrm1 = (v[j, i] ** 2) / unorm if unorm > 1.0e-8 else 0.0
+                        if njacob == 1:
+                            unorm = unrm1 + unorm
+                        cp[j, i] = porc1 + porc2 * unorm
+    return cp
+
+
 def np_xmomentum(d, us, vs, un, vn):
-    """src/momentum.f:278-510 for decks without porous regions (cpj = cps = cpn = 0)."""
+    """src/momentum.f:278-510."""
     from wolfd2_b200 import deck as dk
     nx, ny, m = d.nx, d.ny, d.metrics
     re1, dk2 = 1.0 / d.re, d.dk * 0.5
@@ -272,6 +319,8 @@ def np_xmomentum(d, us, vs, un, vn):
     np_convcoef(nx, ny, 4, 1, m["xzu"], m["xeu"], m["yzu"], m["yeu"], us, vs, cj1, cj2)
     np_convcoef(nx, ny, 1, 0, m["xzn"], m["xec"], m["yzn"], m["yec"], us, vs, c1s, c2s)
     np_convcoef(nx, ny, 1, 0, m["xzn"], m["xec"], m["yzn"], m["yec"], un, vn, c1n, c2n)
+    _porous_divide(d, 1, (cj1, cj2, c1s, c2s, c1n, c2n))
+    cpj, cps, cpn = py_poroscoef(d, 1, 1, us, vs), py_poroscoef(d, 1, 0, us, vs), py_poroscoef(d, 1, 0, un, vn)
     np_dconvu(nx, ny, c1s, c2s, us, cnvs)
     np_dconvu(nx, ny, c1n, c2n, un, cnvn)
     np_ddiffu(nx, ny, m["rac"], m["rbc"], m["rbn"], m["rgn"], us, difs)
@@ -279,11 +328,14 @@ def np_xmomentum(d, us, vs, un, vn):
     W = Rng(1, nx, 2, ny)
     rkj = dk2 * W(m["dju"])
     a1, a2, a3 = _upwind_rows(W, rkj, W(cj1), W(cj1, -1, 0), W(cj1, 1, 0), re1, W(m["rac"]), W(m["rac"], 1, 0), True)
-    b = W(un) - W(us) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn))
+    a2 = a2 + dk2 * W(cpj)
+    b = (W(un) - W(us) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn))
+         - dk2 * (W(cps) * W(us) + W(cpn) * W(un)))
     a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1).tolist()
     b = b.ravel().tolist()
     py_alttridlu(a, b)
     a1, a2, a3 = _upwind_rows(W, rkj, W(cj2), W(cj2, 0, -1), W(cj2, 0, 1), re1, W(m["rgn"], 0, -1), W(m["rgn"]), True)
+    a2 = a2 + dk2 * W(cpj)
     a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1)
     b = np.array(b)
     ind = lambda i, j: (j - 2) * nx + i - 1          # 0-based ind of (i, j)
@@ -305,7 +357,7 @@ def np_xmomentum(d, us, vs, un, vn):
 
 
 def np_ymomentum(d, us, vs, un, vn, dens, densn):
-    """src/momentum.f:603-834 for decks without porous regions."""
+    """src/momentum.f:603-834."""
     from wolfd2_b200 import deck as dk
     nx, ny, m = d.nx, d.ny, d.metrics
     re1, dk2 = 1.0 / d.re, d.dk * 0.5
@@ -314,19 +366,24 @@ def np_ymomentum(d, us, vs, un, vn, dens, densn):
     np_convcoef(nx, ny, 5, 1, m["xzv"], m["xev"], m["yzv"], m["yev"], us, vs, cj1, cj2)
     np_convcoef(nx, ny, 2, 0, m["xzc"], m["xen"], m["yzc"], m["yen"], us, vs, c1s, c2s)
     np_convcoef(nx, ny, 2, 0, m["xzc"], m["xen"], m["yzc"], m["yen"], un, vn, c1n, c2n)
+    _porous_divide(d, 2, (cj1, cj2, c1s, c2s, c1n, c2n))
+    cpj, cps, cpn = py_poroscoef(d, 2, 1, us, vs), py_poroscoef(d, 2, 0, us, vs), py_poroscoef(d, 2, 0, un, vn)
     np_dconvv(nx, ny, c1s, c2s, vs, cnvs)
     np_dconvv(nx, ny, c1n, c2n, vn, cnvn)
     np_ddiffv(nx, ny, m["ran"], m["rbc"], m["rbn"], m["rgc"], vs, difs)
     np_ddiffv(nx, ny, m["ran"], m["rbc"], m["rbn"], m["rgc"], vn, difn)
     W = Rng(2, nx, 1, ny)
     rkj = dk2 * W(m["djv"])
-    a1, a2, a3 = _upwind_rows(W, rkj, W(cj1), W(cj1, -1, 0), W(cj1, 1, 0), re1, W(m["ran"], -1, 0), W(m["ran"]), False)
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj1), W(cj1, -1, 0), W(cj1, 1, 0), re1, W(m["ran"], -1, 0), W(m["ran"]), False,
+                              dk2 * W(cpj))
     buoy = d.dk * (W(dens, 0, 1) + W(dens) + W(densn, 0, 1) + W(densn)) / (4.0 * d.fr)
-    b = W(vn) - W(vs) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn)) - buoy
+    b = (W(vn) - W(vs) + rkj * (-W(cnvs) - W(cnvn)) + rkj * re1 * (W(difs) + W(difn))
+         - dk2 * (W(cps) * W(vs) + W(cpn) * W(vn)) - buoy)
     a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1).tolist()
     b = b.ravel().tolist()
     py_alttridlu(a, b)
-    a1, a2, a3 = _upwind_rows(W, rkj, W(cj2), W(cj2, 0, -1), W(cj2, 0, 1), re1, W(m["rgc"]), W(m["rgc"], 0, 1), False)
+    a1, a2, a3 = _upwind_rows(W, rkj, W(cj2), W(cj2, 0, -1), W(cj2, 0, 1), re1, W(m["rgc"]), W(m["rgc"], 0, 1), False,
+                              dk2 * W(cpj))
     a = np.stack([a1.ravel(), a2.ravel(), a3.ravel()], axis=1)
     b = np.array(b)
     ind = lambda i, j: (j - 1) * (nx - 1) + i - 2    # 0-based ind of (i, j)
@@ -1067,3 +1124,46 @@ def test_thermal_row_second_restatement(orc, k):
     orc.thermenergy(d.nx, d.ny, r.nReg, r.nRegBrd, r.nTRgType, r.nTemBdTp, d.dk, d.pe, r.dTRgVal, r.dHGSTval, r.dBCVal,
                     *mm, un, vn, u, v, tn, b)
     assert np.array_equal(a, b) and not np.array_equal(a, t)
+
+
+def _porous_decks():
+    from wolfd2_b200 import deck as dk
+    out = []
+    reg = dk.RegionTables(40, 32, 2, 1, (18,), ()).porous(2, 1, 0.7, 5.0, 2.0)
+    reg.wall(1, 1, "n", tangent_vel=1.0).wall(2, 1, "n", tangent_vel=1.0)
+    out.append(dk._mk("porous_2x1", 40, 32, reg, 100.0, 0.005))
+    reg = dk.RegionTables(44, 40, 2, 2, (22,), (20,))
+    reg.porous(1, 1, 0.8, 3.0, 1.0).porous(2, 1, 0.5, 6.0, 2.5).porous(2, 2, 0.9, 1.0, 0.5)
+    reg.wall(1, 2, "n", tangent_vel=1.0).wall(2, 2, "n", tangent_vel=-0.5)
+    out.append(dk._mk("porous_2x2", 44, 40, reg, 100.0, 0.005))
+    return out
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_porous_momentum_second_restatement(orc, k):
+    """PorosCoef (both components, both njacob, the mis-parenthesised /dFour, the 1e-8 threshold), the porosity
+    division with its double hit on shared region borders, and the Dupuit-Forchheimer terms of both momentum
+    equations: XMomentum / YMomentum on decks with one and with three adjoining porous regions, bit for bit."""
+    d = _porous_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(500 + k)
+    r, m = d.regions, d.metrics
+    us, vs, un, vn = (rand_field(d, rng, -0.5, 0.5) for _ in range(4))
+    us[3:6, 20:30] = 0.0
+    vs[2:7, 19:31] = 0.0
+    for ncomp in (1, 2):
+        for njacob in (0, 1):
+            o = d.new_field()
+            orc.poroscoef(d.nx, d.ny, ncomp, njacob, r.nReg, r.nRegBrd, r.nRegType, r.dPRporos, r.dPRporc1, r.dPRporc2, us, vs, o)
+            assert np.array_equal(py_poroscoef(d, ncomp, njacob, us, vs), o), (ncomp, njacob)
+    zero = d.new_field()
+    xm = [m[n] for n in "rbn rgn rac rbc dju xec yec xzn yzn xeu yeu xzu yzu".split()]
+    do = d.new_field()
+    orc.xmomentum(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, d.re, r.dPRporos, r.dPRporc1, r.dPRporc2,
+                  *xm, us, vs, un, vn, do)
+    assert np.array_equal(np_xmomentum(d, us, vs, un, vn), do)
+    ym = [m[n] for n in "ran rbn rbc rgc djv xen yen xzc yzc xev yev xzv yzv".split()]
+    do = d.new_field()
+    orc.ymomentum(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, d.re, d.fr, r.dPRporos, r.dPRporc1,
+                  r.dPRporc2, *ym, zero, zero, us, vs, un, vn, do)
+    assert np.array_equal(np_ymomentum(d, us, vs, un, vn, zero, zero), do)
