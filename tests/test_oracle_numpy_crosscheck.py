@@ -1167,3 +1167,92 @@ def test_porous_momentum_second_restatement(orc, k):
     orc.ymomentum(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, d.dk, d.re, d.fr, r.dPRporos, r.dPRporc1,
                   r.dPRporc2, *ym, zero, zero, us, vs, un, vn, do)
     assert np.array_equal(np_ymomentum(d, us, vs, un, vn, zero, zero), do)
+
+
+# ------------------------------------------------------------------ node averages, line SOR
+def py_node_averages(d, u, v, p, util, vbar, pav):
+    """VelAvg (src/utility.f:600-626) and PTDAvg (:536-560)."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            blk = int(r.nRegType[jr, ir]) == dk.RM_BLOCKG
+            for j in range(jS, jN + 1):
+                for i in range(iW, iE + 1):
+                    util[j, i] = 0.0 if blk else (u[j, i] + u[j + 1, i]) / 2.0
+                    vbar[j, i] = 0.0 if blk else (v[j, i] + v[j, i + 1]) / 2.0
+            if blk:
+                for j in range(jS + 1, jN):
+                    for i in range(iW + 1, iE):
+                        pav[j, i] = 0.0
+                continue
+            for j in range(jS, jN + 1):
+                for i in range(iW, iE + 1):
+                    s = (p[j, i] + p[j + 1, i] + p[j + 1, i + 1] + p[j, i + 1]) / 4.0
+                    pav[j, i] = 0.0 if abs(s) < 1.0e-20 else s
+
+
+def py_slor(d, rau, rgv, b, p, msorit):
+    """Slor with ndir = 1 (lines along i, as Ppe calls it; src/pressure.f:704-799) on a one-region grid: each line
+    is assembled from the 5-point matrix, solved with AltTridLU (first-row quirk included), relaxed and stored
+    before the next line is assembled."""
+    nx, ny = d.nx, d.ny
+    for it in range(1, msorit + 1):
+        dif = 0.0
+        for j in range(2, ny + 1):
+            al, bl, old = [], [], []
+            for i in range(2, nx + 1):
+                ind = (j - 2) * (nx - 1) + i - 2
+                a1, a2, a4, a5 = rgv[j - 1, i], rau[j, i - 1], rau[j, i], rgv[j, i]
+                a3 = -rau[j, i] - rau[j, i - 1] - rgv[j, i] - rgv[j - 1, i]
+                old.append(p[j, i])
+                al.append([a2, a3, a4])
+                bl.append(b[ind] - (a1 * p[j - 1, i] + a5 * p[j + 1, i]))
+            py_alttridlu(al, bl)
+            for k in range(nx - 1):
+                s = bl[k] - old[k]
+                p[j, 2 + k] = old[k] + d.sorrel * s
+                dif = max(dif, abs(s))
+        if it > 1 and dif < d.sortol:
+            return it
+    return msorit
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_node_averages_second_restatement(orc, k):
+    d = make_test_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(700 + k)
+    r = d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    p[3, 3:6] = 1e-21
+    s = [rand_field(d, rng) for _ in range(3)]
+    a, b = [x.copy() for x in s], [x.copy() for x in s]
+    py_node_averages(d, u, v, p, *a)
+    orc.velavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, u, v, b[0], b[1])
+    orc.ptdavg(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, p, b[2])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_line_sor_second_restatement(orc):
+    """Ppe with ppe_solver lsor (id 2): whole lines solved by AltTridLU, Gauss-Seidel from line to line."""
+    d = _deck(0, 24, 20)
+    d.sorrel, d.sortol = 1.3, 1e-8
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(6)
+    m, r = d.metrics, d.regions
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    for msorit in (1, 5, 300):
+        po = p.copy()
+        nconv = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, 1, 2, msorit, d.dk, d.sortol, d.sorrel, m["rau"], m["rbu"],
+                        m["rbv"], m["rgv"], m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, po)
+        div = d.new_field()
+        np_divergence(d.nx, d.ny, 1, m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, div)
+        b = np.zeros(d.mnx * d.mny)
+        np_rhsppe(d.nx, d.ny, 1, d.dk, m["rbu"], m["rbv"], div, p, b)
+        pn = p.copy()
+        n = py_slor(d, m["rau"], m["rgv"], b, pn, msorit)
+        assert n == nconv and np.array_equal(pn, po), msorit
+    assert nconv < 300
