@@ -12,7 +12,12 @@
  * reference itself.  Mitigation: every routine is transcribed statement by statement
  * with the same 1-based index expressions, the same operation order, the same
  * (0:mnx,0:mny) pitch and zero-initialised static storage, and is compiled with
- * -O2 -ffp-contract=off (gfortran -O2 on baseline x86-64 emits no FMA).
+ * -O2 -ffp-contract=off (gfortran -O2 on baseline x86-64 emits no FMA).  A second
+ * restatement, written independently in numpy / plain Python from the same Fortran
+ * text (tests/test_oracle_numpy_crosscheck.py), reproduces every routine of the
+ * cold-flow path and of the thermal row, whole time steps included, bit for bit;
+ * two physical pins (Ghia's cavity, plane Poiseuille flow) and the analytic
+ * conduction solutions check the physics (tests/test_oracle_cpu.py).
  *
  * Each function cites the reference file:line it follows (paths relative to the
  * reference tree).  Fortran `stop` becomes: set orc_errflag and return.
