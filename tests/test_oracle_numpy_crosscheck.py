@@ -1256,3 +1256,287 @@ def test_line_sor_second_restatement(orc):
         n = py_slor(d, m["rau"], m["rgv"], b, pn, msorit)
         assert n == nconv and np.array_equal(pn, po), msorit
     assert nconv < 300
+
+
+# ------------------------------------------------------------------ ATD small-scale model
+def py_filter_t(d, fp, qu):
+    """Filter, case(_T_) (src/utility.f:205-229): the region test compares nTRgType with BT_TEMPER (= 1), as written."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    qh = qu.copy()
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            if int(r.nTRgType[jr, ir]) == 1:
+                continue
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            for j in range(jS + 1, jN + 1):
+                for i in range(iW + 1, iE + 1):
+                    qh[j, i] = (qu[j - 1, i] + qu[j, i - 1] + qu[j + 1, i] + qu[j, i + 1] + fp * qu[j, i]) / (fp + 4.0)
+    qu[:d.ny + 2, :d.nx + 2] = qh[:d.ny + 2, :d.nx + 2]
+
+
+def py_smlsclbc_walls(d, u, v, p, t):
+    """SmlSclBC (src/bound_cond.f:1257-1649) for decks whose outer faces are walls or inlets: homogeneous velocity
+    ghosts, PresBoundCond as it is, homogeneous temperature ghosts."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
+                tp = int(r.nMomBdTp[face - 1, jr, ir])
+                if tp == dk.BM_INTERN:
+                    continue
+                assert tp in (dk.BM_WALL1, dk.BM_WALL2, dk.BM_INLET), "outlets are not restated here"
+                sgn = 1.0 if tp == dk.BM_WALL2 else -1.0
+                if face == dk.WEST:
+                    u[jS:jN + 1, iW] = 0.0
+                    v[jS + 1:jN + 1, iW] = sgn * v[jS + 1:jN + 1, iW + 1]
+                elif face == dk.EAST:
+                    u[jS:jN + 1, iE] = 0.0
+                    v[jS + 1:jN + 1, iE + 1] = sgn * v[jS + 1:jN + 1, iE]
+                elif face == dk.SOUTH:
+                    u[jS, iW + 1:iE + 1] = sgn * u[jS + 1, iW + 1:iE + 1]
+                    v[jS, iW:iE + 1] = 0.0
+                else:
+                    u[jN + 1, iW + 1:iE + 1] = sgn * u[jN, iW + 1:iE + 1]
+                    v[jN, iW:iE + 1] = 0.0
+    py_presbc(d, p)
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                t[jS + 1:jN + 1, iW + 1:iE + 1] = 0.0
+                t[jS + 1:jN + 1, iW + 1] = -t[jS + 1:jN + 1, iW]
+                t[jS + 1:jN + 1, iE] = -t[jS + 1:jN + 1, iE + 1]
+                t[jS + 1, iW + 1:iE + 1] = -t[jS, iW + 1:iE + 1]
+                t[jN, iW + 1:iE + 1] = -t[jN + 1, iW + 1:iE + 1]
+                continue
+            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
+                bt = int(r.nTemBdTp[face - 1, jr, ir])
+                if bt == 0:
+                    continue
+                sgn = -1.0 if bt == 1 else 1.0          # BT_TEMPER: mirror, BT_HTFLUX: copy
+                if face == dk.WEST:
+                    t[jS + 1:jN + 1, iW] = sgn * t[jS + 1:jN + 1, iW + 1]
+                elif face == dk.EAST:
+                    t[jS + 1:jN + 1, iE + 1] = sgn * t[jS + 1:jN + 1, iE]
+                elif face == dk.SOUTH:
+                    t[jS, iW + 1:iE + 1] = sgn * t[jS + 1, iW + 1:iE + 1]
+                else:
+                    t[jN + 1, iW + 1:iE + 1] = sgn * t[jN, iW + 1:iE + 1]
+
+
+class PySmallScale:
+    """SmallScale (src/small_scale.f:160-581) with its `save`d state (map iterates, cell areas)."""
+    AR, AM, RC = 4.82842712474, 1.47839783948, 0.20710678119
+
+    def __init__(self, d):
+        self.d = d
+        self.umap = np.zeros((3,) + d.new_field().shape)
+        self.vmap, self.tmap = self.umap.copy(), self.umap.copy()
+        self.area = d.new_field()
+        self.tarea = 0.0
+
+    def call(self, initflg, u1, v1, t1, uss, vss, pss, tss):
+        import math
+        from wolfd2_b200 import deck as dk
+        d = self.d
+        nx, ny, m, r = d.nx, d.ny, d.metrics, d.regions
+        AR, AM, RC = self.AR, self.AM, self.RC
+        fp = d.ss_filt
+        cu0, TsCoef, HsCoef, TemCoef = d.ss_cu0, d.ss_tscoef, d.ss_hscoef, d.ss_temcoef
+        bnumc, rmax, rlc = d.ss_bncrit, d.ss_rmpmax, d.ss_rmpexp
+        dlref, uref, tref, tmax, dka, re, pe = d.dlref, d.uref, d.tref, d.tmax, d.dk, d.re, d.pe
+        piosr2 = math.acos(-1.0) / math.sqrt(2.0)
+        pehmin = 3.0
+        hs = dlref * HsCoef
+        dk_ = dka * dlref / uref
+        pr = pe / re
+        rnu = uref * dlref / re
+        dkappa = rnu / pr
+        djc = m["djc"]
+        if initflg <= 0:
+            ump, vmp, tmp = 0.92, 0.31, 0.50
+            for i in range(0, nx + 2):
+                for j in range(0, ny + 2):
+                    for l in range(3):
+                        ump = RC * AR * ump * (1.0 - AM * abs(ump))
+                        vmp = RC * AR * vmp * (1.0 - AM * abs(vmp))
+                        tmp = RC * AR * tmp * (1.0 - AM * abs(tmp))
+                        self.umap[l, j, i], self.vmap[l, j, i], self.tmap[l, j, i] = ump, vmp, tmp
+                    uss[j, i] = vss[j, i] = tss[j, i] = 0.0
+            self.tarea = 0.0
+            for i in range(1, nx + 1):
+                for j in range(1, ny + 1):
+                    self.area[j, i] = 1.0 / djc[j, i]
+                    self.tarea = self.tarea + self.area[j, i]
+            if initflg < 0:
+                return
+        z = d.new_field
+        xz, xe, yz, ye, rj, vl, ul, tl, uc, vc = (z() for _ in range(10))
+        W = Rng(1, nx, 1, ny)
+        W.put(xz, dlref * W(m["xzc"])); W.put(xe, dlref * W(m["xec"]))
+        W.put(yz, dlref * W(m["yzc"])); W.put(ye, dlref * W(m["yec"]))
+        W.put(rj, W(djc) / (dlref * dlref))
+        W.put(vl, uref * (W(v1) + W(v1, 0, -1)) * 0.5)
+        W.put(ul, uref * (W(u1) + W(u1, -1, 0)) * 0.5)
+        W.put(tl, (tmax - tref) * W(t1) + tref)
+        W.put(uc, W(ye) * W(ul) - W(xe) * W(vl))
+        W.put(vc, W(xz) * W(vl) - W(yz) * W(ul))
+        uf, vf, tf = z(), z(), z()
+        W.put(uf, W(uc)); W.put(vf, W(vc)); W.put(tf, W(tl))
+        # the work arrays are static in the reference: uf, vf, tf keep what earlier calls left outside 1..nx, 1..ny
+        for name, f in (("uf", uf), ("vf", vf), ("tf", tf)):
+            old = getattr(self, name, None)
+            if old is not None:
+                keep = np.ones_like(f, dtype=bool)
+                keep[1:ny + 1, 1:nx + 1] = False
+                f[keep] = old[keep]
+        py_tempbc(d, tf)
+        py_filter(d, 1, fp[0], uf)
+        py_filter(d, 2, fp[1], vf)
+        py_filter_t(d, fp[3], tf)
+        W.put(uf, W(uc) - W(uf)); W.put(vf, W(vc) - W(vf)); W.put(tf, W(tl) - W(tf))
+        self.uf, self.vf, self.tf = uf, vf, tf
+        s15 = math.sqrt(15.0)
+        for jr in range(int(r.nReg[1])):
+            for ir in range(int(r.nReg[0])):
+                iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+                if int(r.nRegType[jr, ir]) == dk.RM_BLOCKG or int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                    continue
+                for i in range(iW + 1, iE + 1):
+                    for j in range(jS + 1, jN + 1):
+                        XZ, YZ, XE, YE, RJ = xz[j, i], yz[j, i], xe[j, i], ye[j, i], rj[j, i]
+                        hxy = math.sqrt(XZ * XZ + YZ * YZ + XE * XE + YE * YE)
+                        uz = (ul[j, i + 1] - ul[j, i - 1]) * 0.5; ue = (ul[j + 1, i] - ul[j - 1, i]) * 0.5
+                        vz = (vl[j, i + 1] - vl[j, i - 1]) * 0.5; ve = (vl[j + 1, i] - vl[j - 1, i]) * 0.5
+                        sq = lambda x: x * x
+                        uxsq = sq(RJ * (YE * uz - YZ * ue)); uysq = sq(RJ * (XZ * ue - XE * uz))
+                        vxsq = sq(RJ * (YE * vz - YZ * ve)); vysq = sq(RJ * (XZ * ve - XE * vz))
+                        delu2n = math.sqrt(uxsq + uysq + vxsq + vysq)
+                        tz = (tl[j, i + 1] - tl[j, i - 1]) * 0.5; te = (tl[j + 1, i] - tl[j - 1, i]) * 0.5
+                        txsq = sq(RJ * (YE * tz - YZ * te)); tysq = sq(RJ * (XZ * te - XE * tz))
+                        delt2n = math.sqrt(txsq + tysq)
+                        reh = delu2n * (hxy * hxy) / rnu
+                        peh = pr * reh
+                        if not peh > pehmin:
+                            continue
+                        cuU, cuV, cuT = cu0 * TemCoef, cu0, cu0
+                        if cu0 > float(np.float32(1.e-10)):
+                            ts = TsCoef * piosr2 * math.pow(reh, 1.0 / 3.0) / (cu0 * delu2n)
+                            nmap = int(1.0 + dk_ / ts)
+                        else:
+                            nmap = 0
+                        nmap = min(nmap, 50)
+                        bnum = s15 * math.pow(hs * hs * delu2n / rnu, 1.0 / 6.0)
+                        rmap = rmax * math.tanh(math.pow(bnum / bnumc, rlc) * math.atanh(RC / rmax))
+                        uz = (uf[j, i + 1] - uf[j, i - 1]) * 0.5; ue = (uf[j + 1, i] - uf[j - 1, i]) * 0.5
+                        vz = (vf[j, i + 1] - vf[j, i - 1]) * 0.5; ve = (vf[j + 1, i] - vf[j - 1, i]) * 0.5
+                        tz = (tf[j, i + 1] - tf[j, i - 1]) * 0.5; te = (tf[j + 1, i] - tf[j - 1, i]) * 0.5
+                        gu1 = RJ * (YE * uz - YZ * ue); gu2 = RJ * (XZ * ue - XE * uz)
+                        gv1 = RJ * (YE * vz - YZ * ve); gv2 = RJ * (XZ * ve - XE * vz)
+                        gt1 = RJ * (YE * tz - YZ * te); gt2 = RJ * (XZ * te - XE * tz)
+                        grduf = math.sqrt(gu1 * gu1 + gu2 * gu2)
+                        grdvf = math.sqrt(gv1 * gv1 + gv2 * gv2)
+                        grdtf = math.sqrt(gt1 * gt1 + gt2 * gt2)
+                        grd = math.sqrt(grduf * grduf + grdvf * grdvf + grdtf * grdtf)
+                        with np.errstate(all="ignore"):
+                            s1, s2 = np.float64(grduf) / grd, np.float64(grdvf) / grd
+                            rnrmjs = np.sqrt(sq(XZ * s1 + XE * s2) + sq(YZ * s1 + YE * s2))
+                            zeta1 = math.sqrt(2.0) * s1 / rnrmjs
+                            zeta2 = math.sqrt(2.0) * s2 / rnrmjs
+                        zeta3 = 1.0
+                        a11, a12 = (gu1 / grduf, gu2 / grduf) if abs(grduf) > 0.0 else (0.0, 0.0)
+                        a21, a22 = (gv1 / grdvf, gv2 / grdvf) if abs(grdvf) > 0.0 else (0.0, 0.0)
+                        if abs(grdtf) > 0.0:
+                            a31, a32, a33 = gu1 / grdtf, gu2 / grdtf, math.sqrt(gt1 * gt1 + gt2 * gt2) / grdtf
+                        else:
+                            a31 = a32 = a33 = 0.0
+                        mp = [self.umap[l, j, i] for l in range(3)] + [self.vmap[l, j, i] for l in range(3)] + \
+                             [self.tmap[l, j, i] for l in range(3)]
+                        for _ in range(nmap):
+                            mp = [rmap * AR * x * (1.0 - AM * abs(x)) for x in mp]
+                        for l in range(3):
+                            self.umap[l, j, i], self.vmap[l, j, i], self.tmap[l, j, i] = mp[l], mp[3 + l], mp[6 + l]
+                        um = a11 * mp[0] + a12 * mp[1]
+                        vm = a21 * mp[0] + a22 * mp[1]
+                        tm = a31 * mp[6] + a32 * mp[7] + a33 * mp[8]
+                        r16 = math.pow(reh, 1.0 / 6.0)
+                        av = cuV * r16 * math.sqrt(rnu * delu2n)
+                        at = math.pow(3.0 * math.pow(cuT, 4.0) * peh / pr, 1.0 / 6.0) * math.sqrt(dkappa)
+                        with np.errstate(all="ignore"):
+                            at = np.float64(at) * delt2n / math.sqrt(delu2n) * TemCoef
+                        av = av * math.sqrt(self.area[j, i] / self.tarea) * math.pow(hxy, 1.0 / 3.0)
+                        at = at * math.sqrt(self.area[j, i] / self.tarea) * math.pow(hxy, 1.0 / 3.0)
+                        uscon = av * zeta1 * um
+                        vscon = av * zeta2 * vm
+                        uss[j, i] = RJ * (XZ * uscon + YE * vscon) / uref
+                        vss[j, i] = RJ * (YE * vscon + YZ * uscon) / uref
+                        tss[j, i] = (at * tm * zeta3) / (tmax - tref)
+                        if abs(uss[j, i]) < 1.0e-14: uss[j, i] = 0.0
+                        if abs(vss[j, i]) < 1.0e-14: vss[j, i] = 0.0
+                        if abs(tss[j, i]) < 1.0e-14: tss[j, i] = 0.0
+        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        pss[0:ny + 1, 0:nx + 1] = 0.0
+        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        sv = (d.msorit, d.sortol, d.sorrel)
+        d.msorit, d.sortol, d.sorrel = d.ss_msorit, d.ss_sortol, d.ss_sorrel
+        try:
+            np_ppe_general(d, uss, vss, pss)
+        finally:
+            d.msorit, d.sortol, d.sorrel = sv
+        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        py_project(d, pss, uss, vss)
+
+
+def _ss_call_args(d, initflg):
+    from wolfd2_b200.deck import PPE_SOLVERS
+    r, m = d.regions, d.metrics
+    fp = np.array(d.ss_filt, dtype=np.float64)
+    return (d.nx, d.ny, initflg, int(d.thermal), int(d.cartesian), r.nReg, r.nRegBrd, r.nRegType, r.nTRgType, r.nMomBdTp,
+            r.nTemBdTp, PPE_SOLVERS[d.ss_ppe_solver], d.ss_msorit, d.dlref, d.uref, d.tref, d.tmax, d.dk, d.re, d.pe,
+            d.ss_sortol, d.ss_sorrel, fp, d.ss_cu0, d.ss_tscoef, d.ss_hscoef, d.ss_temcoef, d.ss_bncrit, d.ss_rmpmax,
+            d.ss_rmpexp, r.dTRgVal, r.dBCVal, m["rau"], m["rbu"], m["rbv"], m["rgv"], m["dju"], m["djv"], m["djc"],
+            m["xeu"], m["yeu"], m["xzv"], m["yzv"], m["xzu"], m["yzu"], m["xev"], m["yev"], m["xec"], m["yec"],
+            m["xzc"], m["yzc"])
+
+
+def _ss_decks():
+    from wolfd2_b200 import deck as dk
+    kw = dict(smallscale=True, ss_cu0=1.0, ss_bncrit=2.0, ss_rmpmax=0.95, ss_ppe_solver="rb_sor", ss_msorit=120,
+              ss_sortol=1e-9, ss_sorrel=1.5, ss_filt=(4e2, 3e2, 0.0, 2e2))
+    out = [dk.cavity(25, re=1000.0, dt=0.01, ny=21, **kw)]
+    reg = dk.RegionTables(30, 26, 2, 2, (14,), (12,))
+    reg.heat_generation(1, 1, 2.0).fixed_temperature_region(2, 2, 0.7)
+    reg.wall_temperature(1, 1, "w", 1.0).wall_heat_flux(1, 2, "w", 0.05).wall(1, 2, "n", tangent_vel=1.0)
+    out.append(dk._mk("atd_thermal_2x2", 30, 26, reg, 900.0, 0.004, thermal=True, nmeiter=2, **kw))
+    return out
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_smallscale_second_restatement(orc, k):
+    """SmallScale through three calls (seeding, then two advances on changing fields): the high-pass filter, the
+    per-cell chaotic-map model with pow / tanh / atanh from the same libm, the clamp nmap <= 50, `av` used for both
+    velocity components (:505-506), the 1e-14 flush, SmlSclBC, the small-scale Ppe and projection -- uss, vss, pss,
+    tss and all nine saved map planes bit for bit.  Wall-bounded decks (cold cavity; thermal 2x2 with a heat source,
+    a fixed-temperature block, temperature and flux faces)."""
+    d = _ss_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(900 + k)
+    mine = PySmallScale(d)
+    g = [d.new_field() for _ in range(4)]
+    o = [d.new_field() for _ in range(4)]
+    for call, initflg in enumerate((0, 1, 1)):
+        u, v, t = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng, 0.0, 1.0)
+        mine.call(initflg, u, v, t, *g)
+        orc.smallscale(*_ss_call_args(d, initflg), u, v, t, *o)
+        assert orc.lib.orc_get_errflag() == 0
+        for name, a, b in zip(("uss", "vss", "pss", "tss"), g, o):
+            assert np.array_equal(a, b), (call, name, np.abs(a - b).max())
+        n = d.new_field().size
+        for fam, mp in enumerate((mine.umap, mine.vmap, mine.tmap)):
+            for l in range(3):
+                ref = np.ctypeslib.as_array(orc.lib.orc_ss_map(fam, l + 1), shape=(n,)).reshape(d.new_field().shape)
+                assert np.array_equal(mp[l], ref), (call, fam, l)
+    assert np.abs(g[0]).max() > 0 and np.abs(g[3]).max() >= 0
