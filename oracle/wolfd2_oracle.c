@@ -15,7 +15,8 @@
  * -O2 -ffp-contract=off (gfortran -O2 on baseline x86-64 emits no FMA).  A second
  * restatement, written independently in numpy / plain Python from the same Fortran
  * text (tests/test_oracle_numpy_crosscheck.py), reproduces every routine of the
- * cold-flow path and of the thermal row, whole time steps included, bit for bit;
+ * cold-flow path, the thermal row, SmallScale and Traject, whole time steps included,
+ * bit for bit;
  * two physical pins (Ghia's cavity, plane Poiseuille flow) and the analytic
  * conduction solutions check the physics (tests/test_oracle_cpu.py).
  *
