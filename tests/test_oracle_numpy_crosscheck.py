@@ -1719,3 +1719,77 @@ def test_traject_second_restatement(orc, method, cdeq):
     assert set(out_m[:4]) >= {2, 3} and (out_m[4:] == 0).sum() > 20      # (on this skewed grid the first match of
     # the particle left of the domain is a node further along a lower row: flag 0, as the reference would)
     assert not np.array_equal(mine[0][4:], xp[4:])
+
+
+# ------------------------------------------------------------------ time steps with the momentum-energy iterations
+def np_step_thermal(d, u, v, p, t, den):
+    """src/main.f:690-972 with the thermal energy equation on: the momentum-energy iteration loop (:736-880) around
+    nAuxMomentum (buoyancy from d, dn) ... Project, ThermEnergy, EqState, its convergence rule, Filter(_T_),
+    TempBoundCond, four norms."""
+    nx, ny = d.nx, d.ny
+    pn, un, vn, tn, dn = p.copy(), u.copy(), v.copy(), t.copy(), den.copy()
+    nmeiter = d.nmeiter if d.thermal else min(d.nmeiter, 1)
+    nql = nsor = None
+    for l in range(1, nmeiter + 1):
+        us, vs, ts = u.copy(), v.copy(), t.copy()
+        us[1:ny + 2, 1:nx + 2] = un[1:ny + 2, 1:nx + 2]
+        vs[1:ny + 2, 1:nx + 2] = vn[1:ny + 2, 1:nx + 2]
+        nql = -1
+        for it in range(1, d.mqiter + 1):
+            py_velbc(d, us, vs, outflow_only=True)
+            dus = np_xmomentum(d, us, vs, un, vn)
+            dvs = np_ymomentum(d, us, vs, un, vn, den, dn)
+            us[1:ny + 1, 1:nx + 1] += dus[1:ny + 1, 1:nx + 1]
+            vs[1:ny + 1, 1:nx + 1] += dvs[1:ny + 1, 1:nx + 1]
+            if max(np_dmaxnorm(nx, ny, dus), np_dmaxnorm(nx, ny, dvs)) <= d.qtol:
+                nql = it
+                break
+        py_velbc(d, us, vs, False)
+        py_presbc(d, p)
+        nsor = np_ppe_general(d, us, vs, p)
+        py_presbc(d, p)
+        py_project(d, p, us, vs)
+        py_velbc(d, us, vs, False)
+        py_presbc(d, p)
+        if d.thermal:
+            np_thermenergy(d, un, vn, us, vs, tn, ts)
+        if d.eqstate:
+            np_eqstate(d, p, ts, den)
+        dif = [np_diffmaxnorm(nx, ny, u, us), np_diffmaxnorm(nx, ny, v, vs), np_diffmaxnorm(nx, ny, t, ts)]
+        u[:ny + 2, :nx + 2] = us[:ny + 2, :nx + 2]
+        v[:ny + 2, :nx + 2] = vs[:ny + 2, :nx + 2]
+        t[:ny + 2, :nx + 2] = ts[:ny + 2, :nx + 2]
+        if l > 1 and max(dif) < d.dmeittol:
+            break
+    if d.thermal and d.nfiltt == 1:
+        py_filter_t(d, d.fpt, t)
+    py_velbc(d, u, v, False)
+    py_presbc(d, p)
+    if d.thermal:
+        py_tempbc(d, t)
+    dif = [np_diffmaxnorm(nx, ny, pn, p), np_diffmaxnorm(nx, ny, un, u), np_diffmaxnorm(nx, ny, vn, v),
+           np_diffmaxnorm(nx, ny, tn, t)]
+    return nql, nsor, dif
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_thermal_time_steps_second_restatement(orc, k):
+    """Three time steps with the thermal energy equation (2-3 momentum-energy iterations per step, buoyancy through
+    EqState, heat sources, a fixed-temperature block): u, v, p, t, d bit for bit, counts and the four-column
+    PrintDiff tuple identical."""
+    import dataclasses
+    d = _thermal_decks()[k]
+    d = dataclasses.replace(d, msorit=60, sortol=1e-7, sorrel=1.5, mqiter=5, qtol=1e-6, nfiltt=1 if k == 1 else 0, fpt=300.0)
+    orc.config(d.mnx, d.mny)
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    t[:d.ny + 2, :d.nx + 2] = 0.5
+    uo, vo, po, to, do = u.copy(), v.copy(), p.copy(), t.copy(), den.copy()
+    for step in range(3):
+        nql, nsor, dif = np_step_thermal(d, u, v, p, t, den)
+        rc, lg = orc.step(d, uo, vo, po, 1, t=to, d=do)
+        assert rc == 0
+        assert (nql, nsor) == (lg[0]["nQLiter"], lg[0]["nSorConv"]), (step, nql, nsor)
+        for name, a, b in zip("uvptd", (u, v, p, t, den), (uo, vo, po, to, do)):
+            assert np.array_equal(a, b), (step, name, np.abs(a - b).max())
+        assert dif == list(lg[0]["dif"]), step
+    assert np.abs(t[2:d.ny + 1, 2:d.nx + 1] - 0.5).max() > 1e-4
