@@ -1722,12 +1722,16 @@ def test_traject_second_restatement(orc, method, cdeq):
 
 
 # ------------------------------------------------------------------ time steps with the momentum-energy iterations
-def np_step_thermal(d, u, v, p, t, den):
+def np_step_thermal(d, u, v, p, t, den, ss=None):
     """src/main.f:690-972 with the thermal energy equation on: the momentum-energy iteration loop (:736-880) around
     nAuxMomentum (buoyancy from d, dn) ... Project, ThermEnergy, EqState, its convergence rule, Filter(_T_),
     TempBoundCond, four norms."""
     nx, ny = d.nx, d.ny
     pn, un, vn, tn, dn = p.copy(), u.copy(), v.copy(), t.copy(), den.copy()
+    if ss is not None:          # src/main.f:706-727: the time-level-n fields carry the small scales once more
+        model, uss, vss, pss, tss = ss
+        usn, vsn, tsn = uss.copy(), vss.copy(), tss.copy()
+        un += uss; vn += vss; tn += tss
     nmeiter = d.nmeiter if d.thermal else min(d.nmeiter, 1)
     nql = nsor = None
     for l in range(1, nmeiter + 1):
@@ -1763,6 +1767,11 @@ def np_step_thermal(d, u, v, p, t, den):
             break
     if d.thermal and d.nfiltt == 1:
         py_filter_t(d, d.fpt, t)
+    if ss is not None:          # src/main.f:896-940: strip the old small scales, advance the model, add the new ones
+        W = (slice(0, ny + 2), slice(0, nx + 2))
+        u[W] = u[W] - usn[W]; v[W] = v[W] - vsn[W]; t[W] = t[W] - tsn[W]
+        model.call(1, u, v, t, uss, vss, pss, tss)
+        u[W] = u[W] + uss[W]; v[W] = v[W] + vss[W]; t[W] = t[W] + tss[W]
     py_velbc(d, u, v, False)
     py_presbc(d, p)
     if d.thermal:
@@ -1793,3 +1802,39 @@ def test_thermal_time_steps_second_restatement(orc, k):
             assert np.array_equal(a, b), (step, name, np.abs(a - b).max())
         assert dif == list(lg[0]["dif"]), step
     assert np.abs(t[2:d.ny + 1, 2:d.nx + 1] - 0.5).max() > 1e-4
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_atd_time_steps_second_restatement(orc, k):
+    """Time steps with the ATD small-scale model inside (src/main.f:643-665, :706-727, :896-940) on a developed
+    vortex: cold cavity and thermal 2x2 deck.  u, v, p, t, d, uss, vss, pss, tss bit for bit."""
+    import dataclasses
+    d = _ss_decks()[k]
+    d = dataclasses.replace(d, ss_cu0=0.05, msorit=60, sortol=1e-7, sorrel=1.5, mqiter=5, qtol=1e-6, ss_msorit=60)
+    orc.config(d.mnx, d.mny)
+    gx, gy = d.node_arrays()
+    X, Y = gx / gx.max(), gy / gy.max()
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    u[:] = np.sin(np.pi * X) ** 2 * np.sin(2 * np.pi * Y)
+    v[:] = -np.sin(2 * np.pi * X) * np.sin(np.pi * Y) ** 2
+    py_velbc(d, u, v, False)
+    uo, vo, po, to, do = (a.copy() for a in (u, v, p, t, den))
+    ss_m = [d.new_field() for _ in range(4)]
+    ss_o = [d.new_field() for _ in range(4)]
+    model = PySmallScale(d)
+    model.call(0, u, v, t, *ss_m)
+    orc.atd_init(d, uo, vo, to, *ss_o)
+    for a, b in zip(ss_m, ss_o):
+        assert np.array_equal(a, b)
+    active = False
+    for step in range(3):
+        nql, nsor, dif = np_step_thermal(d, u, v, p, t, den, ss=(model, *ss_m))
+        rc, lg = orc.step_full(d, uo, vo, po, to, do, ss_fields=ss_o, nsteps=1)
+        assert rc == 0
+        assert (nql, nsor) == (lg[0]["nQLiter"], lg[0]["nSorConv"]), (step, nql, nsor)
+        names = "u v p t d uss vss pss tss".split()
+        for name, a, b in zip(names, (u, v, p, t, den, *ss_m), (uo, vo, po, to, do, *ss_o)):
+            assert np.array_equal(a, b), (step, name, np.abs(a - b).max())
+        assert dif == list(lg[0]["dif"]), step
+        active = active or np.abs(ss_m[0]).max() > 1e-8
+    assert active
