@@ -1838,3 +1838,108 @@ def test_atd_time_steps_second_restatement(orc, k):
         assert dif == list(lg[0]["dif"]), step
         active = active or np.abs(ss_m[0]).max() > 1e-8
     assert active
+
+
+# ------------------------------------------------------------------ all six solvers, Cartesian flag on and off
+def py_ppe_any_solver(d, solver, cartes, u, v, p, msorit):
+    """Ppe on a one-region grid (src/pressure.f:90-246) with solver ids 1..6: Sor :411-446, Slor :704-799, SlorRB
+    :873-955, SlorRBP :1026-1133, SorRB :478-541, SorRBP :576-652.  With lCartesGrid false the right-hand side is
+    rebuilt from the current p where each routine says so."""
+    nx, ny, m = d.nx, d.ny, d.metrics
+    rau, rgv, rbu, rbv = m["rau"], m["rgv"], m["rbu"], m["rbv"]
+    div = d.new_field()
+    np_divergence(nx, ny, 1, m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, div)
+    b = np.zeros(d.mnx * d.mny)
+    rhs = lambda: np_rhsppe(nx, ny, cartes, d.dk, rbu, rbv, div, p, b)
+    ind = lambda i, j: (j - 2) * (nx - 1) + i - 2
+    coef = lambda i, j: (rgv[j - 1, i], rau[j, i - 1], -rau[j, i] - rau[j, i - 1] - rgv[j, i] - rgv[j - 1, i], rau[j, i], rgv[j, i])
+
+    def point(i, j):
+        a1, a2, a3, a4, a5 = coef(i, j)
+        s = b[ind(i, j)] - a1 * p[j - 1, i] - a2 * p[j, i - 1] - a4 * p[j, i + 1] - a5 * p[j + 1, i]
+        s = s / a3 - p[j, i]
+        p[j, i] = p[j, i] + d.sorrel * s
+        return abs(s)
+
+    def line(j):
+        al, bl = [], []
+        for i in range(2, nx + 1):
+            a1, a2, a3, a4, a5 = coef(i, j)
+            al.append([a2, a3, a4])
+            bl.append(b[ind(i, j)] - (a1 * p[j - 1, i] + a5 * p[j + 1, i]))
+        py_alttridlu(al, bl)
+        return bl
+    if cartes:
+        rhs()
+    for it in range(1, msorit + 1):
+        dif = 0.0
+        if solver == 1:
+            if not cartes: rhs()
+            for j in range(2, ny + 1):
+                for i in range(2, nx + 1):
+                    dif = max(dif, point(i, j))
+        elif solver in (5, 6):
+            if not cartes: rhs()
+            for par in (0, 1):                  # black: i starts at 2 + mod(j, 2); red: 2 + mod(j + 1, 2)
+                for j in range(2, ny + 1):
+                    for i in range(2 + (j + par) % 2, nx + 1, 2):
+                        dif = max(dif, point(i, j))
+        elif solver == 2:
+            if not cartes: rhs()
+            for j in range(2, ny + 1):
+                old = [p[j, i] for i in range(2, nx + 1)]
+                bl = line(j)
+                for k in range(nx - 1):
+                    s = bl[k] - old[k]
+                    p[j, 2 + k] = old[k] + d.sorrel * s
+                    dif = max(dif, abs(s))
+        elif solver == 3:
+            for k0 in (2, 3):
+                if not cartes: rhs()
+                for j in range(k0, ny + 1, 2):
+                    old = [p[j, i] for i in range(2, nx + 1)]
+                    bl = line(j)
+                    for k in range(nx - 1):
+                        s = bl[k] - old[k]
+                        p[j, 2 + k] = old[k] + d.sorrel * s
+                        dif = max(dif, abs(s))
+        else:                                   # 4: SlorRBP, relaxation after all lines of a colour are solved
+            pn = p.copy()
+            for k0 in (2, 3):
+                if not cartes: rhs()
+                for j in range(k0, ny + 1, 2):
+                    bl = line(j)
+                    for k in range(nx - 1):
+                        p[j, 2 + k] = bl[k]
+                for j in range(k0, ny + 1, 2):
+                    for i in range(2, nx + 1):
+                        p[j, i] = pn[j, i] + d.sorrel * (p[j, i] - pn[j, i])
+            dif = np.abs(pn[2:ny + 1, 2:nx + 1] - p[2:ny + 1, 2:nx + 1]).max()
+        if it > 1 and dif < d.sortol:
+            return it
+    return msorit
+
+
+@pytest.mark.parametrize("solver", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("cartes", [1, 0])
+def test_all_ppe_solvers_second_restatement(orc, solver, cartes):
+    """Every ppe_solver id through Ppe on a skewed grid, with the Cartesian flag on (right-hand side built once)
+    and off (rebuilt from the current iterate, cross-derivative terms included): iterate path, iteration count and
+    result bit for bit -- at 1 iteration, at a few, and to convergence."""
+    from wolfd2_b200 import deck as dk
+    x, y = dk.stretched_grid(22, 18)
+    d = dk._mk("skew", 22, 18, dk.RegionTables(22, 18), 100.0, 0.01, x=x, y=y, cartesian=bool(cartes))
+    d.sorrel, d.sortol = 1.25, 1e-8
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(20 + solver)
+    m, r = d.metrics, d.regions
+    assert np.abs(m["rbu"]).max() > 1e-4          # the grid really is non-orthogonal
+    u, v, p = rand_field(d, rng), rand_field(d, rng), rand_field(d, rng)
+    for msorit in (1, 4, 600):
+        po = p.copy()
+        nconv = orc.ppe(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, cartes, solver, msorit, d.dk, d.sortol, d.sorrel, m["rau"],
+                        m["rbu"], m["rbv"], m["rgv"], m["xeu"], m["yeu"], m["xzv"], m["yzv"], u, v, po)
+        pn = p.copy()
+        n = py_ppe_any_solver(d, solver, cartes, u, v, pn, msorit)
+        assert n == nconv, (msorit, n, nconv)
+        assert np.array_equal(pn, po), (msorit, np.abs(pn - po).max())
