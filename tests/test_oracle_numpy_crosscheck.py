@@ -1943,3 +1943,102 @@ def test_all_ppe_solvers_second_restatement(orc, solver, cartes):
         n = py_ppe_any_solver(d, solver, cartes, u, v, pn, msorit)
         assert n == nconv, (msorit, n, nconv)
         assert np.array_equal(pn, po), (msorit, np.abs(pn - po).max())
+
+
+# ------------------------------------------------------------------ SmlSclBC with outlets
+def py_smlsclbc(d, u, v, p, t):
+    """SmlSclBC in full (src/bound_cond.f:1257-1649): the wall / inlet branches of py_smlsclbc_walls plus the outlet
+    branches, as written (east OUTLT1 assigns u(iE+1,j) to itself; the south outlets write row jS-1)."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    O1, O2 = dk.BM_OUTLT1, dk.BM_OUTLT2
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            bd = lambda face: int(r.nMomBdTp[face - 1, jr, ir])
+            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
+                tp = bd(face)
+                if tp in (dk.BM_WALL1, dk.BM_WALL2, dk.BM_INLET):
+                    sgn = 1.0 if tp == dk.BM_WALL2 else -1.0
+                    if face == dk.WEST:
+                        u[jS:jN + 1, iW] = 0.0
+                        v[jS + 1:jN + 1, iW] = sgn * v[jS + 1:jN + 1, iW + 1]
+                    elif face == dk.EAST:
+                        u[jS:jN + 1, iE] = 0.0
+                        v[jS + 1:jN + 1, iE + 1] = sgn * v[jS + 1:jN + 1, iE]
+                    elif face == dk.SOUTH:
+                        u[jS, iW + 1:iE + 1] = sgn * u[jS + 1, iW + 1:iE + 1]
+                        v[jS, iW:iE + 1] = 0.0
+                    else:
+                        u[jN + 1, iW + 1:iE + 1] = sgn * u[jN, iW + 1:iE + 1]
+                        v[jN, iW:iE + 1] = 0.0
+                elif face == dk.WEST and tp == O1:
+                    for j in range(jS, jN + 1): u[j, iW - 1] = +u[j, iW]
+                    for j in range(jS + 1, jN + 1): v[j, iW] = -v[j, iW + 1]
+                elif face == dk.WEST and tp == O2:
+                    for j in range(jS, jN + 1): u[j, iW] = u[j, iW + 1] - v[j, iW] + v[j - 1, iW]
+                    for j in range(jS + 1, jN + 1):
+                        v[j, iW] = -v[j - 1, iW] + 5.0 * (v[j, iW + 1] - v[j - 1, iW + 1]) + 8.0 * (u[j, iW + 1] - u[j, iW])
+                elif face == dk.EAST and tp == O1:
+                    for j in range(jS + 1, jN + 1): v[j, iE + 1] = -v[j, iE]
+                elif face == dk.EAST and tp == O2:
+                    for j in range(jS + 1, jN + 1): u[j, iE] = u[j, iE - 1] - (v[j, iE] - v[j - 1, iE])
+                    for j in range(jS + 1, jN):
+                        v[j, iE + 1] = v[j - 1, iE + 1] + 3.0 * (v[j - 1, iE] - v[j, iE]) - 4.0 * (u[j, iE] - u[j, iE - 1])
+                elif face == dk.SOUTH and tp == O1:
+                    for i in range(iW + 1, iE + 1): u[jS, i] = -u[jS + 1, i]
+                    for i in range(iW, iE + 1): v[jS - 1, i] = +v[jS, i]
+                elif face == dk.SOUTH and tp == O2:
+                    for i in range(iW + 1, iE + 1):
+                        u[jS - 1, i] = u[jS - 1, i - 1] + 5.0 * (u[jS, i] - u[jS, i - 1]) + 8.0 * (v[jS, i] - v[jS - 1, i - 1])
+                    for i in range(iW, iE + 1): v[jS - 1, i] = v[jS, i] - u[jS, i] - u[jS, i - 1]
+                elif face == dk.NORTH and tp == O1:
+                    for i in range(iW + 1, iE + 1): u[jN + 1, i] = -u[jN, i]
+                    for i in range(iW, iE + 1): v[jN + 1, i] = +v[jN, i]
+                elif face == dk.NORTH and tp == O2:
+                    for i in range(iW, iE + 1): v[jN, i] = v[jN - 1, i] - (u[jN, i] - u[jN, i - 1])
+                    for i in range(iW + 1, iE):
+                        u[jN + 1, i] = u[jN + 1, i - 1] + 3.0 * (u[jN, i - 1] - u[jN, i]) - 4.0 * (v[jN, i] - v[jN - 1, i])
+    _smlscl_pt(d, p, t)
+
+
+def _smlscl_pt(d, p, t):
+    """PresBoundCond + the homogeneous temperature ghosts of SmlSclBC (:1480-1649)."""
+    from wolfd2_b200 import deck as dk
+    r = d.regions
+    py_presbc(d, p)
+    for jr in range(int(r.nReg[1])):
+        for ir in range(int(r.nReg[0])):
+            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+            if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                t[jS + 1:jN + 1, iW + 1:iE + 1] = 0.0
+                t[jS + 1:jN + 1, iW + 1] = -t[jS + 1:jN + 1, iW]
+                t[jS + 1:jN + 1, iE] = -t[jS + 1:jN + 1, iE + 1]
+                t[jS + 1, iW + 1:iE + 1] = -t[jS, iW + 1:iE + 1]
+                t[jN, iW + 1:iE + 1] = -t[jN + 1, iW + 1:iE + 1]
+                continue
+            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
+                bt = int(r.nTemBdTp[face - 1, jr, ir])
+                if bt == 0:
+                    continue
+                sgn = -1.0 if bt == 1 else 1.0
+                if face == dk.WEST: t[jS + 1:jN + 1, iW] = sgn * t[jS + 1:jN + 1, iW + 1]
+                elif face == dk.EAST: t[jS + 1:jN + 1, iE + 1] = sgn * t[jS + 1:jN + 1, iE]
+                elif face == dk.SOUTH: t[jS, iW + 1:iE + 1] = sgn * t[jS + 1, iW + 1:iE + 1]
+                else: t[jN + 1, iW + 1:iE + 1] = sgn * t[jN, iW + 1:iE + 1]
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_smlsclbc_second_restatement(orc, k):
+    """SmlSclBC on all six decks (every face type on every side): bit for bit."""
+    d = make_test_decks()[k]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(1200 + k)
+    r = d.regions
+    f = [rand_field(d, rng) for _ in range(4)]
+    a, b = [x.copy() for x in f], [x.copy() for x in f]
+    py_smlsclbc(d, *a)
+    orc.smlsclbc(d.nx, d.ny, r.nReg, r.nRegBrd, r.nRegType, r.nMomBdTp, r.nTRgType, r.nTemBdTp, r.dBCVal, *b)
+    for name, x, y in zip("uvpt", a, b):
+        assert np.array_equal(x, y), name
+    assert not np.array_equal(a[0], f[0])
