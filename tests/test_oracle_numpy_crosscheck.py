@@ -1275,58 +1275,6 @@ def py_filter_t(d, fp, qu):
     qu[:d.ny + 2, :d.nx + 2] = qh[:d.ny + 2, :d.nx + 2]
 
 
-def py_smlsclbc_walls(d, u, v, p, t):
-    """SmlSclBC (src/bound_cond.f:1257-1649) for decks whose outer faces are walls or inlets: homogeneous velocity
-    ghosts, PresBoundCond as it is, homogeneous temperature ghosts."""
-    from wolfd2_b200 import deck as dk
-    r = d.regions
-    for jr in range(int(r.nReg[1])):
-        for ir in range(int(r.nReg[0])):
-            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
-            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
-                tp = int(r.nMomBdTp[face - 1, jr, ir])
-                if tp == dk.BM_INTERN:
-                    continue
-                assert tp in (dk.BM_WALL1, dk.BM_WALL2, dk.BM_INLET), "outlets are not restated here"
-                sgn = 1.0 if tp == dk.BM_WALL2 else -1.0
-                if face == dk.WEST:
-                    u[jS:jN + 1, iW] = 0.0
-                    v[jS + 1:jN + 1, iW] = sgn * v[jS + 1:jN + 1, iW + 1]
-                elif face == dk.EAST:
-                    u[jS:jN + 1, iE] = 0.0
-                    v[jS + 1:jN + 1, iE + 1] = sgn * v[jS + 1:jN + 1, iE]
-                elif face == dk.SOUTH:
-                    u[jS, iW + 1:iE + 1] = sgn * u[jS + 1, iW + 1:iE + 1]
-                    v[jS, iW:iE + 1] = 0.0
-                else:
-                    u[jN + 1, iW + 1:iE + 1] = sgn * u[jN, iW + 1:iE + 1]
-                    v[jN, iW:iE + 1] = 0.0
-    py_presbc(d, p)
-    for jr in range(int(r.nReg[1])):
-        for ir in range(int(r.nReg[0])):
-            iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
-            if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
-                t[jS + 1:jN + 1, iW + 1:iE + 1] = 0.0
-                t[jS + 1:jN + 1, iW + 1] = -t[jS + 1:jN + 1, iW]
-                t[jS + 1:jN + 1, iE] = -t[jS + 1:jN + 1, iE + 1]
-                t[jS + 1, iW + 1:iE + 1] = -t[jS, iW + 1:iE + 1]
-                t[jN, iW + 1:iE + 1] = -t[jN + 1, iW + 1:iE + 1]
-                continue
-            for face in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH):
-                bt = int(r.nTemBdTp[face - 1, jr, ir])
-                if bt == 0:
-                    continue
-                sgn = -1.0 if bt == 1 else 1.0          # BT_TEMPER: mirror, BT_HTFLUX: copy
-                if face == dk.WEST:
-                    t[jS + 1:jN + 1, iW] = sgn * t[jS + 1:jN + 1, iW + 1]
-                elif face == dk.EAST:
-                    t[jS + 1:jN + 1, iE + 1] = sgn * t[jS + 1:jN + 1, iE]
-                elif face == dk.SOUTH:
-                    t[jS, iW + 1:iE + 1] = sgn * t[jS + 1, iW + 1:iE + 1]
-                else:
-                    t[jN + 1, iW + 1:iE + 1] = sgn * t[jN, iW + 1:iE + 1]
-
-
 class PySmallScale:
     """SmallScale (src/small_scale.f:160-581) with its `save`d state (map iterates, cell areas)."""
     AR, AM, RC = 4.82842712474, 1.47839783948, 0.20710678119
@@ -1477,16 +1425,16 @@ class PySmallScale:
                         if abs(uss[j, i]) < 1.0e-14: uss[j, i] = 0.0
                         if abs(vss[j, i]) < 1.0e-14: vss[j, i] = 0.0
                         if abs(tss[j, i]) < 1.0e-14: tss[j, i] = 0.0
-        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        py_smlsclbc(d, uss, vss, pss, tss)
         pss[0:ny + 1, 0:nx + 1] = 0.0
-        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        py_smlsclbc(d, uss, vss, pss, tss)
         sv = (d.msorit, d.sortol, d.sorrel)
         d.msorit, d.sortol, d.sorrel = d.ss_msorit, d.ss_sortol, d.ss_sorrel
         try:
             np_ppe_general(d, uss, vss, pss)
         finally:
             d.msorit, d.sortol, d.sorrel = sv
-        py_smlsclbc_walls(d, uss, vss, pss, tss)
+        py_smlsclbc(d, uss, vss, pss, tss)
         py_project(d, pss, uss, vss)
 
 
@@ -1511,16 +1459,19 @@ def _ss_decks():
     reg.heat_generation(1, 1, 2.0).fixed_temperature_region(2, 2, 0.7)
     reg.wall_temperature(1, 1, "w", 1.0).wall_heat_flux(1, 2, "w", 0.05).wall(1, 2, "n", tangent_vel=1.0)
     out.append(dk._mk("atd_thermal_2x2", 30, 26, reg, 900.0, 0.004, thermal=True, nmeiter=2, **kw))
+    reg = dk.RegionTables(30, 22, 2, 1, (14,), ())
+    reg.inlet(1, 1, "w", normal_vel=1.0).outlet(2, 1, "e", fully_dev=False).outlet(2, 1, "n", fully_dev=True)
+    out.append(dk._mk("atd_channel", 30, 22, reg, 700.0, 0.004, **kw))
     return out
 
 
-@pytest.mark.parametrize("k", range(2))
+@pytest.mark.parametrize("k", range(3))
 def test_smallscale_second_restatement(orc, k):
     """SmallScale through three calls (seeding, then two advances on changing fields): the high-pass filter, the
     per-cell chaotic-map model with pow / tanh / atanh from the same libm, the clamp nmap <= 50, `av` used for both
     velocity components (:505-506), the 1e-14 flush, SmlSclBC, the small-scale Ppe and projection -- uss, vss, pss,
-    tss and all nine saved map planes bit for bit.  Wall-bounded decks (cold cavity; thermal 2x2 with a heat source,
-    a fixed-temperature block, temperature and flux faces)."""
+    tss and all nine saved map planes bit for bit.  Cold cavity; thermal 2x2 deck with a heat source, a
+    fixed-temperature block, temperature and flux faces; channel with an inlet and both outlet types."""
     d = _ss_decks()[k]
     orc.config(d.mnx, d.mny)
     rng = np.random.default_rng(900 + k)
@@ -1947,8 +1898,9 @@ def test_all_ppe_solvers_second_restatement(orc, solver, cartes):
 
 # ------------------------------------------------------------------ SmlSclBC with outlets
 def py_smlsclbc(d, u, v, p, t):
-    """SmlSclBC in full (src/bound_cond.f:1257-1649): the wall / inlet branches of py_smlsclbc_walls plus the outlet
-    branches, as written (east OUTLT1 assigns u(iE+1,j) to itself; the south outlets write row jS-1)."""
+    """SmlSclBC (src/bound_cond.f:1257-1649): homogeneous velocity ghosts per face type, as written (east OUTLT1
+    assigns u(iE+1,j) to itself; the south outlets write row jS-1), then PresBoundCond and homogeneous temperature
+    ghosts."""
     from wolfd2_b200 import deck as dk
     r = d.regions
     O1, O2 = dk.BM_OUTLT1, dk.BM_OUTLT2
