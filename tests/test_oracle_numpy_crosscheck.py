@@ -1994,3 +1994,27 @@ def test_smlsclbc_second_restatement(orc, k):
     for name, x, y in zip("uvpt", a, b):
         assert np.array_equal(x, y), name
     assert not np.array_equal(a[0], f[0])
+
+
+def test_taveraged_second_restatement(orc):
+    """TAveraged (src/utility.f:699-736): node average of t; fixed-temperature regions take dTRgVal (large scales)
+    or zero (small scales); later regions overwrite shared border nodes."""
+    from wolfd2_b200 import deck as dk
+    d = _thermal_decks()[1]
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(77)
+    r = d.regions
+    t = rand_field(d, rng)
+    for nscale in (0, 1):
+        s = rand_field(d, rng)
+        a, b = s.copy(), s.copy()
+        for jr in range(int(r.nReg[1])):
+            for ir in range(int(r.nReg[0])):
+                iW, iE, jS, jN = (int(r.nRegBrd[k - 1, jr, ir]) for k in (dk.WEST, dk.EAST, dk.SOUTH, dk.NORTH))
+                if int(r.nTRgType[jr, ir]) == dk.RT_TEMPER:
+                    a[jS:jN + 1, iW:iE + 1] = r.dTRgVal[jr, ir] if nscale == 0 else 0.0
+                    continue
+                W = Rng(iW, iE, jS, jN)
+                W.put(a, (W(t) + W(t, 0, 1) + W(t, 1, 1) + W(t, 1, 0)) / 4.0)
+        orc.taveraged(d.nx, d.ny, nscale, r.nReg, r.nRegBrd, r.nTRgType, r.dTRgVal, t, b)
+        assert np.array_equal(a, b) and not np.array_equal(a, s), nscale
