@@ -226,6 +226,39 @@ def test_cavity_matches_ghia_at_doubled_reynolds(orc):
 
 
 @pytest.mark.slow
+def test_cavity_matches_ghia_re400_at_nominal_200(orc):
+    """The same check one octave up: Ghia, Ghia & Shin's Re=400 centreline profile is reproduced by a deck with
+    Re=200 (convection counted twice, see above), not by one with Re=400.  At this Reynolds number the O(dt)
+    splitting error of the steady state is visible (Poiseuille pin): the profile is extrapolated to
+    dt = 0 from dt = 0.2 h and 0.1 h.  40^2 grid: 0.023 against 0.118 (64^2 with dt -> 0: 0.007)."""
+    n = 40
+    h = 1.0 / (n - 1)
+    gy = [0.9766, 0.9688, 0.9609, 0.9531, 0.8516, 0.7344, 0.6172, 0.5, 0.4531, 0.2813, 0.1719, 0.1016, 0.0703, 0.0625, 0.0547]
+    gu = np.array([0.75837, 0.68439, 0.61756, 0.55892, 0.29093, 0.16256, 0.02135, -0.11477, -0.17119, -0.32726, -0.24299,
+                   -0.14612, -0.10338, -0.09266, -0.08186])
+    err = {}
+    for re in (200.0, 400.0):
+        prof = {}
+        for dtf in (0.2, 0.1):
+            d = dk.cavity(n, re=re, dt=dtf * h)
+            d.sorrel, d.sortol = 2.0 / (1.0 + np.sin(np.pi * h)), 1e-7
+            u, v, p = d.new_field(), d.new_field(), d.new_field()
+            orc.coldstart(d, u, v, p)
+            for _ in range(300):
+                rc, lg = orc.step(d, u, v, p, 100)
+                assert rc == 0
+                if max(lg[-1]["dif"][1:3]) < 2e-7:
+                    break
+            xi = (np.arange(d.nx + 2) - 1.0) * h
+            yc = (np.arange(d.ny + 2) - 1.5) * h
+            col = np.array([np.interp(0.5, xi[1:d.nx + 1], u[j, 1:d.nx + 1]) for j in range(d.ny + 2)])
+            prof[dtf] = np.array([np.interp(y, yc[1:d.ny + 2], col[1:d.ny + 2]) for y in gy])
+        err[re] = np.abs(2.0 * prof[0.1] - prof[0.2] - gu).max()
+    assert err[200.0] < 0.03
+    assert err[400.0] > 0.09
+
+
+@pytest.mark.slow
 def test_poiseuille_channel_converges_to_the_discrete_parabola(orc):
     """Plane channel 6 x 1, uniform inlet (`inlet 1 1 w normal_vel 1`), `outlet 1 1 e mass_cons`, no-slip walls, Re = 1.
     Far from both ends the flow is fully developed: convection vanishes (so the doubled convection of DConvU does
