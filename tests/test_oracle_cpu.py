@@ -302,6 +302,40 @@ def test_poiseuille_channel_converges_to_the_discrete_parabola(orc):
     assert abs(g0 + 2.0 * c) < 1e-6
 
 
+def test_natural_convection_matches_de_vahl_davis_ra1000(orc):
+    """Differentially heated square cavity, Pr = 0.71, Ra = 10^3: de Vahl Davis' benchmark solution (1983) has a
+    mean Nusselt number of 1.118 and mid-plane velocity maxima of 3.649 (u on x = 1/2) and 3.697 (v on y = 1/2) in
+    units of alpha/L.  Here the buoyancy comes from the ideal-gas EqState with (Tmax - Tref)/Tref = 1/30 (close to
+    Boussinesq), Ra = (dT/T) Re^2 Pr / Fr, and the steady state is reached through the momentum-energy iterations.
+    24^2 grid: Nu = 1.115 on BOTH walls (energy conservation), u_max = 3.54, v_max = 3.59.  At this Rayleigh number
+    inertia is negligible, so the doubled momentum convection does not matter (at Ra = 10^4 it costs 2 % in Nu: 2.20
+    against 2.243).  Pins ThermEnergy, TempBoundCond, EqState, the buoyancy term of YMomentum and their coupling."""
+    n, ra, re, pr = 24, 1.0e3, 10.0, 0.71
+    h = 1.0 / (n - 1)
+    eps = (310.0 - 300.0) / 300.0
+    fr = eps * re * re * pr / ra
+    uref = np.sqrt(fr * 9.81)
+    dt_nd = 0.05 * re * pr * h * h
+    d = dk.heated_cavity(n, re=re, dt=dt_nd / uref, uref=uref, nmeiter=3)
+    d.sorrel, d.sortol, d.msorit = 2.0 / (1.0 + np.sin(np.pi * h)), 1e-8, 2000
+    assert abs(d.fr - fr) < 1e-12 * fr and abs(d.dk - dt_nd) < 1e-15 and abs(d.pe - re * pr) < 1e-12
+    u, v, p, t, den = (d.new_field() for _ in range(5))
+    t[:d.ny + 2, :d.nx + 2] = 0.5
+    orc.coldstart(d, u, v, p)
+    for _ in range(100):
+        rc, lg = orc.step(d, u, v, p, 100, t=t, d=den)
+        assert rc == 0
+        if max(lg[-1]["dif"][1:4]) < 2e-8:
+            break
+    nu_w = ((1.0 - t[2:n + 1, 2]) / (0.5 * h)).mean()          # wall value 1, first cell centre h/2 away
+    nu_e = ((t[2:n + 1, n] - 0.0) / (0.5 * h)).mean()
+    xi = (np.arange(n + 2) - 1.0) * h
+    umax = np.abs([np.interp(0.5, xi[1:n + 1], u[j, 1:n + 1]) for j in range(n + 2)]).max() * re * pr
+    vmax = np.abs([np.interp(0.5, xi[1:n + 1], v[1:n + 1, i]) for i in range(n + 2)]).max() * re * pr
+    assert abs(nu_w - 1.118) < 0.006 and abs(nu_w - nu_e) < 2e-5
+    assert abs(umax - 3.649) < 0.15 and abs(vmax - 3.697) < 0.15
+
+
 # ------------------------------------------------------------------ regression fixtures
 @pytest.mark.parametrize("name", ["cavity24x20", "channel22x18_fd", "channel22x18_mc", "bstep26x20", "heated_cavity26x22"])
 def test_oracle_reproduces_golden_fixtures(orc, name):
