@@ -17,8 +17,9 @@
  * text (tests/test_oracle_numpy_crosscheck.py), reproduces every routine of the
  * cold-flow path, the thermal row, SmallScale and Traject, whole time steps included,
  * bit for bit;
- * two physical pins (Ghia's cavity, plane Poiseuille flow) and the analytic
- * conduction solutions check the physics (tests/test_oracle_cpu.py).
+ * physical pins (Ghia's cavity at two Reynolds numbers, plane Poiseuille flow, de Vahl
+ * Davis' natural convection, analytic conduction) check the physics
+ * (tests/test_oracle_cpu.py).
  *
  * Each function cites the reference file:line it follows (paths relative to the
  * reference tree).  Fortran `stop` becomes: set orc_errflag and return.
