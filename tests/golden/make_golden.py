@@ -3,7 +3,8 @@
 The reference ships no golden vectors and cannot be built here (no Fortran compiler), so these fixtures
 are REGRESSION PINS of the oracle (oracle/wolfd2_oracle.c at -O2 -ffp-contract=off), not outputs of the
 reference.  They let the GPU tests check the CUDA path against committed numbers and catch any later
-drift of the oracle itself.   Run:  python tests/golden/make_golden.py
+drift of the oracle itself.  tests/test_oracle_numpy_crosscheck.py reproduces every fixture bit for bit with the second
+(numpy / Python) restatement, without calling the oracle.   Run:  python tests/golden/make_golden.py
 """
 import os
 import sys
