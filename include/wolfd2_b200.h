@@ -216,6 +216,11 @@ int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
 int wolfd2_b200_download_field(wolfd2_ctx *ctx, int32_t which, double *host);
+/* Rows jfirst..jfirst+nrows-1 (global row indices, within the rows the context holds) of metric array `which`
+ * (0-based position in wolfd2_metrics) from a host block of nrows x (mnx+1) doubles: lets the host build the metrics
+ * of a large grid window by window (src/grid.f:368-535 is a local formula of the node rows j-2..j+2) and pass NULL
+ * metric pointers to wolfd2_b200_create. */
+int wolfd2_b200_upload_metric_rows(wolfd2_ctx *ctx, int32_t which, int32_t jfirst, int32_t nrows, const double *host);
 
 /* Cold-start projection, src/main.f:606-641. */
 int wolfd2_b200_coldstart(wolfd2_ctx *ctx, int32_t *nSorConv);
@@ -257,6 +262,12 @@ int wolfd2_b200_comm_init(int32_t rank, int32_t world, const unsigned char id[12
 int wolfd2_b200_comm_finalize(void);
 int wolfd2_b200_create_slab(wolfd2_ctx **out, const wolfd2_params *par, const wolfd2_regions *reg,
                             const wolfd2_metrics *met, int32_t rank, int32_t world);
+/* Verification of a slab run against one GPU (collective over the ranks): gather_global copies every rank's rows of
+ * the 30 metric arrays (what & 1) and of u, v, p (what & 2) into `global`, a one-GPU context of the same grid on rank
+ * 0's device (NULL on the other ranks); compare_global gathers field `which` of the slab run and counts the cells
+ * 0..nx+1 x 0..ny+1 whose bit patterns differ from `global`'s own field (results on rank 0). */
+int wolfd2_b200_gather_global(wolfd2_ctx *slab, wolfd2_ctx *global, int32_t what);
+int wolfd2_b200_compare_global(wolfd2_ctx *slab, wolfd2_ctx *global, int32_t which, uint64_t *ndiff, double *maxabs);
 
 /* ---- (1) literal shims: gfortran ABI of the reference subroutines --------------- */
 

@@ -150,3 +150,23 @@ def test_gloo_world2_halo_rows_reassemble_the_global_field():
     port = 29100 + (os.getpid() % 500)
     mp.spawn(_halo_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)
+
+
+def test_metric_windows_of_any_size_are_the_global_rows():
+    """api.Context.stream_uniform_metrics uploads deck.metrics_window chunk by chunk: every window, down to a single
+    row and including the physical edge rows 0 and ny+1, must reproduce the global arrays bit for bit."""
+    import numpy as np
+    from wolfd2_b200 import deck
+    from wolfd2_b200._abi import METRIC_NAMES
+    nx, ny = 41, 53
+    g = deck.cavity(nx, ny=ny, re=100.0)
+    for chunk in (1, 2, 5, 16, 60):
+        for j0 in range(0, ny + 2, chunk):
+            j1 = min(ny + 1, j0 + chunk - 1)
+            w = deck.metrics_window(nx, ny, j0, j1, g.mnx)
+            for k in METRIC_NAMES:
+                assert np.array_equal(w[k], g.metrics[k][j0:j1 + 1, :]), (chunk, j0, k)
+    lazy = deck.cavity(nx, ny=ny, re=100.0, lazy_metrics=True)
+    assert lazy.metrics == {} and lazy.nx == nx and lazy.mny == g.mny
+    m = lazy.metrics_struct()
+    assert all(not getattr(m, k) for k in METRIC_NAMES)       # NULL pointers: nothing uploaded at create

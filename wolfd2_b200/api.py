@@ -65,6 +65,9 @@ def lib():
     L.wolfd2_b200_node_averages.argtypes = [C.c_void_p, C.c_int32] + [c_f64p] * 4
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
+    L.wolfd2_b200_upload_metric_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_f64p]
+    L.wolfd2_b200_gather_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.wolfd2_b200_compare_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.wolfd2_b200_coldstart.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     L.wolfd2_b200_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(StepLog)]
     L.wolfd2_b200_step_host.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_f64p, c_f64p, C.POINTER(StepLog)]
@@ -142,7 +145,7 @@ RhsPpe = _routine("rhsppe")
 class Context:
     """Device-resident run: what `program wolfd2` holds after set-up, living in HBM."""
 
-    def __init__(self, deck):
+    def __init__(self, deck, stream_metrics=True):
         L = lib()
         self.deck = deck
         config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
@@ -156,6 +159,9 @@ class Context:
             _check(L.wolfd2_b200_create(C.byref(h), C.byref(self._par), C.byref(self._reg), C.byref(self._met)),
                    "wolfd2_b200_create")
         self._h = h
+        if not deck.metrics and stream_metrics:   # uniform grid, metrics built and uploaded window by window
+            # (stream_metrics=False: the caller fills them, e.g. Context.gather_global)
+            self.stream_uniform_metrics()
         if getattr(deck, "thermal", False) or getattr(deck, "smallscale", False):
             self._th = deck.thermal_struct()   # cold ATD runs still need the thermal region tables
             _check(L.wolfd2_b200_set_thermal(h, C.byref(self._th)), "wolfd2_b200_set_thermal")
@@ -224,6 +230,42 @@ class Context:
         ptr = [q.ctypes.data_as(c_f64p) for q in out] + ([] if temperature else [None])
         _check(lib().wolfd2_b200_node_averages(self._h, 1 if small_scale else 0, *ptr), "wolfd2_b200_node_averages")
         return tuple(out)
+
+    def stream_uniform_metrics(self, chunk_rows=None, threads=None):
+        """Metric arrays of a uniform grid, built by deck.metrics_window in windows of chunk_rows rows (several
+        windows at a time on host threads: numpy releases the GIL) and uploaded with wolfd2_b200_upload_metric_rows.
+        Bit-identical to the global arrays (tests/test_slab_cpu.py); the host never holds more than a few windows."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import deck as dk
+        d = self.deck
+        a0, a1 = (d.slab[4], d.slab[5]) if d.slab else (0, d.ny + 1)
+        if chunk_rows is None:
+            chunk_rows = max(16, min(512, (1 << 22) // (d.nx + 2)))     # ~32 MB per array window
+        if threads is None:
+            threads = max(1, min(8, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        wins = [(j, min(a1, j + chunk_rows - 1)) for j in range(a0, a1 + 1, chunk_rows)]
+        L = lib()
+
+        def build(w):
+            return w, dk.metrics_window(d.nx, d.ny, w[0], w[1], d.mnx, d.dlref)
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            for (j0, j1), m in ex.map(build, wins):
+                for k, name in enumerate(_abi.METRIC_NAMES):
+                    _check(L.wolfd2_b200_upload_metric_rows(self._h, k, j0, j1 - j0 + 1, m[name].ctypes.data_as(c_f64p)),
+                           "wolfd2_b200_upload_metric_rows")
+
+    def gather_global(self, glob, metrics=True, fields=True):
+        """Slab context: collect every rank's rows into the one-GPU context `glob` on rank 0 (None elsewhere)."""
+        _check(lib().wolfd2_b200_gather_global(self._h, glob._h if glob is not None else None,
+                                               (1 if metrics else 0) | (2 if fields else 0)), "wolfd2_b200_gather_global")
+
+    def compare_global(self, glob, which):
+        """(cells whose bit patterns differ, max |difference|) of field `which`: slab run vs `glob` (rank 0)."""
+        n, m = C.c_uint64(0), C.c_double(0.0)
+        _check(lib().wolfd2_b200_compare_global(self._h, glob._h if glob is not None else None, which, C.byref(n), C.byref(m)),
+               "wolfd2_b200_compare_global")
+        return int(n.value), float(m.value)
 
     def upload(self, which, arr):
         assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]

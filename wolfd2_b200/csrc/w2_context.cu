@@ -67,6 +67,18 @@ static int balloc(wolfd2_ctx *c, unsigned char **p, size_t planes) {
     *p -= c->row_off;
     return W2_OK;
 }
+// chain-layout work arrays of the line solvers (ppe_solver 2-4) and of the alttridlu_ / rhsppe_ shims: allocated on
+// first use (five full-size arrays: 10.7 GB at 16384^2 that the point-SOR path never touches)
+int w2_ensure_chain(wolfd2_ctx *c) {
+    if (c->tx) return W2_OK;
+    const long long nmax = ((long long)c->nx * (long long)c->ny / 4096 + 3) * 4096;
+    W2_TRY(dalloc(&c->ta, (size_t)nmax));
+    W2_TRY(dalloc(&c->td, (size_t)nmax));
+    W2_TRY(dalloc(&c->tc, (size_t)nmax));
+    W2_TRY(dalloc(&c->tb, (size_t)nmax));
+    W2_TRY(dalloc(&c->tx, (size_t)nmax));
+    return W2_OK;
+}
 int w2_alloc_pormap(wolfd2_ctx *c) { return c->pormap ? W2_OK : balloc(c, &c->pormap, 6); }
 int w2_alloc_field(wolfd2_ctx *c, double **p) { return falloc(c, p); }
 static void ffree(wolfd2_ctx *c, double *p) { if (p) cudaFree(p + c->row_off); }
@@ -161,6 +173,8 @@ int w2_ctx_set_regions(wolfd2_ctx *c, const W2Regions *r) {
     return W2_OK;
 }
 
+static int ctx_create_body(wolfd2_ctx *c, int nx, int ny, int rank, int world, const int32_t *lay);
+
 int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     *out = nullptr;
     W2_TRY(check_device());
@@ -177,6 +191,14 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     }
     wolfd2_ctx *c = (wolfd2_ctx *)calloc(1, sizeof(wolfd2_ctx));
     if (!c) return W2_ERR_BAD_ARG;
+    // a half-built context (e.g. out of memory at 16384^2) is torn down again: destroy copes with null members
+    const int rc = ctx_create_body(c, nx, ny, rank, world, lay);
+    if (rc != W2_OK) { wolfd2_b200_destroy(c); return rc; }
+    *out = c;
+    return W2_OK;
+}
+
+static int ctx_create_body(wolfd2_ctx *c, int nx, int ny, int rank, int world, const int32_t *lay) {
     c->device = g_device;
     c->nx = nx; c->ny = ny; c->mnx = g_mnx; c->mny = g_mny;
     c->pitch = ((nx + 2 + 15) / 16) * 16;
@@ -193,7 +215,6 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     c->coop_ok = prop.cooperativeLaunch;
     if (prop.major < 10) {
         w2_set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
-        free(c);
         return W2_ERR_NO_DEVICE;
     }
     W2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -217,13 +238,6 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     c->th.pe = 1.0;
     // chain arrays are read in whole segments by the tridiagonal solver: pad generously
     const long long nmax = ((long long)nx * (long long)ny / 4096 + 3) * 4096;
-    if (world == 1) {   // chain-layout work of the line solvers and of the AltTridLU shim (one GPU only)
-        W2_TRY(dalloc(&c->ta, (size_t)nmax));
-        W2_TRY(dalloc(&c->td, (size_t)nmax));
-        W2_TRY(dalloc(&c->tc, (size_t)nmax));
-        W2_TRY(dalloc(&c->tb, (size_t)nmax));
-        W2_TRY(dalloc(&c->tx, (size_t)nmax));
-    }
     // level-0 spike arrays hold only this rank's segments; the segment table and upper levels are global
     const long long cap0 = world == 1 ? nmax : (long long)(c->rows + 2) * nx + 3 * 2048;
     W2_TRY(w2_tri_prepare(c, nmax, cap0));
@@ -233,14 +247,13 @@ int w2_ctx_create_raw(wolfd2_ctx **out, int nx, int ny, int rank, int world) {
     W2_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     W2_CUDA(cudaMallocHost((void **)&c->h_norm, 64 * sizeof(unsigned long long)));
     W2_CUDA(cudaMallocHost((void **)&c->h_flags, 64 * sizeof(int)));
-    *out = c;
     return W2_OK;
 }
 
 extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     w2_atd_release(c);
     w2_traj_release(c);
     double **mp = &c->met.rau;
@@ -256,10 +269,10 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);
     cudaFreeHost(c->h_norm); cudaFreeHost(c->h_flags);
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    for (int k = 0; k < 8; ++k) cudaEventDestroy(c->ev[k]);
-    cudaEventDestroy(c->ev_p);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->ev_p) cudaEventDestroy(c->ev_p);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     free(c);
 }
 
@@ -355,6 +368,24 @@ extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const doub
     W2_TRY(w2_upload2d(c, c->fld[which], host));
     if (which == W2_F_D || which == W2_F_DN) c->dn_valid = 0;
     W2_CUDA(cudaStreamSynchronize(c->stream));
+    return W2_OK;
+}
+// Rows jfirst .. jfirst+nrows-1 (GLOBAL row indices, inside the rows this context holds) of metric array `which`
+// (0-based position in wolfd2_metrics) from a host block of nrows x (mnx+1) doubles.  Lets a caller build the
+// metrics of a large grid window by window instead of holding 30 full arrays on the host (16384^2: 64 GB).
+extern "C" int wolfd2_b200_upload_metric_rows(wolfd2_ctx *c, int32_t which, int32_t jfirst, int32_t nrows, const double *host) {
+    if (!c || !host || which < 0 || which >= 30 || nrows < 0) return W2_ERR_BAD_ARG;
+    if (jfirst < c->A0 || jfirst + nrows - 1 > c->A1) {
+        w2_set_error("upload_metric_rows: rows %d..%d outside the rows %d..%d held by this context", jfirst, jfirst + nrows - 1, c->A0, c->A1);
+        return W2_ERR_BAD_ARG;
+    }
+    if (nrows == 0) return W2_OK;
+    W2_CUDA(cudaSetDevice(c->device));
+    double *dev = (&c->met.rau)[which];
+    if (dev == c->met.rau || dev == c->met.rgv) c->sorf_met_valid = 0;
+    W2_CUDA(cudaMemcpy2DAsync(dev + (size_t)c->pitch * (size_t)jfirst, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
+                              (size_t)(c->nx + 2) * 8, (size_t)nrows, cudaMemcpyHostToDevice, c->stream));
+    W2_CUDA(cudaStreamSynchronize(c->stream));   // the caller reuses the host block
     return W2_OK;
 }
 extern "C" int wolfd2_b200_download_field(wolfd2_ctx *c, int32_t which, double *host) {

@@ -218,3 +218,92 @@ void w2_peer_release(wolfd2_ctx *c) {
     if (P.state == 1) cudaFree(P.mail[c->rank]);
     memset(&P, 0, sizeof(P));
 }
+
+// ---- verification plumbing: a slab run collected into ONE global context on rank 0 ---------------------------
+// bench.py and the multi-GPU tests use this to run the same grid on one GPU from the same state and compare the
+// fields bit for bit.  Rank r contributes the rows it updates (E0..E1: its unknown rows
+// plus the physical ghost rows of the first / last rank), so together the ranks cover rows 0..ny+1 exactly once.
+static int gather_array(wolfd2_ctx *s, double *src, double *dst /* rank 0: global array, global row indexing */) {
+    const size_t pitch = (size_t)s->pitch;
+    if (s->rank == 0) {
+        W2_CUDA(cudaMemcpyAsync(dst + pitch * (size_t)s->E0, src + pitch * (size_t)s->E0,
+                                pitch * (size_t)(s->E1 - s->E0 + 1) * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        W2_NCCL(N.GroupStart());
+        for (int r = 1; r < s->world; ++r) {
+            int J0, J1, A0, A1, HG;
+            w2_slab_layout(s->nx, s->ny, s->world, r, &J0, &J1, &A0, &A1, &HG);
+            const int e0 = J0, e1 = r == s->world - 1 ? s->ny + 1 : J1;
+            W2_NCCL(N.Recv(dst + pitch * (size_t)e0, pitch * (size_t)(e1 - e0 + 1), ncclDouble, r, g_comm, s->stream));
+        }
+        W2_NCCL(N.GroupEnd());
+    } else {
+        W2_NCCL(N.Send(src + pitch * (size_t)s->E0, pitch * (size_t)(s->E1 - s->E0 + 1), ncclDouble, 0, g_comm, s->stream));
+    }
+    return W2_OK;
+}
+
+static int gather_check(wolfd2_ctx *s, wolfd2_ctx *g) {
+    if (!s || s->world < 2 || s->world != g_world || s->rank != g_rank) { w2_set_error("gather: not a slab context of the current communicator"); return W2_ERR_BAD_ARG; }
+    if (s->rank == 0 && (!g || g->world != 1 || g->nx != s->nx || g->ny != s->ny || g->device != s->device)) {
+        w2_set_error("gather: rank 0 needs a one-GPU context of the same %dx%d grid on the same device", s->nx, s->ny);
+        return W2_ERR_BAD_ARG;
+    }
+    return W2_OK;
+}
+
+extern "C" int wolfd2_b200_gather_global(wolfd2_ctx *s, wolfd2_ctx *g, int32_t what) {
+    W2_TRY(gather_check(s, g));
+    W2_CUDA(cudaSetDevice(s->device));
+    if (g) W2_CUDA(cudaStreamSynchronize(g->stream));
+    if (what & 1) {
+        double **sp = &s->met.rau, **gp = g ? &g->met.rau : nullptr;
+        for (int k = 0; k < 30; ++k) W2_TRY(gather_array(s, sp[k], gp ? gp[k] : nullptr));
+        if (g) g->sorf_met_valid = 0;
+    }
+    if (what & 2)
+        for (int k = W2_F_U; k <= W2_F_P; ++k) W2_TRY(gather_array(s, s->fld[k], g ? g->fld[k] : nullptr));
+    W2_CUDA(cudaStreamSynchronize(s->stream));
+    return W2_OK;
+}
+
+__global__ void __launch_bounds__(256) field_compare_kernel(int nx, int ny, int pitch, const double *__restrict__ a,
+                                                            const double *__restrict__ b, unsigned long long *out) {
+    __shared__ double red[32];
+    unsigned long long nd = 0;
+    double mx = 0.0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nx + 1)
+        for (int j = blockIdx.y; j <= ny + 1; j += gridDim.y) {
+            const double x = a[IDX(i, j)], y = b[IDX(i, j)];
+            if (__double_as_longlong(x) != __double_as_longlong(y)) { ++nd; const double d = fabs(x - y); mx = d == d ? fmax(mx, d) : 1.0e300; }
+        }
+    mx = w2_block_max(mx, red);
+    if (threadIdx.x == 0 && mx > 0.0) atomicMax(out + 1, w2_dbits(mx));
+    if (nd) atomicAdd(out, nd);
+}
+
+// Field `which` of the slab run against the same field of the one-GPU context: number of cells (0..nx+1, 0..ny+1)
+// whose bit patterns differ and the largest |difference|.  Results on rank 0 (zeros elsewhere).
+extern "C" int wolfd2_b200_compare_global(wolfd2_ctx *s, wolfd2_ctx *g, int32_t which, uint64_t *ndiff, double *maxabs) {
+    W2_TRY(gather_check(s, g));
+    if (which < 0 || which >= W2_F_CORE) return W2_ERR_BAD_ARG;
+    W2_CUDA(cudaSetDevice(s->device));
+    if (g) W2_CUDA(cudaStreamSynchronize(g->stream));
+    W2_TRY(gather_array(s, s->fld[which], g ? g->div : nullptr));   // div is rebuilt by every Ppe: free as scratch
+    if (ndiff) *ndiff = 0;
+    if (maxabs) *maxabs = 0.0;
+    if (g) {
+        W2_CUDA(cudaMemsetAsync(g->d_norm + 32, 0, 16, s->stream));
+        dim3 grid((g->nx + 2 + 255) / 256, g->ny + 2 < 1024 ? g->ny + 2 : 1024);
+        field_compare_kernel<<<grid, 256, 0, s->stream>>>(g->nx, g->ny, g->pitch, g->div, g->fld[which], g->d_norm + 32);
+        W2_CUDA(cudaGetLastError());
+        unsigned long long h[2];
+        W2_CUDA(cudaMemcpyAsync(h, g->d_norm + 32, 16, cudaMemcpyDeviceToHost, s->stream));
+        W2_CUDA(cudaStreamSynchronize(s->stream));
+        if (ndiff) *ndiff = h[0];
+        if (maxabs) memcpy(maxabs, &h[1], 8);
+    } else {
+        W2_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return W2_OK;
+}

@@ -430,11 +430,11 @@ static int mom_tail_exchange(wolfd2_ctx *c, double *out) {
 
 template <int COMP, int STEP, bool POR>
 static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
-    static bool attr = false;
+    static bool attr[W2_MAXDEV] = {};   // the attribute is per device: one flag per device id
     const size_t smem = (size_t)4 * MR_LEN * sizeof(double);
-    if (!attr) {
+    if (!attr[c->device % W2_MAXDEV]) {
         W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, POR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr[c->device % W2_MAXDEV] = true;
     }
     W2TriWork &w = c->tri;
     const long long nseg = (n + TRI_S - 1) / TRI_S;

@@ -99,6 +99,7 @@ int w2_ppe_line_sor(wolfd2_ctx *c, double *p, int *nSorConv, int *converged, int
     a.nx = nx; a.ny = ny; a.pitch = c->pitch; a.sorrel = par.sorrel;
     a.rau = c->met.rau; a.rgv = c->met.rgv; a.b = c->fld[W2_F_B];
     a.mask = c->pmask; a.has_mask = c->hreg.has_blockage;
+    W2_TRY(w2_ensure_chain(c));
     a.p = p; a.ta = c->ta; a.td = c->td; a.tc = c->tc; a.tb = c->tb; a.x = c->tx;
     a.slot = c->d_norm + 12;
     a.relaxed_norm = par.nPpeSolver == W2_PPE_PAR_RB_LSOR;

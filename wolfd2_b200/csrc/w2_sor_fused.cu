@@ -465,10 +465,10 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     const size_t smem = SorFCfg<T>::smem;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[W2_MAXDEV] = {};   // per device
+    if (!attr_set[c->device % W2_MAXDEV]) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[c->device % W2_MAXDEV] = true;
     }
     sor_rb_fused_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
     return W2_OK;

@@ -51,7 +51,9 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         W2_TRY(w2_copy_field(c, a->tsn, tss));
         W2_TRY(w2_axpy3(c, +1.0, un, uss, vn, vss, tn, tss));
     }
-    if (thermal || !c->dn_valid) { W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D])); c->dn_valid = 1; }
+    // d changes through EqState, which runs whenever neqstate == 1 -- with or without the energy equation (:853)
+    const bool eqstate = c->th.neqstate == 1;
+    if (thermal || eqstate || !c->dn_valid) { W2_TRY(w2_copy_field(c, c->fld[W2_F_DN], c->fld[W2_F_D])); c->dn_valid = 1; }
     int nme = c->par.nmeiter;
     if (!thermal && nme > 0) nme = 1;                        // :736
     int nQL = -1, nSor = 0, conv = 0;
@@ -83,7 +85,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         W2_TRY(w2_vel_bc(c, us, vs));                   // :829
         W2_TRY(w2_pres_bc(c, p));                       // :833
         if (thermal) W2_TRY(w2_thermenergy(c, ts));     // :840-850
-        if (thermal && c->th.neqstate == 1) W2_TRY(w2_eqstate(c, p, ts, c->fld[W2_F_D]));   // :853-855
+        if (eqstate) W2_TRY(w2_eqstate(c, p, ts, c->fld[W2_F_D]));   // :853-855 (not gated on thermal_energy)
         double dme[3] = {0, 0, 0};
         if (nme > 1) {                                  // :857-859 (only the l > 1 test reads them)
             W2_TRY(w2_norm_reset(c));
@@ -114,6 +116,9 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     W2_TRY(w2_diffmaxnorm_async(c, un, u, 1));
     W2_TRY(w2_diffmaxnorm_async(c, vn, v, 2));
     if (thermal || atd) W2_TRY(w2_diffmaxnorm_async(c, tn, t, 3));
+    // :1000-1024; enqueued before the closing event so that the step time includes the particle integration
+    // (the norms above do not depend on it; after a divergence abort the particle state is as undefined as the fields)
+    if (c->traj && c->traj->active) W2_TRY(w2_traject_step(c));
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
     W2_TRY(w2_norm_fetch(c, thermal || atd ? 4 : 3, dif)); // syncs the stream
@@ -137,7 +142,6 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         w2_set_error("* Solution diverged. Please reduce CFL number.");   // :970
         return W2_ERR_DIVERGED;
     }
-    if (c->traj && c->traj->active) W2_TRY(w2_traject_step(c));   // :1000-1024
     return W2_OK;
 }
 
@@ -410,6 +414,7 @@ extern "C" void alttridlu_(const int32_t *n_, double *a, double *b) {
     while ((long long)side * side < n + 8) side += 8;
     if (g_mnx < side + 1 || g_mny < side + 1) { w2_set_error("alttridlu_: n=%lld needs mnx,mny >= %d (wolfd2_b200_config)", n, side + 1); die(who); }
     wolfd2_ctx *c = shim_ctx(side, side, who);
+    SHIM_TRY(w2_ensure_chain(c), who);
     double *tmp = nullptr;  // AoS staging
     if (cudaMalloc((void **)&tmp, 3 * n * sizeof(double)) != cudaSuccess) { w2_set_error("alttridlu_: out of device memory"); die(who); }
     cudaMemcpyAsync(tmp, a, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -611,6 +616,7 @@ extern "C" void rhsppe_(const int32_t *nx, const int32_t *ny, const int32_t *lCa
                         const double *rbv, const double *div, const double *p, double *b) {
     const char *who = "rhsppe_";
     wolfd2_ctx *c = shim_ctx(*nx, *ny, who);
+    SHIM_TRY(w2_ensure_chain(c), who);
     up(c, c->met.rbu, rbu, who); up(c, c->met.rbv, rbv, who); up(c, c->div, div, who); up(c, c->fld[W2_F_P], p, who);
     SHIM_TRY(w2_unit_rhsppe(c, *lCartesGrid != 0, *dk, c->met.rbu, c->met.rbv, c->div, c->fld[W2_F_P], c->fld[W2_F_B], c->tb), who);
     const size_t n = (size_t)(*nx - 1) * (size_t)(*ny - 1);

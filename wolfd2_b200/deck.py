@@ -470,7 +470,8 @@ class Deck:
     def metrics_struct(self) -> Metrics:
         m = Metrics()
         for n in METRIC_NAMES:
-            setattr(m, n, self.metrics[n].ctypes.data_as(c_f64p))
+            if n in self.metrics:    # an empty dict (lazy_metrics) leaves NULL pointers: nothing is uploaded at create
+                setattr(m, n, self.metrics[n].ctypes.data_as(c_f64p))
         return m
 
     def new_field(self) -> np.ndarray:
@@ -594,16 +595,24 @@ def metrics_window(nx: int, ny: int, a0: int, a1: int, mnx: int, dlref: float = 
 
 def _mk(name, nx, ny, regions, re, dt, x=None, y=None, mnx=None, mny=None, slab=None, **kw) -> Deck:
     mnx = mnx if mnx is not None else nx + 1   # smallest legal size, src/grid.f:551
+    # lazy_metrics: leave the metric dict empty; api.Context then builds and uploads the metrics of the uniform grid
+    # window by window (a 16384^2 grid would need 64 GB of host arrays otherwise)
+    lazy = kw.pop("lazy_metrics", False)
+    if lazy and x is not None:
+        raise ValueError("lazy_metrics is for uniform grids")
     if slab is not None:   # (rank, world): build this rank's rows directly (uniform grids)
         from .slab import slab_layout
         if x is not None:
             raise ValueError("slab decks are built for uniform grids; cut others with Deck.to_slab")
         rank, world = slab
         j0, j1, a0, a1, hg = slab_layout(nx, ny, world, rank)
-        met = metrics_window(nx, ny, a0, a1, mnx, kw.get("dlref", 1.0))
+        met = {} if lazy else metrics_window(nx, ny, a0, a1, mnx, kw.get("dlref", 1.0))
         return Deck(name=name, nx=nx, ny=ny, mnx=mnx, mny=a1 - a0, regions=regions.complete(), metrics=met,
                     dt=dt, re=re, slab=(rank, world, j0, j1, a0, a1, hg), **kw)
     mny = mny if mny is not None else ny + 1
+    if lazy:
+        return Deck(name=name, nx=nx, ny=ny, mnx=mnx, mny=mny, regions=regions.complete(), metrics={},
+                    dt=dt, re=re, **kw)
     if x is None:
         x, y = uniform_grid(nx, ny)
     met = metrics_from_grid(x, y, mnx, mny, kw.get("dlref", 1.0))

@@ -27,7 +27,7 @@ import numpy as np
 
 from .restart import _read_record, _write_record
 
-FT_FORMATTED, FT_UNFORMATTED = 1, 2
+FT_FORMATTED, FT_UNFORMATTED = 0, 1   # the nForm flags of include/wolfd2.h:82-83
 
 
 def _nodes(a, nx, ny):
