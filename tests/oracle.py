@@ -114,7 +114,7 @@ class Oracle:
         t = deck.new_field() if t is None else t
         d = deck.new_field() if d is None else d
         logs = (_abi.StepLog * nsteps)()
-        if getattr(deck, "thermal", False):
+        if getattr(deck, "thermal", False) or getattr(deck, "eqstate", False):
             th = deck.thermal_struct()
             rc = self.lib.orc_step_thermal(C.byref(par), C.byref(reg), C.byref(met), C.byref(th),
                                            *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, d)], nsteps, logs)

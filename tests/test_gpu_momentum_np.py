@@ -1,0 +1,54 @@
+"""The QL loop keeps the time-level-n halves of the explicit momentum terms (cnvn, difn: momentum.f:327-330, :652-655)
+across its iterations and, on the first iteration of a deck without outlets, takes them from the starred fields, which
+are then bitwise copies of un, vn.  Both shortcuts must give THE SAME BITS as evaluating them from un, vn every time
+(option mom_np_cache 0), on every deck family, including those where the shortcut must not be taken."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from wolfd2_b200 import api as a
+    a.lib()
+    return a
+
+
+def _decks():
+    from wolfd2_b200 import deck as dk
+    from util import make_test_decks
+    out = list(make_test_decks(70, 45))
+    out.append(dk.cavity(300, re=400.0, dt=2e-3, ny=130))
+    out.append(dk.channel(1100, re=100.0, dt=2e-4, ny=40, fully_dev=False))
+    return out
+
+
+@pytest.mark.parametrize("k", range(9))
+def test_np_cache_is_bit_identical(api, k):
+    decks = _decks()
+    if k >= len(decks):
+        pytest.skip("no such deck")
+    d = decks[k]
+    d.msorit, d.mqiter, d.qtol = 60, 5, 1e-9          # several QL iterations per step
+    rng = np.random.default_rng(11 + k)
+    f0 = [d.new_field() for _ in range(3)]
+    for f in f0[:2]:
+        f[:d.ny + 2, :d.nx + 2] = 0.05 * rng.standard_normal((d.ny + 2, d.nx + 2))
+    res = []
+    for cache in (0, 1):
+        api.set_option("mom_np_cache", cache)
+        try:
+            with api.Context(d) as ctx:
+                for w, f in zip((api.F_U, api.F_V, api.F_P), f0):
+                    ctx.upload(w, f)
+                ctx.coldstart()
+                lg = ctx.step(3)
+                res.append((lg, [ctx.download(w) for w in (api.F_U, api.F_V, api.F_P)]))
+        finally:
+            api.set_option("mom_np_cache", 1)
+    (l0, f_off), (l1, f_on) = res
+    assert [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l0] == [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l1]
+    assert any(abs(a["nQLiter"]) != 1 for a in l1)        # the cached path did run
+    for a, b in zip(f_off, f_on):
+        assert np.isfinite(a).all() and np.array_equal(a, b), d.name

@@ -195,3 +195,37 @@ def test_thermal_off_is_the_cold_path(api, orc):
             res.append([ctx.download(w) for w in (api.F_U, api.F_V, api.F_P)])
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+
+
+def test_buoyancy_without_the_energy_equation(api, orc):
+    """`buoyancy` without `thermal_energy` (parse.f sets neqstate independently of nthermen): the reference still
+    calls EqState every step (main.f:853), so d follows p at a frozen temperature and feeds the YMomentum buoyancy
+    term through d and dn.  Steps against the oracle, d included."""
+    from wolfd2_b200 import deck as dk
+    import dataclasses
+    d = dataclasses.replace(dk.heated_cavity(40, re=100.0, dt=0.005, ny=34), thermal=False, eqstate=True, nmeiter=1)
+    d.msorit = 300
+    orc.config(d.mnx, d.mny)
+    rng = np.random.default_rng(5)
+    uo, vo, po, do = (d.new_field() for _ in range(4))
+    to = d.new_field()
+    yy, xx = np.mgrid[0:d.ny + 2, 0:d.nx + 2]
+    to[:d.ny + 2, :d.nx + 2] = 0.5 + 0.3 * np.sin(0.2 * xx) * np.cos(0.15 * yy) + 0.01 * rng.standard_normal(xx.shape)
+    t0 = to.copy()
+    nso = orc.coldstart(d, uo, vo, po)
+    with api.Context(d) as ctx:
+        z = d.new_field()
+        for w in (api.F_U, api.F_V, api.F_P, api.F_D):
+            ctx.upload(w, z)
+        ctx.upload(api.F_T, t0)
+        assert ctx.coldstart() == nso
+        for step in range(4):
+            lg = ctx.step(1)[0]
+            rc, lo = orc.step(d, uo, vo, po, 1, t=to, d=do)
+            assert rc == 0
+            assert lg["nQLiter"] == lo[0]["nQLiter"] and lg["nSorConv"] == lo[0]["nSorConv"]
+            got = [ctx.download(w) for w in (api.F_U, api.F_V, api.F_P, api.F_D)]
+            errs = [rel_l2(g, o) for g, o in zip(got, (uo, vo, po, do))]
+            assert max(errs) <= TOL_STEP, f"step {step}: rel-L2 (u,v,p,d) = {errs}"
+        assert np.array_equal(ctx.download(api.F_T), t0)       # the temperature itself is frozen
+    assert np.abs(do).max() > 0 and np.abs(vo[2:d.ny, 2:d.nx]).max() > 1e-6    # buoyancy did drive a flow

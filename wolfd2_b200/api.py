@@ -162,7 +162,7 @@ class Context:
         if not deck.metrics and stream_metrics:   # uniform grid, metrics built and uploaded window by window
             # (stream_metrics=False: the caller fills them, e.g. Context.gather_global)
             self.stream_uniform_metrics()
-        if getattr(deck, "thermal", False) or getattr(deck, "smallscale", False):
+        if getattr(deck, "thermal", False) or getattr(deck, "eqstate", False) or getattr(deck, "smallscale", False):
             self._th = deck.thermal_struct()   # cold ATD runs still need the thermal region tables
             _check(L.wolfd2_b200_set_thermal(h, C.byref(self._th)), "wolfd2_b200_set_thermal")
         if getattr(deck, "smallscale", False):

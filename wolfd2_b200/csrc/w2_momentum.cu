@@ -16,6 +16,8 @@
 
 __device__ __forceinline__ double a_sum4_sic(double a, double b, double c, double d) { return a + b + c + d / 4.0; }
 
+enum { NP_COMPUTE = 0, NP_SAME = 1, NP_CACHED = 2 };   // see mom_row (w2_mom_rows.inc)
+
 struct MomArgs {
     int nx, ny, pitch;
     double dk, re, fr;
@@ -25,7 +27,8 @@ struct MomArgs {
     // y-momentum metrics
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
     const unsigned char *xmask, *ymask;
-    const double *x1;  // first-step solution, field layout
+    const double *x1;  // first-step solution, field layout (local part Y only: the spike correction is applied by the reader)
+    double *np_c, *np_d;   // cache of cnvn, difn of the component being solved (null: not kept)
     // thermal energy equation (COMP 2, thermal.f:24-272): time-level-n temperature, heat source, fixed-T mask
     const double *tn, *heat, *rau, *rbu, *rbv, *rgv, *djc;
     const unsigned char *tmask;
@@ -108,11 +111,17 @@ struct ChainWalk {
 #endif
 static constexpr int kMomU1 = MOM_U1, kMomU2 = MOM_U2;   // (#pragma unroll does not expand macros)
 
-template <int COMP, int STEP, bool POR>
+// STEP 2 reads the first-step solution as  x1 = Y - Sg[g-1]*V - Sg[g]*W  (sig1: the first step's separator values):
+// the first step leaves only its local part Y in m.x1 and its spikes in Vg / Wg / ext, and the correction -- a few
+// hundred unknowns per segment, where the spikes are not exactly zero -- is applied here while the row is assembled,
+// in the operation order of mom_finalize_kernel.  The second step uses the same segments, so CTA g reads the spike
+// entries of segment g before it overwrites them with its own in phase C.
+template <int COMP, int STEP, bool POR, int NP>
 __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
-                                                              long long nseg, int direct, long long seg0) {
+                                                              long long nseg, int direct, long long seg0,
+                                                              const double *__restrict__ sig1) {
     extern __shared__ __align__(16) double sm[];
     double *s0 = sm, *s1 = sm + MR_LEN, *s2 = sm + 2 * MR_LEN, *s3 = sm + 3 * MR_LEN;
     __shared__ int s_ext[2];
@@ -129,6 +138,12 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     // issuing the loads of the next unrolled unknown before the current one is finished.  Elements past the end
     // of the chain (last segment only) assemble the row of the last valid point and are then replaced by the
     // identity; the first-row quirk is patched in after the loop.
+    int extV1 = 0, extW1 = 0;
+    double sl1 = 0.0, sr1 = 0.0;
+    if (STEP == 2 && sig1 != nullptr) {
+        extV1 = ext[2 * g]; extW1 = ext[2 * g + 1];
+        sl1 = g > 0 ? sig1[g - 1] : 0.0; sr1 = sig1[g];
+    }
     const long long e0 = ebase + t;
     ChainWalk<COMP> wa(m, e0 < n ? e0 : n - 1);
     int ci = wa.i(), cj = wa.j;
@@ -143,8 +158,15 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
             ci = live ? wa.i() : ci; cj = live ? wa.j : cj;
         }
         double a1, a2, a3, b;
-        if (POR) mom_po::mom_row<COMP, STEP>(m, ci, cj, a1, a2, a3, b);
-        else mom_np::mom_row<COMP, STEP>(m, ci, cj, a1, a2, a3, b);
+        if (POR) mom_po::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
+        else mom_np::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
+        if (STEP == 2) {   // x1 of this unknown: apply the first step's spike correction (identity rows keep b = 0)
+            const bool inV = el < extV1, inW = el >= TRI_S - extW1;
+            const long long ec = live ? e : n - 1;
+            const double v = inV ? Vg[ec] : 0.0, ww = inW ? Wg[ec] : 0.0;
+            const bool ident = COMP == 0 ? m.xmask[IDX(ci, cj)] != 0 : COMP == 1 ? m.ymask[IDX(ci, cj)] != 0 : m.tmask[IDX(ci, cj)] != 0;
+            b = ((inV || inW) && !ident) ? b - sl1 * v - sr1 * ww : b;
+        }
         a3 = (e == n - 1) ? 0.0 : a3;
         const int p = MR_PAD(el);
         s0[p] = live ? a1 : 0.0; s1[p] = live ? a2 : 1.0; s2[p] = live ? a3 : 0.0; s3[p] = live ? b : 0.0;
@@ -152,8 +174,8 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     if (ebase == 0 && t == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
         int i2, j2; double b1, b2, b3, bb;
         chain_ij<COMP>(m, 1, i2, j2);
-        if (POR) mom_po::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
-        else mom_np::mom_row<COMP, STEP>(m, i2, j2, b1, b2, b3, bb);
+        if (POR) mom_po::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
+        else mom_np::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
         s0[0] = 0.0;
         s2[0] = s2[0] * s1[0] / b2;
     }
@@ -368,6 +390,7 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xev = t.xev; m.yev = t.yev; m.xzv = t.xzv; m.yzv = t.yzv;
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->x1;
+    m.np_c = nullptr; m.np_d = nullptr;
     m.tn = c->fld[W2_F_TN]; m.heat = c->heat_s; m.tmask = c->tmask; m.pe = c->th.pe;
     m.rau = t.rau; m.rbu = t.rbu; m.rbv = t.rbv; m.rgv = t.rgv; m.djc = t.djc;
     m.porous = c->hreg.has_porous; m.R = c->dreg;
@@ -376,12 +399,16 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xcp = pm + 4 * c->nelem; m.ycp = pm + 5 * c->nelem;
 }
 
-template <int COMP, int STEP, bool POR>
-static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out);
+template <int COMP, int STEP, bool POR, int NP>
+static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, const double *sig1, const double **sig_out);
 
+// one split step of component COMP; sig1 / sig_out: separator values of the first step (see mom_reduce_kernel)
 template <int COMP, int STEP>
-static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
-    return c->hreg.has_porous ? mom_solve_impl<COMP, STEP, true>(c, m, n, out) : mom_solve_impl<COMP, STEP, false>(c, m, n, out);
+static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out, int np, const double *sig1, const double **sig_out) {
+    if (c->hreg.has_porous) return mom_solve_impl<COMP, STEP, true, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
+    if (STEP == 1 && np == NP_SAME) return mom_solve_impl<COMP, STEP, false, (STEP == 1 ? NP_SAME : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+    if (STEP == 1 && np == NP_CACHED) return mom_solve_impl<COMP, STEP, false, (STEP == 1 ? NP_CACHED : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+    return mom_solve_impl<COMP, STEP, false, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
 }
 
 // Chain unknowns [lo, hi) that lie in the rows this rank updates.  The level-0 segments keep their GLOBAL
@@ -428,12 +455,12 @@ static int mom_tail_exchange(wolfd2_ctx *c, double *out) {
     return w2_send_recv_pieces(c, up, nup, dn, ndn);
 }
 
-template <int COMP, int STEP, bool POR>
-static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
+template <int COMP, int STEP, bool POR, int NP>
+static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, const double *sig1, const double **sig_out) {
     static bool attr[W2_MAXDEV] = {};   // the attribute is per device: one flag per device id
     const size_t smem = (size_t)4 * MR_LEN * sizeof(double);
     if (!attr[c->device % W2_MAXDEV]) {
-        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, POR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, POR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr[c->device % W2_MAXDEV] = true;
     }
     W2TriWork &w = c->tri;
@@ -453,37 +480,58 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out) {
     }
     double *V0 = w.V0 - s_lo * TRI_S, *W0 = w.W0 - s_lo * TRI_S;
     int *ext = w.ext - 2 * s_lo;
-    mom_reduce_kernel<COMP, STEP, POR><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(m, n, out, V0, W0, w.lv[0].seg, ext, nseg,
-                                                                                           direct, s_lo);
+    mom_reduce_kernel<COMP, STEP, POR, NP><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(
+        m, n, out, V0, W0, w.lv[0].seg, ext, nseg, direct, s_lo, (STEP == 2 && !direct) ? sig1 : nullptr);
     c->launches[1]++;
+    if (sig_out) *sig_out = nullptr;
     if (!direct) {
         // every rank holds the records of its own segments; summing with the zeros of the others is exact
         W2_TRY(w2_allreduce_sum_f64(c, w.lv[0].seg, 10 * (size_t)nseg));
         const double *sigma = nullptr;
         W2_TRY(w2_tri_upper(c, nseg, &sigma));   // a few thousand unknowns: solved redundantly on every rank
-        mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
-        c->launches[1]++;
+        if (STEP == 1) {
+            if (sig_out) *sig_out = sigma;       // the second step applies the correction while it reads x1
+        } else {
+            mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
+            c->launches[1]++;
+        }
     }
     W2_CUDA(cudaGetLastError());
     if (STEP == 2) W2_TRY(mom_tail_exchange<COMP>(c, out));
     return W2_OK;
 }
 
-int w2_xmomentum(wolfd2_ctx *c, double *dus) {
-    MomArgs m;
-    fill_args(c, m);
-    const long long n = (long long)c->nx * (c->ny - 1);
-    W2_TRY((mom_solve<0, 1>(c, m, n, c->x1)));   // :350-389, result in field layout
-    W2_TRY((mom_solve<0, 2>(c, m, n, dus)));     // :396-510
+// Arrays that are free during the momentum solve hold the cache of cnvn / difn (NP modes of mom_row): the
+// divergence work array and the PPE right-hand side for u, the two colour-split pressure buffers of the fused SOR
+// for v.  All four are rewritten from scratch by the PPE that follows (w2_ppe.cu, w2_sor_fused.cu).
+static int np_cache(wolfd2_ctx *c, int comp, double **pc, double **pd) {
+    if (comp == 0) { *pc = c->div; *pd = c->fld[W2_F_B]; return W2_OK; }
+    for (int k = 0; k < 2; ++k)
+        if (!c->sorf_buf[k]) W2_TRY(w2_alloc_field(c, &c->sorf_buf[k]));
+    *pc = c->sorf_buf[0]; *pd = c->sorf_buf[1];
     return W2_OK;
 }
 
-int w2_ymomentum(wolfd2_ctx *c, double *dvs) {
+// np: NP_COMPUTE / NP_SAME / NP_CACHED (mom_row); keep: fill the cnvn / difn cache for later QL iterations
+int w2_xmomentum(wolfd2_ctx *c, double *dus, int np, int keep) {
     MomArgs m;
     fill_args(c, m);
+    if (np == NP_CACHED || keep) W2_TRY(np_cache(c, 0, &m.np_c, &m.np_d));
+    const long long n = (long long)c->nx * (c->ny - 1);
+    const double *sig1 = nullptr;
+    W2_TRY((mom_solve<0, 1>(c, m, n, c->x1, np, nullptr, &sig1)));   // :350-389, local part in field layout
+    W2_TRY((mom_solve<0, 2>(c, m, n, dus, NP_COMPUTE, sig1, nullptr)));     // :396-510
+    return W2_OK;
+}
+
+int w2_ymomentum(wolfd2_ctx *c, double *dvs, int np, int keep) {
+    MomArgs m;
+    fill_args(c, m);
+    if (np == NP_CACHED || keep) W2_TRY(np_cache(c, 1, &m.np_c, &m.np_d));
     const long long n = (long long)(c->nx - 1) * c->ny;
-    W2_TRY((mom_solve<1, 1>(c, m, n, c->x1)));   // :675-716
-    W2_TRY((mom_solve<1, 2>(c, m, n, dvs)));     // :723-834
+    const double *sig1 = nullptr;
+    W2_TRY((mom_solve<1, 1>(c, m, n, c->x1, np, nullptr, &sig1)));   // :675-716
+    W2_TRY((mom_solve<1, 2>(c, m, n, dvs, NP_COMPUTE, sig1, nullptr)));     // :723-834
     return W2_OK;
 }
 
@@ -495,10 +543,13 @@ int w2_thermal_solve(wolfd2_ctx *c, double *dts) {
     MomArgs m;
     fill_args(c, m);
     const long long n = (long long)(c->nx - 1) * (c->ny - 1);
-    W2_TRY((mom_solve_impl<2, 1, false>(c, m, n, c->x1)));
-    W2_TRY((mom_solve_impl<2, 2, false>(c, m, n, dts)));
+    const double *sig1 = nullptr;
+    W2_TRY((mom_solve_impl<2, 1, false, NP_COMPUTE>(c, m, n, c->x1, nullptr, &sig1)));
+    W2_TRY((mom_solve_impl<2, 2, false, NP_COMPUTE>(c, m, n, dts, sig1, nullptr)));
     return W2_OK;
 }
+
+int g_mom_np_cache = 1;   // option "mom_np_cache": 0 = always evaluate cnvn / difn from un, vn (tests compare both ways)
 
 // nAuxMomentum (:33-193).  One host read-back (16 bytes) per QL iteration decides convergence.
 int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
@@ -512,11 +563,20 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
         ql_init_kernel<<<g, 256, 0, c->stream>>>(nx, jlo, jhi, c->pitch, c->fld[W2_F_UN], c->fld[W2_F_VN], us, vs);
         c->launches[1]++;
     }
+    // Time-level-n halves of the explicit terms (mom_row, NP modes).  On the first QL iteration us, vs are bitwise
+    // copies of un, vn on every cell (main.f:696-747) unless nAuxMomentum's own initialisation loop ran (it skips row and
+    // column 0, :114-119) or VelOutflowBCs (:133) has just rewritten the outlet ghost cells of us, vs.
+    bool has_outlet = false;
+    for (int q = 0; q < c->hreg.nreg; ++q)
+        for (int k = 0; k < 4; ++k) has_outlet |= c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2;
+    const bool cache_ok = !c->hreg.has_porous && g_mom_np_cache;
+    const int keep = cache_ok && c->par.mqiter > 1;
     for (int m = 1; m <= c->par.mqiter; ++m) {
         W2_TRY(w2_outflow_bc(c, us, vs));  // :133
+        const int np = !cache_ok ? NP_COMPUTE : m > 1 ? NP_CACHED : (!init_star && !has_outlet) ? NP_SAME : NP_COMPUTE;
         // dus, dvs are zero outside the ranges XMomentum/YMomentum write (:139-144 re-zeroes the same cells)
-        W2_TRY(w2_xmomentum(c, c->dus));   // :147
-        W2_TRY(w2_ymomentum(c, c->dvs));   // :158
+        W2_TRY(w2_xmomentum(c, c->dus, np, keep));   // :147
+        W2_TRY(w2_ymomentum(c, c->dvs, np, keep));   // :158
         W2_CUDA(cudaMemsetAsync(c->d_norm + 8, 0, 2 * sizeof(unsigned long long), c->stream));
         int jlo = 1, jhi = ny;
         w2_clip(c, jlo, jhi);

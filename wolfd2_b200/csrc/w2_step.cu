@@ -61,7 +61,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         // :741-747  starred quantities
         W2_TRY(w2_copy_field(c, us, u));
         W2_TRY(w2_copy_field(c, vs, v));
-        if (thermal) W2_TRY(w2_copy_field(c, ts, t));
+        if (thermal || eqstate) W2_TRY(w2_copy_field(c, ts, t));   // EqState reads ts (:853)
         // us == un on the first pass (not with the ATD model, where un carries uss: then the loop of :114-119 is real), so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
         // on later passes it resets us, vs to un, vn as the reference does
         W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1 || atd, &nQL));   // :753
