@@ -440,6 +440,9 @@ def run_gpu(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api.set_device(local)
+    for o in args.opt:
+        k, v = o.split("=")
+        api.set_option(k, int(v))
     from wolfd2_b200 import slab
     n, nyg, scaling = resolve_grid(args, world)
     lazy = (n - 1) * (nyg - 1) // world > 40e6      # large slabs: metrics built and uploaded window by window
@@ -635,6 +638,8 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="Lagrangian particles (configs[4]: 1000000)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N>1: strong (default) = the n x n grid cut into N slabs; weak = n x (n*N) grid, n rows per GPU")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option (wolfd2_b200_set_option), e.g. mom_np_cache=0, sor_fused_T=1")
     args = ap.parse_args()
     args.fixed_work = args.mode == "fixed"
     if args.warmup < 3 and args.impl == "ours":

@@ -34,7 +34,7 @@ def test_np_cache_is_bit_identical(api, k):
     rng = np.random.default_rng(11 + k)
     f0 = [d.new_field() for _ in range(3)]
     for f in f0[:2]:
-        f[:d.ny + 2, :d.nx + 2] = 0.05 * rng.standard_normal((d.ny + 2, d.nx + 2))
+        f[:d.ny + 2, :d.nx + 2] = 0.002 * rng.standard_normal((d.ny + 2, d.nx + 2))
     res = []
     for cache in (0, 1):
         api.set_option("mom_np_cache", cache)
@@ -49,6 +49,6 @@ def test_np_cache_is_bit_identical(api, k):
             api.set_option("mom_np_cache", 1)
     (l0, f_off), (l1, f_on) = res
     assert [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l0] == [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l1]
-    assert any(abs(a["nQLiter"]) != 1 for a in l1)        # the cached path did run
+    assert any(a["nQLiter"] == -1 or a["nQLiter"] > 1 for a in l1)        # several QL iterations: the cached path did run
     for a, b in zip(f_off, f_on):
         assert np.isfinite(a).all() and np.array_equal(a, b), d.name

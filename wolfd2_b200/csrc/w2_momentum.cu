@@ -27,7 +27,7 @@ struct MomArgs {
     // y-momentum metrics
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
     const unsigned char *xmask, *ymask;
-    const double *x1;  // first-step solution, field layout (local part Y only: the spike correction is applied by the reader)
+    const double *x1;  // first-step solution, field layout
     double *np_c, *np_d;   // cache of cnvn, difn of the component being solved (null: not kept)
     // thermal energy equation (COMP 2, thermal.f:24-272): time-level-n temperature, heat source, fixed-T mask
     const double *tn, *heat, *rau, *rbu, *rbv, *rgv, *djc;
@@ -111,17 +111,11 @@ struct ChainWalk {
 #endif
 static constexpr int kMomU1 = MOM_U1, kMomU2 = MOM_U2;   // (#pragma unroll does not expand macros)
 
-// STEP 2 reads the first-step solution as  x1 = Y - Sg[g-1]*V - Sg[g]*W  (sig1: the first step's separator values):
-// the first step leaves only its local part Y in m.x1 and its spikes in Vg / Wg / ext, and the correction -- a few
-// hundred unknowns per segment, where the spikes are not exactly zero -- is applied here while the row is assembled,
-// in the operation order of mom_finalize_kernel.  The second step uses the same segments, so CTA g reads the spike
-// entries of segment g before it overwrites them with its own in phase C.
 template <int COMP, int STEP, bool POR, int NP>
 __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
-                                                              long long nseg, int direct, long long seg0,
-                                                              const double *__restrict__ sig1) {
+                                                              long long nseg, int direct, long long seg0) {
     extern __shared__ __align__(16) double sm[];
     double *s0 = sm, *s1 = sm + MR_LEN, *s2 = sm + 2 * MR_LEN, *s3 = sm + 3 * MR_LEN;
     __shared__ int s_ext[2];
@@ -138,12 +132,6 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     // issuing the loads of the next unrolled unknown before the current one is finished.  Elements past the end
     // of the chain (last segment only) assemble the row of the last valid point and are then replaced by the
     // identity; the first-row quirk is patched in after the loop.
-    int extV1 = 0, extW1 = 0;
-    double sl1 = 0.0, sr1 = 0.0;
-    if (STEP == 2 && sig1 != nullptr) {
-        extV1 = ext[2 * g]; extW1 = ext[2 * g + 1];
-        sl1 = g > 0 ? sig1[g - 1] : 0.0; sr1 = sig1[g];
-    }
     const long long e0 = ebase + t;
     ChainWalk<COMP> wa(m, e0 < n ? e0 : n - 1);
     int ci = wa.i(), cj = wa.j;
@@ -160,13 +148,6 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
         double a1, a2, a3, b;
         if (POR) mom_po::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
         else mom_np::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
-        if (STEP == 2) {   // x1 of this unknown: apply the first step's spike correction (identity rows keep b = 0)
-            const bool inV = el < extV1, inW = el >= TRI_S - extW1;
-            const long long ec = live ? e : n - 1;
-            const double v = inV ? Vg[ec] : 0.0, ww = inW ? Wg[ec] : 0.0;
-            const bool ident = COMP == 0 ? m.xmask[IDX(ci, cj)] != 0 : COMP == 1 ? m.ymask[IDX(ci, cj)] != 0 : m.tmask[IDX(ci, cj)] != 0;
-            b = ((inV || inW) && !ident) ? b - sl1 * v - sr1 * ww : b;
-        }
         a3 = (e == n - 1) ? 0.0 : a3;
         const int p = MR_PAD(el);
         s0[p] = live ? a1 : 0.0; s1[p] = live ? a2 : 1.0; s2[p] = live ? a3 : 0.0; s3[p] = live ? b : 0.0;
@@ -402,7 +383,7 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
 template <int COMP, int STEP, bool POR, int NP>
 static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, const double *sig1, const double **sig_out);
 
-// one split step of component COMP; sig1 / sig_out: separator values of the first step (see mom_reduce_kernel)
+// one split step of component COMP (sig1 / sig_out: separator values, unused hooks)
 template <int COMP, int STEP>
 static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out, int np, const double *sig1, const double **sig_out) {
     if (c->hreg.has_porous) return mom_solve_impl<COMP, STEP, true, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
@@ -481,7 +462,7 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, c
     double *V0 = w.V0 - s_lo * TRI_S, *W0 = w.W0 - s_lo * TRI_S;
     int *ext = w.ext - 2 * s_lo;
     mom_reduce_kernel<COMP, STEP, POR, NP><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(
-        m, n, out, V0, W0, w.lv[0].seg, ext, nseg, direct, s_lo, (STEP == 2 && !direct) ? sig1 : nullptr);
+        m, n, out, V0, W0, w.lv[0].seg, ext, nseg, direct, s_lo);
     c->launches[1]++;
     if (sig_out) *sig_out = nullptr;
     if (!direct) {
@@ -489,12 +470,11 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, c
         W2_TRY(w2_allreduce_sum_f64(c, w.lv[0].seg, 10 * (size_t)nseg));
         const double *sigma = nullptr;
         W2_TRY(w2_tri_upper(c, nseg, &sigma));   // a few thousand unknowns: solved redundantly on every rank
-        if (STEP == 1) {
-            if (sig_out) *sig_out = sigma;       // the second step applies the correction while it reads x1
-        } else {
-            mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
-            c->launches[1]++;
-        }
+        // (Applying the first step's correction inside the second step's assembly instead was measured: the extra
+        // predicated loads cost that kernel 88 us at 4096^2, the finalize launch it saves 50 us.)
+        mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
+        c->launches[1]++;
+        if (sig_out) *sig_out = sigma;
     }
     W2_CUDA(cudaGetLastError());
     if (STEP == 2) W2_TRY(mom_tail_exchange<COMP>(c, out));
