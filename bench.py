@@ -362,7 +362,8 @@ def run_extra(label, d, steps, warmup, particles=0, atd=False):
                         "sections_ms_per_step": {"momentum": tm["momentum_ms"] / steps, "ppe": tm["ppe_ms"] / steps,
                                                  "other": tm["other_ms"] / steps},
                         "sor_us_per_iteration": tm["sor_ms"] / max(tm["sor_iters"], 1) * 1e3,
-                        "dif_last": logs[-1]["dif"][:3], "gpu_launches": int(launches)})
+                        "dif_last": logs[-1]["dif"][:3], "gpu_launches": int(launches),
+                        "host_syncs_per_step": tm["host_syncs"] / steps})
             if particles:
                 gxp, gyp, gup, gvp, gout = ctx.particles()
                 out["particles"] = {"n": int(gxp.size), "in_bounds": int((gout == 0).sum()),
@@ -573,6 +574,7 @@ def run_gpu(args):
         "e2e": {"value": e2e, "unit": "Gcell-updates/s", "h2d_bytes_per_step": copy_bytes,
                 "d2h_bytes_per_step": copy_bytes, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches),
+        "host_syncs_per_step": tm["host_syncs"] / args.steps,
         "clocks": clocks,
     }
     if verify is not None:

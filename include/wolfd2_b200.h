@@ -240,6 +240,9 @@ int wolfd2_b200_last_timing(wolfd2_ctx *ctx, double ms[4], int64_t launches[4]);
 /* Average device time of the SOR sweep kernel launches inside the last step (ms)
  * and the number of SOR iterations they covered. */
 int wolfd2_b200_last_sor_timing(wolfd2_ctx *ctx, double *ms_total, int64_t *iterations);
+/* Host waits (stream / event synchronisations) issued by the last wolfd2_b200_step call: the loop control of the QL and
+ * SOR loops lives on the device, the host only reads the step's status tuple and throttles how far it runs ahead. */
+int wolfd2_b200_last_host_syncs(wolfd2_ctx *ctx, int64_t *syncs);
 int wolfd2_b200_sync(wolfd2_ctx *ctx);
 /* Page-locked host buffers for the e2e path (cudaMallocHost / cudaFreeHost). */
 void *wolfd2_b200_host_alloc(uint64_t bytes);

@@ -73,6 +73,7 @@ def lib():
     L.wolfd2_b200_step_host.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_f64p, c_f64p, C.POINTER(StepLog)]
     L.wolfd2_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.wolfd2_b200_last_sor_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.wolfd2_b200_last_host_syncs.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.wolfd2_b200_sync.argtypes = [C.c_void_p]
     L.wolfd2_b200_host_alloc.argtypes = [C.c_uint64]
     L.wolfd2_b200_host_alloc.restype = C.c_void_p
@@ -304,7 +305,9 @@ class Context:
         _check(lib().wolfd2_b200_last_timing(self._h, ms, ln), "last_timing")
         sm, si = C.c_double(0), C.c_int64(0)
         _check(lib().wolfd2_b200_last_sor_timing(self._h, C.byref(sm), C.byref(si)), "last_sor_timing")
-        return dict(total_ms=ms[0], momentum_ms=ms[1], ppe_ms=ms[2], other_ms=ms[3],
+        hs = C.c_int64(0)
+        _check(lib().wolfd2_b200_last_host_syncs(self._h, C.byref(hs)), "last_host_syncs")
+        return dict(total_ms=ms[0], momentum_ms=ms[1], ppe_ms=ms[2], other_ms=ms[3], host_syncs=hs.value,
                     launches=dict(momentum=ln[1], ppe=ln[2], other=ln[3]),
                     sor_ms=sm.value, sor_iters=si.value)
 

@@ -52,7 +52,8 @@ __device__ __forceinline__ void bc_scan(double *s1, double *s2, double prev0, do
 
 template <bool kOutflowOnly>
 __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__restrict__ R, int pitch,
-                                                            int jlo, int jhi, double *u, double *v) {
+                                                            int jlo, int jhi, double *u, double *v, const int *done) {
+    if (done != nullptr && *done) return;   // VelOutflowBCs of a speculatively enqueued QL iteration
     const double dZero = 0.0, dTwo = 2.0, dThree = 3.0, dFour = 4.0, dFive = 5.0, dEight = 8.0;
     __shared__ double sc1[BC_CHUNK], sc2[BC_CHUNK + 1];   // bc_scan staging
     const int nreg = R->nreg;
@@ -196,10 +197,17 @@ __global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__
         const double vW = R->val[q][W2_WEST - 1][W2_P - 1], vE = R->val[q][W2_EAST - 1][W2_P - 1];
         const double vS = R->val[q][W2_SOUTH - 1][W2_P - 1], vN = R->val[q][W2_NORTH - 1][W2_P - 1];
         if (R->type[q] == W2_RM_BLOCKG) {  // :903-936
+            // The zero fill of the interior iW+1..iE x jS+1..jN: its outer layer here, in sequence (neighbouring
+            // regions write into it and the four loops below overwrite it); the cells further inside, which no other
+            // statement of the routine touches, by blk_zero_kernel on the whole GPU before this kernel starts.
             const int w = iE - iW, h = jN - jS;
-            for (int t = threadIdx.x; t < w * h; t += BC_THREADS) {
-                const int j = jS + 1 + t / w;
-                if (j >= jlo && j <= jhi) P(iW + 1 + t % w, j) = dZero;
+            for (int t = threadIdx.x; t < 2 * (w + h); t += BC_THREADS) {
+                int i, j;
+                if (t < w) { i = iW + 1 + t; j = jS + 1; }
+                else if (t < 2 * w) { i = iW + 1 + (t - w); j = jN; }
+                else if (t < 2 * w + h) { i = iW + 1; j = jS + 1 + (t - 2 * w); }
+                else { i = iE; j = jS + 1 + (t - 2 * w - h); }
+                if (j >= jlo && j <= jhi) P(i, j) = dZero;
             }
             __syncthreads();
             PFORJ(j, jS + 1, jN) P(iW + 1, j) = vW + P(iW, j);
@@ -244,24 +252,40 @@ __global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__
 }
 
 int w2_vel_bc(wolfd2_ctx *c, double *u, double *v) {
-    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v);
+    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, nullptr);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
-int w2_outflow_bc(wolfd2_ctx *c, double *u, double *v) {
+int w2_outflow_bc(wolfd2_ctx *c, double *u, double *v, const int *done) {
     // skip the launch when no face is an outlet (VelOutflowBCs is then a no-op, :1709-1710)
     bool any = false;
     for (int q = 0; q < c->hreg.nreg && !any; ++q)
         for (int k = 0; k < 4; ++k)
             if (c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2) any = true;
     if (!any) return W2_OK;
-    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v);
+    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, done);
     c->launches[1]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
 }
+// deep interior of a blockage region (iW+2..iE-1, jS+2..jN-1): only ever zeroed (:903-908)
+__global__ void __launch_bounds__(256) blk_zero_kernel(int iW, int iE, int jS, int jN, int jlo, int jhi, int pitch, double *p) {
+    const int i = iW + 2 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > iE - 1) return;
+    for (int j = max(jS + 2, jlo) + blockIdx.y; j <= min(jN - 1, jhi); j += gridDim.y) P(i, j) = 0.0;
+}
+
 int w2_pres_bc(wolfd2_ctx *c, double *p) {
+    if (c->hreg.has_blockage)
+        for (int q = 0; q < c->hreg.nreg; ++q) {
+            if (c->hreg.type[q] != W2_RM_BLOCKG) continue;
+            const int w = c->hreg.iE[q] - c->hreg.iW[q] - 2, h = c->hreg.jN[q] - c->hreg.jS[q] - 2;
+            if (w <= 0 || h <= 0) continue;
+            dim3 g((w + 255) / 256, h < 1024 ? h : 1024);
+            blk_zero_kernel<<<g, 256, 0, c->stream>>>(c->hreg.iW[q], c->hreg.iE[q], c->hreg.jS[q], c->hreg.jN[q], c->A0, c->A1, c->pitch, p);
+            c->launches[3]++;
+        }
     pres_bc_kernel<<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, p);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());

@@ -247,6 +247,8 @@ static int ctx_create_body(wolfd2_ctx *c, int nx, int ny, int rank, int world, c
     W2_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     W2_CUDA(cudaMallocHost((void **)&c->h_norm, 64 * sizeof(unsigned long long)));
     W2_CUDA(cudaMallocHost((void **)&c->h_flags, 64 * sizeof(int)));
+    W2_CUDA(cudaMallocHost((void **)&c->h_sor, 96 * sizeof(int)));
+    memset(c->h_sor, 0, 96 * sizeof(int));
     return W2_OK;
 }
 
@@ -267,7 +269,8 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
     w2_tri_release(c);
     cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);
-    cudaFreeHost(c->h_norm); cudaFreeHost(c->h_flags);
+    cudaFreeHost(c->h_norm); cudaFreeHost(c->h_flags); cudaFreeHost(c->h_sor);
+    for (int k = 0; k < 2; ++k) { if (c->ev_ql[k]) cudaEventDestroy(c->ev_ql[k]); if (c->ev_sor[k]) cudaEventDestroy(c->ev_sor[k]); }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->ev_p) cudaEventDestroy(c->ev_p);

@@ -37,6 +37,7 @@ struct MomArgs {
     int porous;
     const W2Regions *R;
     const unsigned char *xd1, *xd2, *yd1, *yd2, *xcp, *ycp;
+    const int *done;   // device flag of the QL loop (null outside it): set = converged, later launches do nothing
 };
 
 namespace mom_np { constexpr bool kPorous = false;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
                                                               double *__restrict__ seg, int *__restrict__ ext,
                                                               long long nseg, int direct, long long seg0) {
     extern __shared__ __align__(16) double sm[];
+    if (m.done != nullptr && *m.done) return;
     double *s0 = sm, *s1 = sm + MR_LEN, *s2 = sm + 2 * MR_LEN, *s3 = sm + 3 * MR_LEN;
     __shared__ int s_ext[2];
     __shared__ double sSig;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) mom_finalize_kernel(MomArgs m, long long 
                                                            const double *__restrict__ sig, const int *__restrict__ ext,
                                                            long long seg0, long long seg1) {
     const long long g = seg0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= seg1) return;
+    if (g >= seg1 || (m.done != nullptr && *m.done)) return;
     const int lane = threadIdx.x & 31;
     const int pitch = m.pitch;
     const int extV = ext[2 * g], extW = ext[2 * g + 1];
@@ -299,8 +301,9 @@ __global__ void __launch_bounds__(256) ql_init_kernel(int nx, int jlo, int jhi, 
 __global__ void __launch_bounds__(256) ql_update_kernel(int nx, int ny, int jlo, int jhi, int seed, int pitch,
                                                         const double *__restrict__ dus,
                                                         const double *__restrict__ dvs, double *__restrict__ us,
-                                                        double *__restrict__ vs, unsigned long long *slots) {
+                                                        double *__restrict__ vs, unsigned long long *slots, const int *done) {
     __shared__ double red[32];
+    if (*done) return;
     double mu = 0.0, mv = 0.0;
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= nx)
@@ -372,6 +375,7 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->x1;
     m.np_c = nullptr; m.np_d = nullptr;
+    m.done = c->ql_active ? (const int *)(c->d_norm + W2_QL_SLOT) : nullptr;
     m.tn = c->fld[W2_F_TN]; m.heat = c->heat_s; m.tmask = c->tmask; m.pe = c->th.pe;
     m.rau = t.rau; m.rbu = t.rbu; m.rbv = t.rbv; m.rgv = t.rgv; m.djc = t.djc;
     m.porous = c->hreg.has_porous; m.R = c->dreg;
@@ -469,7 +473,7 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, c
         // every rank holds the records of its own segments; summing with the zeros of the others is exact
         W2_TRY(w2_allreduce_sum_f64(c, w.lv[0].seg, 10 * (size_t)nseg));
         const double *sigma = nullptr;
-        W2_TRY(w2_tri_upper(c, nseg, &sigma));   // a few thousand unknowns: solved redundantly on every rank
+        W2_TRY(w2_tri_upper(c, nseg, &sigma, m.done));   // a few thousand unknowns: solved redundantly on every rank
         // (Applying the first step's correction inside the second step's assembly instead was measured: the extra
         // predicated loads cost that kernel 88 us at 4096^2, the finalize launch it saves 50 us.)
         mom_finalize_kernel<COMP><<<(unsigned)((s_hi - s_lo + 7) / 8), 256, 0, c->stream>>>(m, n, out, V0, W0, sigma, ext, s_lo, s_hi);
@@ -531,11 +535,31 @@ int w2_thermal_solve(wolfd2_ctx *c, double *dts) {
 
 int g_mom_np_cache = 1;   // option "mom_np_cache": 0 = always evaluate cnvn / difn from un, vn (tests compare both ways)
 
-// nAuxMomentum (:33-193).  One host read-back (16 bytes) per QL iteration decides convergence.
+__global__ void ql_ctl_reset(int *ctl) { ctl[0] = 0; ctl[1] = -1; }
+
+// End of QL iteration m: `difmax.le.qtol` (:182-188) on the device.  ctl[0] = converged flag, ctl[1] = nQLiter.
+__global__ void ql_decide_kernel(int *ctl, const unsigned long long *slots, double qtol, int m) {
+    if (ctl[0]) return;
+    const double du = __longlong_as_double((long long)slots[0]), dv = __longlong_as_double((long long)slots[1]);
+    const double difmax = du > dv ? du : dv;
+    if (difmax <= qtol) { ctl[0] = 1; ctl[1] = m; }
+}
+
+// nAuxMomentum (:33-193) with the loop control on the device.  Every kernel of an iteration returns at once when the
+// convergence flag is set, so the host enqueues iterations WITHOUT waiting for their outcome: iteration k is enqueued
+// as soon as the outcome of iteration k-2 is known (one speculative iteration at most, its launches cost a few
+// microseconds each), and the GPU never idles on a host round trip.  With max_ql_iter <= 2 (the fixed-work mode) there
+// is no wait at all; nQLiter travels back with the step's norms.  On several GPUs the decision is taken from the
+// all-reduced norms, so every rank enqueues the same sequence (the NCCL calls of a speculative iteration move stale
+// data and change nothing).
 int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
     const int nx = c->nx, ny = c->ny;
     double *us = c->fld[W2_F_US], *vs = c->fld[W2_F_VS];
-    *nQLiter = -1;  // :111
+    int *ctl = (int *)(c->d_norm + W2_QL_SLOT);
+    int *hctl = (int *)(c->h_norm + W2_QL_SLOT);     // pinned: [2*k], [2*k+1] = flag, count after iteration k (k = 0: final)
+    if (nQLiter) *nQLiter = -1;  // :111
+    if (!c->ev_ql[0]) for (int k = 0; k < 2; ++k) W2_CUDA(cudaEventCreateWithFlags(&c->ev_ql[k], cudaEventDisableTiming));
+    ql_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
     if (init_star) {
         // all held rows: un, vn have valid halos, so the copy needs no exchange
         const int jlo = c->A0 > 1 ? c->A0 : 1, jhi = c->A1;
@@ -551,32 +575,55 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
         for (int k = 0; k < 4; ++k) has_outlet |= c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2;
     const bool cache_ok = !c->hreg.has_porous && g_mom_np_cache;
     const int keep = cache_ok && c->par.mqiter > 1;
-    for (int m = 1; m <= c->par.mqiter; ++m) {
-        W2_TRY(w2_outflow_bc(c, us, vs));  // :133
+    c->ql_active = 1;
+    int rc = W2_OK;
+    for (int m = 1; m <= c->par.mqiter && rc == W2_OK; ++m) {
+        if (m >= 3) {   // outcome of iteration m-2 (iteration m-1 is in flight)
+            W2_CUDA(cudaEventSynchronize(c->ev_ql[m & 1]));
+            c->host_syncs++;
+            if (hctl[2 + 2 * (m & 1)]) break;
+        }
+        rc = w2_outflow_bc(c, us, vs, ctl);  // :133
         const int np = !cache_ok ? NP_COMPUTE : m > 1 ? NP_CACHED : (!init_star && !has_outlet) ? NP_SAME : NP_COMPUTE;
         // dus, dvs are zero outside the ranges XMomentum/YMomentum write (:139-144 re-zeroes the same cells)
-        W2_TRY(w2_xmomentum(c, c->dus, np, keep));   // :147
-        W2_TRY(w2_ymomentum(c, c->dvs, np, keep));   // :158
-        W2_CUDA(cudaMemsetAsync(c->d_norm + 8, 0, 2 * sizeof(unsigned long long), c->stream));
+        if (rc == W2_OK) rc = w2_xmomentum(c, c->dus, np, keep);   // :147
+        if (rc == W2_OK) rc = w2_ymomentum(c, c->dvs, np, keep);   // :158
+        if (rc != W2_OK) break;
+        cudaMemsetAsync(c->d_norm + 8, 0, 2 * sizeof(unsigned long long), c->stream);
         int jlo = 1, jhi = ny;
         w2_clip(c, jlo, jhi);
         dim3 g((nx + 255) / 256, (jhi - jlo + 1) < 2048 ? (jhi - jlo + 1) : 2048);
-        ql_update_kernel<<<g, 256, 0, c->stream>>>(nx, ny, jlo, jhi, c->rank == 0, c->pitch, c->dus, c->dvs, us, vs, c->d_norm + 8);
+        ql_update_kernel<<<g, 256, 0, c->stream>>>(nx, ny, jlo, jhi, c->rank == 0, c->pitch, c->dus, c->dvs, us, vs, c->d_norm + 8, ctl);
         c->launches[1]++;
-        W2_CUDA(cudaGetLastError());
         if (c->world > 1) {
-            W2_TRY(w2_allreduce_max_u64(c, c->d_norm + 8, 2));
+            rc = w2_allreduce_max_u64(c, c->d_norm + 8, 2);
             double *uv[2] = {us, vs};
-            W2_TRY(w2_halo_exchange(c, uv, 2, c->HG));
+            if (rc == W2_OK) rc = w2_halo_exchange(c, uv, 2, c->HG);
+            if (rc != W2_OK) break;
         }
-        W2_CUDA(cudaMemcpyAsync(c->h_norm + 8, c->d_norm + 8, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ql_decide_kernel<<<1, 1, 0, c->stream>>>(ctl, c->d_norm + 8, c->par.qtol, m);   // :182-188
+        c->launches[1]++;
+        if (m + 2 <= c->par.mqiter) {   // somebody will ask for this outcome
+            cudaMemcpyAsync(hctl + 2 + 2 * (m & 1), ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+            cudaEventRecord(c->ev_ql[m & 1], c->stream);
+        }
+    }
+    c->ql_active = 0;
+    if (rc != W2_OK) return rc;
+    W2_CUDA(cudaGetLastError());
+    W2_CUDA(cudaMemcpyAsync(hctl, ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (nQLiter) {
         W2_CUDA(cudaStreamSynchronize(c->stream));
-        double dif[2];
-        memcpy(dif, c->h_norm + 8, 16);
-        const double difmax = dif[0] > dif[1] ? dif[0] : dif[1];  // :182
-        if (difmax <= c->par.qtol) { *nQLiter = m; return W2_OK; }  // :185-188
+        c->host_syncs++;
+        *nQLiter = w2_ql_result(c);
     }
     return W2_OK;
+}
+
+// nQLiter of the last w2_nauxmomentum call; valid once the stream has been synchronised after it
+int w2_ql_result(wolfd2_ctx *c) {
+    const int *hctl = (const int *)(c->h_norm + W2_QL_SLOT);
+    return hctl[0] ? hctl[1] : -1;
 }
 
 // ---- unit-parity entry points ("internal but worth exporting") -------------------------

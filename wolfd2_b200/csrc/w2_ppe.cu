@@ -256,6 +256,27 @@ void rhs_cross_launch(wolfd2_ctx *c, double *p) {
 
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done);
+int w2_sor_fused_result(wolfd2_ctx *c, int *nSorConv, int *converged, int *iters_done);
+
+// Outcome and device time of the last fused solve (the stream has been synchronised since it was enqueued).
+int w2_sor_collect(wolfd2_ctx *c, int *nSorConv, int *converged) {
+    if (!c->sor_pending) {
+        if (c->sor_saved[2]) {   // collected early (another Ppe of the same step needed the events)
+            if (nSorConv) *nSorConv = c->sor_saved[0];
+            if (converged) *converged = c->sor_saved[1];
+            c->sor_saved[2] = 0;
+        }
+        return W2_OK;
+    }
+    c->sor_pending = 0;
+    int iters = 0;
+    W2_TRY(w2_sor_fused_result(c, nSorConv, converged, &iters));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    c->sor_ms += ms;
+    c->sor_iters += iters;
+    return W2_OK;
+}
 
 int g_sor_T = -1;   // set by wolfd2_b200_set_option("sor_fused_T", t); -1: take W2_SOR_T or the default
 static int fused_T() {   // 0 selects the plain half-sweep kernels, 1 or 2 the fused pipeline
@@ -300,15 +321,22 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
         // the second pressure buffer
         double *pf = nullptr;
         int iters = 0;
+        if (c->sor_pending) {   // an earlier solve of this step (the small-scale model's own Ppe) still owns the events
+            W2_CUDA(cudaStreamSynchronize(c->stream));
+            c->host_syncs++;
+            W2_TRY(w2_sor_collect(c, &c->sor_saved[0], &c->sor_saved[1]));
+            c->sor_saved[2] = 1;
+        }
         cudaEventRecord(c->ev[4], c->stream);
         W2_TRY(w2_sor_fused(c, p, c->div, T, nSorConv, converged, &pf, &iters));
         if (pf != p) W2_TRY(w2_copy_field(c, p, pf));
         cudaEventRecord(c->ev[5], c->stream);
-        W2_CUDA(cudaStreamSynchronize(c->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
-        c->sor_ms += ms;
-        c->sor_iters += iters;
+        c->sor_pending = 1;
+        if (nSorConv || converged) {   // the caller wants the outcome now
+            W2_CUDA(cudaStreamSynchronize(c->stream));
+            c->host_syncs++;
+            W2_TRY(w2_sor_collect(c, nSorConv, converged));
+        }
         return W2_OK;
     }
     if (!rb_point) {   // ids 1-4: w2_ppe_other.cu

@@ -178,6 +178,7 @@ int w2_norm_fetch(wolfd2_ctx *c, int nslots, double *out) {
     W2_TRY(w2_allreduce_max_u64(c, c->d_norm, nslots));
     W2_CUDA(cudaMemcpyAsync(c->h_norm, c->d_norm, nslots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     W2_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_syncs++;
     for (int k = 0; k < nslots; ++k) memcpy(&out[k], &c->h_norm[k], 8);
     return W2_OK;
 }

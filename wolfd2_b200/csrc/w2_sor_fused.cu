@@ -449,6 +449,21 @@ __global__ void __launch_bounds__(256) sorf_pack_kernel(int pitch, int rows, con
     }
 }
 
+// colour-split -> interleaved, the source being the buffer the control block names as the current iterate
+__global__ void __launch_bounds__(256) sorf_unpack_cur_kernel(int pitch, int rows, const double *__restrict__ pA,
+                                                              const double *__restrict__ pB, const SorFCtl *__restrict__ ctl,
+                                                              double *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pitch) return;
+    const double *__restrict__ src = ctl->cur ? pB : pA;
+    const int hp = pitch >> 1;
+    const int s = (i & 1) * hp + (i >> 1);
+    for (int j = blockIdx.y; j < rows; j += gridDim.y) {
+        const size_t r = (size_t)pitch * j;
+        dst[r + i] = src[r + s];
+    }
+}
+
 int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
     const int rows = c->rows + 1;
     dim3 grid((c->pitch + 255) / 256, rows < 2048 ? rows : 2048);
@@ -500,7 +515,7 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     const wolfd2_params &par = c->par;
     const int nx = c->nx, ny = c->ny;
     SorFCtl *ctl = (SorFCtl *)c->d_flags;
-    static_assert(sizeof(SorFCtl) <= 64 * sizeof(int), "ctl block too large");
+    static_assert(sizeof(SorFCtl) <= 32 * sizeof(int), "ctl block too large");
     SorFSlabArgs a;
     a.nx = nx; a.ny = ny; a.pitch = c->pitch;
     a.j0 = c->J0; a.j1 = c->J1; a.ext_decide = c->world > 1;
@@ -541,23 +556,25 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         sorf_ready_p2p<<<1, 32, 0, c->stream>>>(a, ++c->peer.solves);
         c->launches[2]++;
     }
-    const int passes_total = (par.msorit + T - 1) / T + 1;
+    // Passes are enqueued WITHOUT waiting for their outcome: every pass kernel returns at once when the control block
+    // says done, so over-enqueuing costs a few microseconds per launch.  The host only throttles itself: chunk k goes
+    // out once the control block as it stood after chunk k-2 has arrived, which also tells it when to stop.  Nothing
+    // is read back at the end: the unpack kernel picks the final buffer from the control block on the device, and
+    // the outcome (iterations, convergence) is copied to pinned memory for w2_sor_collect.
+    const int passes_max = (par.msorit + T - 1) / T + 1;     // + one repeat pass (mid-pass convergence, at most once)
     const double cells = (double)(nx - 1) * (double)nrows;
     int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + (c->world > 1 ? 4.0e-5 : 4.0e-6)));
     if (chunk < 4) chunk = 4;
     if (chunk > 128) chunk = 128;
-    SorFCtl h;
-    memset(&h, 0, sizeof(h));
+    if (!c->ev_sor[0]) for (int k = 0; k < 2; ++k) W2_CUDA(cudaEventCreateWithFlags(&c->ev_sor[k], cudaEventDisableTiming));
     int queued = 0;
-    // an upper bound on launches: every pass may need one redo at the very end only, but a redo can
-    // follow any pass, so keep launching until the control block says done
-    while (true) {
-        // passes still needed if no convergence intervenes (+1 for a possible repeat pass)
-        const int need = (par.msorit - h.m + T - 1) / T + (h.redo > 0 ? 1 : 0);
-        int n = chunk < need ? chunk : need;
-        if (n < 1) n = 1;
-        if (queued + n > 2 * passes_total) n = 2 * passes_total - queued;
-        if (n <= 0) break;
+    for (int k = 0; queued < passes_max; ++k) {
+        if (k >= 2) {
+            W2_CUDA(cudaEventSynchronize(c->ev_sor[k & 1]));
+            c->host_syncs++;
+            if (((const SorFCtl *)(c->h_sor + 32 + 32 * (k & 1)))->done) break;
+        }
+        const int n = chunk < passes_max - queued ? chunk : passes_max - queued;
         for (int q = 0; q < n; ++q) {
             if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
             else W2_TRY(launch_fused<2>(c, a, grid));
@@ -579,21 +596,36 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         }
         queued += n;
         W2_CUDA(cudaGetLastError());
-        W2_CUDA(cudaMemcpyAsync(c->h_flags, ctl, sizeof(SorFCtl), cudaMemcpyDeviceToHost, c->stream));
-        W2_CUDA(cudaStreamSynchronize(c->stream));
-        memcpy(&h, c->h_flags, sizeof(SorFCtl));
-        if (h.done) break;
+        if (queued < passes_max) {
+            W2_CUDA(cudaMemcpyAsync(c->h_sor + 32 + 32 * (k & 1), ctl, sizeof(SorFCtl), cudaMemcpyDeviceToHost, c->stream));
+            W2_CUDA(cudaEventRecord(c->ev_sor[k & 1], c->stream));
+        }
     }
+    {   // back to the reference order, from whichever buffer holds the final iterate
+        const int rows = c->rows + 1;
+        dim3 g((c->pitch + 255) / 256, rows < 2048 ? rows : 2048);
+        sorf_unpack_cur_kernel<<<g, 256, 0, c->stream>>>(c->pitch, rows, pA + c->row_off, pB + c->row_off, ctl, p + c->row_off);
+        c->launches[2]++;
+        W2_CUDA(cudaGetLastError());
+    }
+    W2_CUDA(cudaMemcpyAsync(c->h_sor, ctl, sizeof(SorFCtl), cudaMemcpyDeviceToHost, c->stream));
+    (void)nSorConv; (void)converged; (void)iters_done;
+    *p_final = p;
+    return W2_OK;
+}
+
+// Outcome of the last fused solve; the stream must have been synchronised since.
+int w2_sor_fused_result(wolfd2_ctx *c, int *nSorConv, int *converged, int *iters_done) {
+    SorFCtl h;
+    memcpy(&h, c->h_sor, sizeof(SorFCtl));
     if (!h.done) { w2_set_error("fused SOR did not terminate"); return W2_ERR_CUDA; }
-    if (a.ext_decide == 2) {
+    if (c->world > 1 && c->peer.state == 1) {
         int to = 0;
-        W2_CUDA(cudaMemcpy(&to, &a.mail[a.rank]->timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        W2_CUDA(cudaMemcpy(&to, &c->peer.mail[c->rank]->timeout, sizeof(int), cudaMemcpyDeviceToHost));
         if (to) { w2_set_error("fused SOR: timed out waiting for a peer GPU (rank %d of %d)", c->rank, c->world); return W2_ERR_CUDA; }
     }
     if (converged) *converged = h.nconv > 0;
-    if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : par.msorit;
+    if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : c->par.msorit;
     if (iters_done) *iters_done = h.m;
-    W2_TRY(w2_sorf_pack(c, h.cur ? pB : pA, p, false));   // back to the reference order
-    *p_final = p;
     return W2_OK;
 }

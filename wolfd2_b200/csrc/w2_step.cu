@@ -64,7 +64,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         if (thermal || eqstate) W2_TRY(w2_copy_field(c, ts, t));   // EqState reads ts (:853)
         // us == un on the first pass (not with the ATD model, where un carries uss: then the loop of :114-119 is real), so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
         // on later passes it resets us, vs to un, vn as the reference does
-        W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1 || atd, &nQL));   // :753
+        W2_TRY(w2_nauxmomentum(c, /*init_star=*/l > 1 || atd, nullptr));   // :753; nQLiter comes back with the step's norms
         if (l == 1) {
             // The momentum solve does not read p; step_host uploads p on a second stream meanwhile.  pn <- p
             // (:696) therefore happens here, after that upload has landed.
@@ -77,7 +77,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
         W2_TRY(w2_vel_bc(c, us, vs));                   // :793
         W2_TRY(w2_pres_bc(c, p));                       // :797
         if (l == 1) cudaEventRecord(c->ev[2], s);
-        W2_TRY(w2_ppe(c, us, vs, p, &nSor, &conv));     // :803
+        W2_TRY(w2_ppe(c, us, vs, p, nullptr, nullptr)); // :803; the outcome comes back with the step's norms (w2_sor_collect)
         if (l == 1) cudaEventRecord(c->ev[3], s);
         W2_TRY(w2_pres_bc(c, p));                       // :813
         W2_TRY(w2_project(c, p, us, vs));               // :820
@@ -122,6 +122,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
     W2_TRY(w2_norm_fetch(c, thermal || atd ? 4 : 3, dif)); // syncs the stream
+    if (nme > 0) { nQL = w2_ql_result(c); W2_TRY(w2_sor_collect(c, &nSor, &conv)); }
     float t_tot = 0, t_mom = 0, t_bc1 = 0, t_ppe = 0, t_tail = 0;
     if (nme > 0) {
         cudaEventElapsedTime(&t_tot, c->ev[0], c->ev[6]);
@@ -149,7 +150,7 @@ extern "C" int wolfd2_b200_step(wolfd2_ctx *c, int32_t nsteps, wolfd2_step_log *
     if (!c || nsteps < 0) return W2_ERR_BAD_ARG;
     W2_CUDA(cudaSetDevice(c->device));
     for (int q = 0; q < 4; ++q) c->last_ms[q] = 0.0;
-    c->sor_ms = 0.0; c->sor_iters = 0;
+    c->sor_ms = 0.0; c->sor_iters = 0; c->host_syncs = 0;
     for (int k = 0; k < nsteps; ++k) W2_TRY(one_step(c, logs ? &logs[k] : nullptr));
     return W2_OK;
 }
@@ -180,6 +181,11 @@ extern "C" int wolfd2_b200_step_host(wolfd2_ctx *c, int32_t nsteps, double *u, d
 extern "C" int wolfd2_b200_last_timing(wolfd2_ctx *c, double ms[4], int64_t launches[4]) {
     if (!c) return W2_ERR_BAD_ARG;
     for (int q = 0; q < 4; ++q) { if (ms) ms[q] = c->last_ms[q]; if (launches) launches[q] = c->launches[q]; }
+    return W2_OK;
+}
+extern "C" int wolfd2_b200_last_host_syncs(wolfd2_ctx *c, int64_t *syncs) {
+    if (!c || !syncs) return W2_ERR_BAD_ARG;
+    *syncs = c->host_syncs;
     return W2_OK;
 }
 extern "C" int wolfd2_b200_last_sor_timing(wolfd2_ctx *c, double *ms_total, int64_t *iterations) {

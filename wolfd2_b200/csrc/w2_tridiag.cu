@@ -90,8 +90,9 @@ template <class Prov>
 __global__ void __launch_bounds__(TRI_T, 512 / TRI_T) tri_reduce_kernel(Prov prov, long long n, double *__restrict__ Yg,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, long long nseg, int direct,
-                                                              double *__restrict__ xout) {
+                                                              double *__restrict__ xout, const int *__restrict__ done) {
     __shared__ double sA[TRI_T], sD[TRI_T], sC[TRI_T], sY[TRI_T], sV[TRI_T], sW[TRI_T];
+    if (done != nullptr && *done) return;   // QL loop already converged: this launch was enqueued speculatively
     const int t = threadIdx.x;
     const long long g = blockIdx.x;
     const long long e0 = g * (long long)TRI_S + (long long)t * TRI_M;
@@ -137,9 +138,10 @@ __global__ void __launch_bounds__(TRI_T, 512 / TRI_T) tri_reduce_kernel(Prov pro
 // x = Y - Sg[g-1]*V - Sg[g]*W
 __global__ void __launch_bounds__(256) tri_finalize_kernel(long long n, const double *__restrict__ Y,
                                                            const double *__restrict__ V, const double *__restrict__ W,
-                                                           const double *__restrict__ sig, double *__restrict__ x) {
+                                                           const double *__restrict__ sig, double *__restrict__ x,
+                                                           const int *__restrict__ done) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    if (idx >= n || (done != nullptr && *done)) return;
     const long long g = idx / TRI_S;
     const double sl = g > 0 ? sig[g - 1] : 0.0;
     x[idx] = Y[idx] - sl * V[idx] - sig[g] * W[idx];
@@ -193,7 +195,7 @@ void w2_tri_release(wolfd2_ctx *c) {
 
 // Levels >= 1: solve the separator system whose rows are formed from the level-0 segment records in
 // tri.lv[0].seg (nseg0 of them).  On return *sigma points at the nseg0 separator values.
-int w2_tri_upper(wolfd2_ctx *c, long long nseg0, const double **sigma) {
+int w2_tri_upper(wolfd2_ctx *c, long long nseg0, const double **sigma, const int *done) {
     W2TriWork &w = c->tri;
     long long ns[6], segs[6];
     int nl = 1;
@@ -209,13 +211,13 @@ int w2_tri_upper(wolfd2_ctx *c, long long nseg0, const double **sigma) {
         const int direct = (l == nl - 1);
         ProvSeg ps{w.lv[l - 1].seg, ns[l]};
         tri_reduce_kernel<ProvSeg><<<(unsigned)segs[l], TRI_T, 0, c->stream>>>(ps, ns[l], lv.Y, lv.V, lv.W, lv.seg, segs[l], direct,
-                                                                               direct ? lv.x : nullptr);
+                                                                               direct ? lv.x : nullptr, done);
         c->launches[1]++;
     }
     for (int l = nl - 2; l >= 1; --l) {
         W2TriLevel &lv = w.lv[l];
         const unsigned blocks = (unsigned)((ns[l] + 255) / 256);
-        tri_finalize_kernel<<<blocks, 256, 0, c->stream>>>(ns[l], lv.Y, lv.V, lv.W, w.lv[l + 1].x, lv.x);
+        tri_finalize_kernel<<<blocks, 256, 0, c->stream>>>(ns[l], lv.Y, lv.V, lv.W, w.lv[l + 1].x, lv.x, done);
         c->launches[1]++;
     }
     W2_CUDA(cudaGetLastError());
@@ -232,12 +234,12 @@ static int tri_solve_impl(wolfd2_ctx *c, const ProvSoA &p0, double *x) {
     W2TriLevel &lv = w.lv[0];
     const int direct = nseg0 == 1;
     tri_reduce_kernel<ProvSoA><<<(unsigned)nseg0, TRI_T, 0, c->stream>>>(p0, n0, lv.Y, lv.V, lv.W, lv.seg, nseg0, direct,
-                                                                         direct ? x : nullptr);
+                                                                         direct ? x : nullptr, nullptr);
     c->launches[1]++;
     if (!direct) {
         const double *sigma = nullptr;
         W2_TRY(w2_tri_upper(c, nseg0, &sigma));
-        tri_finalize_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, c->stream>>>(n0, lv.Y, lv.V, lv.W, sigma, x);
+        tri_finalize_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, c->stream>>>(n0, lv.Y, lv.V, lv.W, sigma, x, nullptr);
         c->launches[1]++;
     }
     W2_CUDA(cudaGetLastError());
