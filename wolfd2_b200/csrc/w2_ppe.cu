@@ -287,7 +287,19 @@ static int fused_T() {   // 0 selects the plain half-sweep kernels, 1 or 2 the f
     return t;
 }
 
+static int ppe_impl(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSorConv, int *converged, bool deferred);
+
 int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSorConv, int *converged) {
+    // deferred outcome (both pointers null): the fused path leaves it pending for w2_sor_collect; the other solvers
+    // know it at once and park it where w2_sor_collect looks
+    const bool deferred = nSorConv == nullptr && converged == nullptr;
+    int n = 0, cv = 0;
+    W2_TRY(ppe_impl(c, u, v, p, deferred ? &n : nSorConv, deferred ? &cv : converged, deferred));
+    if (deferred && !c->sor_pending) { c->sor_saved[0] = n; c->sor_saved[1] = cv; c->sor_saved[2] = 1; }
+    return W2_OK;
+}
+
+static int ppe_impl(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSorConv, int *converged, bool deferred) {
     const wolfd2_params &par = c->par;
     if (par.nPpeSolver < 1 || par.nPpeSolver > 6) {
         w2_set_error("Wrong nPpeSolver flag passed to Ppe: %d", par.nPpeSolver);   // :238-239
@@ -332,7 +344,7 @@ int w2_ppe(wolfd2_ctx *c, const double *u, const double *v, double *p, int *nSor
         if (pf != p) W2_TRY(w2_copy_field(c, p, pf));
         cudaEventRecord(c->ev[5], c->stream);
         c->sor_pending = 1;
-        if (nSorConv || converged) {   // the caller wants the outcome now
+        if (!deferred) {   // the caller wants the outcome now
             W2_CUDA(cudaStreamSynchronize(c->stream));
             c->host_syncs++;
             W2_TRY(w2_sor_collect(c, nSorConv, converged));

@@ -477,6 +477,8 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 
 // ---------------------------------------------------------------------------------------- host
 
+int g_sor_band_opt = 1;   // option "sor_band_opt": 0 = always one full wave of bands
+
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     const size_t smem = SorFCfg<T>::smem;
@@ -540,6 +542,23 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     if (per_sm < 1) per_sm = 1;
     int want = (per_sm * c->num_sms) / a.nstrips;
     if (want < 1) want = 1;
+    // The kernel is bound by instruction issue, so what counts is the number of row steps an SM executes per pass:
+    // (CTAs per SM) x (rows of a band + the 4T halo rows and the pipeline fill/drain, ~ 8T + 5 rows).  A full wave of
+    // short bands pays that overhead once per CTA; on small grids (1024^2: 18-row bands) half as many bands of twice
+    // the height do less work in total.  Large grids keep the full wave (the estimate must win by 10 %).
+    if (g_sor_band_opt) {
+        const int ovh = 8 * T + 5;
+        auto cost = [&](int nb) {
+            const int rpb = (nrows + nb - 1) / nb;
+            const int nbands = (nrows + rpb - 1) / rpb;
+            const int ctas = a.nstrips * nbands;
+            return (long long)((ctas + c->num_sms - 1) / c->num_sms) * (rpb + ovh);
+        };
+        int best = want;
+        for (int nb = want - 1; nb >= 1; --nb)
+            if (cost(nb) * 10 < cost(best) * 9 || (best != want && cost(nb) < cost(best))) best = nb;
+        want = best;
+    }
     a.rows_per_band = (nrows + want - 1) / want;
     if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
     a.nbands = (nrows + a.rows_per_band - 1) / a.rows_per_band;
