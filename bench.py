@@ -446,7 +446,7 @@ def run_gpu(args):
         api.set_option(k, int(v))
     from wolfd2_b200 import slab
     n, nyg, scaling = resolve_grid(args, world)
-    lazy = (n - 1) * (nyg - 1) // world > 40e6      # large slabs: metrics built and uploaded window by window
+    lazy = (n - 1) * (nyg - 1) // world > 20e6      # large slabs: metrics built and uploaded window by window, on host threads
     if world > 1:
         slab.init_comm(dist, local)     # the library's own NCCL communicator; torch only carries the id
         d = make_deck(args.workload, n, args.fixed_work, args.q_iters, args.s_iters, ny=nyg, slab=(rank, world), lazy=lazy,

@@ -22,7 +22,7 @@ from . import _abi
 from ._abi import Metrics, Params, Regions, SmallScale, StepLog, Thermal, Traject, c_f64p, c_i32p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwolfd2_b200.so")
+LIB_PATH = os.environ.get("WOLFD2_B200_LIB") or os.path.join(_HERE, "libwolfd2_b200.so")   # (env: A/B builds of the same source)
 
 F_U, F_V, F_P, F_US, F_VS, F_UN, F_VN, F_PN, F_D, F_DN, F_B, F_T, F_TS, F_TN, F_USS, F_VSS, F_PSS, F_TSS = range(18)
 

@@ -28,7 +28,14 @@
 
 #define SF_W 256              // strip width held in shared memory (cells)
 #define SF_HALF (SF_W / 2)    // cells of one colour parity per strip row
-#define SF_CPT 1              // column pairs per thread (threads per stage = SF_HALF / SF_CPT)
+// Column pairs per thread (threads per stage = SF_HALF / SF_CPT).  2: each thread relaxes two cells of a row as
+// straight-line code (w2_div_fast: no branch inside the update), so the two dependent fp64 chains overlap and the
+// per-row costs (barrier, mbarrier wait, ring bookkeeping) are paid once per two updates: 0.2175 -> 0.2101 ms per T=2
+// pass at 4096^2.  (1 with the same straight-line update: 0.2654 ms -- every lane then pays the full quotient that the
+// old zero-numerator branch skipped; 2 with the branchy update was measured slower than 1 in round 1.)
+#ifndef SF_CPT
+#define SF_CPT 2
+#endif
 #define SF_TPS (SF_HALF / SF_CPT)
 #define SF_PADL 2             // pad cells on each side of a half row (keeps TMA destinations 16-byte aligned)
 #define SF_HSTR (SF_HALF + 2 * SF_PADL)   // one half row in shared memory
@@ -272,23 +279,38 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         }
         if (any_row && (unsigned)(q - qlo) <= qspan) {
             const bool row_owned = (unsigned)(q - jA) <= jspan;
+            // straight-line code for all SF_CPT cells of this thread: every operand is loaded and every quotient formed
+            // (w2_div_fast) before anything is branched on, so the independent updates overlap; cells that are not
+            // unknowns compute on whatever the ring holds and are simply not stored
+            double pcv[SF_CPT], sumv[SF_CPT], a3v[SF_CPT], qdv[SF_CPT], bbv[SF_CPT];
+            bool okv[SF_CPT], valid[SF_CPT];
+            bool all_ok = true;
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {
-                if (!((vmask >> (2 * u + par)) & 1u)) continue;
+                valid[u] = (vmask >> (2 * u + par)) & 1u;
                 const unsigned iq = off_q + ha8 + u * PAIRB, is = off_s + ha8 + u * PAIRB, in = off_n + ha8 + u * PAIRB,
                                iw = off_q + hw8 + u * PAIRB;
-                const double bb = lds_f64(aB + iq);
-                const double pc = lds_f64(aP + iq);
-                // all ten operands are read before anything is decided: with the loads inside an else-branch the
-                // warp pays two shared-memory round trips per update instead of one
+                bbv[u] = lds_f64(aB + iq);
+                pcv[u] = lds_f64(aP + iq);
                 const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
                 const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
-                const double a3 = -a4 - a2 - a5 - a1;
-                double sum = bb - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
-                sum = w2_div_exact(sum, a3) - pc;
-                if (bb != bb) sum = 0.0 - pc;   // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
-                sts_f64(aP + iq, pc + sorrel * sum);
-                if (row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
+                a3v[u] = -a4 - a2 - a5 - a1;
+                sumv[u] = bbv[u] - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
+                qdv[u] = w2_div_fast(sumv[u], a3v[u], okv[u]);
+                all_ok = all_ok && (okv[u] || !valid[u]);
+            }
+            if (!all_ok) {   // operands outside the fast path's range (tiny or huge numerators, ...): the full division
+#pragma unroll
+                for (int u = 0; u < SF_CPT; ++u)
+                    if (!okv[u] && valid[u]) qdv[u] = sumv[u] / a3v[u];
+            }
+#pragma unroll
+            for (int u = 0; u < SF_CPT; ++u) {
+                const unsigned iq = off_q + ha8 + u * PAIRB;
+                double sum = qdv[u] - pcv[u];
+                if (bbv[u] != bbv[u]) sum = 0.0 - pcv[u];   // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
+                if (valid[u]) sts_f64(aP + iq, pcv[u] + sorrel * sum);
+                if (valid[u] && row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
             }
         }
         __syncthreads();
@@ -477,8 +499,6 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 
 // ---------------------------------------------------------------------------------------- host
 
-int g_sor_band_opt = 1;   // option "sor_band_opt": 0 = always one full wave of bands
-
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     const size_t smem = SorFCfg<T>::smem;
@@ -542,23 +562,9 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     if (per_sm < 1) per_sm = 1;
     int want = (per_sm * c->num_sms) / a.nstrips;
     if (want < 1) want = 1;
-    // The kernel is bound by instruction issue, so what counts is the number of row steps an SM executes per pass:
-    // (CTAs per SM) x (rows of a band + the 4T halo rows and the pipeline fill/drain, ~ 8T + 5 rows).  A full wave of
-    // short bands pays that overhead once per CTA; on small grids (1024^2: 18-row bands) half as many bands of twice
-    // the height do less work in total.  Large grids keep the full wave (the estimate must win by 10 %).
-    if (g_sor_band_opt) {
-        const int ovh = 8 * T + 5;
-        auto cost = [&](int nb) {
-            const int rpb = (nrows + nb - 1) / nb;
-            const int nbands = (nrows + rpb - 1) / rpb;
-            const int ctas = a.nstrips * nbands;
-            return (long long)((ctas + c->num_sms - 1) / c->num_sms) * (rpb + ovh);
-        };
-        int best = want;
-        for (int nb = want - 1; nb >= 1; --nb)
-            if (cost(nb) * 10 < cost(best) * 9 || (best != want && cost(nb) < cost(best))) best = nb;
-        want = best;
-    }
+    // (Measured and rejected: half as many bands of twice the height on small grids, where the 4T halo rows and the
+    // pipeline fill are a large share of an 18-row band -- 1024^2: 31.4 -> 37.5 us per pass, 2048^2: 70.7 -> 95.5 us.
+    // Two resident CTAs per SM hide the per-row block barrier of each other; one tall CTA cannot.)
     a.rows_per_band = (nrows + want - 1) / want;
     if (a.rows_per_band < 8 * T) a.rows_per_band = 8 * T;
     a.nbands = (nrows + a.rows_per_band - 1) / a.rows_per_band;
@@ -583,7 +589,7 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     const int passes_max = (par.msorit + T - 1) / T + 1;     // + one repeat pass (mid-pass convergence, at most once)
     const double cells = (double)(nx - 1) * (double)nrows;
     int chunk = (int)(2.0e-3 / (cells * 40.0 / 5.0e12 + (c->world > 1 ? 4.0e-5 : 4.0e-6)));
-    if (chunk < 4) chunk = 4;
+    if (chunk < 32) chunk = 32;   // a pass launched after the solve has finished costs ~2 us: 64 of them are cheaper than a poll per 2 ms
     if (chunk > 128) chunk = 128;
     if (!c->ev_sor[0]) for (int k = 0; k < 2; ++k) W2_CUDA(cudaEventCreateWithFlags(&c->ev_sor[k], cudaEventDisableTiming));
     int queued = 0;
