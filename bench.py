@@ -626,7 +626,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cavity", choices=["channel", "cavity", "bstep"])
     ap.add_argument("--outlet", default="fully_dev", choices=["fully_dev", "mass_cons"])
-    ap.add_argument("--n", type=int, default=None, help="grid points per side (default: 4096 on 1 GPU, 16384 on N > 1)")
+    # (--grid-n: under `python -m torch.distributed.run` a bare --n is claimed by the launcher's own abbreviations)
+    ap.add_argument("--n", "--grid-n", dest="n", type=int, default=None,
+                    help="grid points per side (default: 4096 on 1 GPU, 16384 on N > 1)")
     ap.add_argument("--mode", default="fixed", choices=["fixed", "converged"])
     ap.add_argument("--q-iters", type=int, default=2)
     ap.add_argument("--s-iters", type=int, default=100)

@@ -213,6 +213,15 @@ int wolfd2_b200_get_particles(wolfd2_ctx *ctx, double *xp, double *yp, double *u
  * it needs the thermal region tables (wolfd2_b200_set_thermal).  Any output pointer may be NULL.  One GPU only. */
 int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double *vbar, double *pav, double *tav);
 
+/* Time-series monitor points: SaveTimeSrs case 1 (src/file_manip.f:806-834) as called from src/main.f:984-995.  After
+ * set_probes every wolfd2_b200_step samples u, v, p, t, uss, vss, pss, tss at the points (iTS, jTS) (1-based, as in
+ * the reference; points outside 1..nx, 1..ny become (1,1) with the reference's warning) whenever the number of steps
+ * taken since set_probes is a multiple of freq (nTSFreq).  get_probe_records returns the records gathered since the
+ * last call, out[rec][point][8], with the step number of each; *nrec = records copied (at most maxrec; with out NULL:
+ * the number waiting).  The `.ts` files themselves are written by the host (wolfd2_b200/timeseries.py).  One GPU. */
+int wolfd2_b200_set_probes(wolfd2_ctx *ctx, int32_t npoints, const int32_t *iTS, const int32_t *jTS, int32_t freq);
+int wolfd2_b200_get_probe_records(wolfd2_ctx *ctx, int32_t maxrec, double *out, int32_t *steps, int32_t *nrec);
+
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
 int wolfd2_b200_download_field(wolfd2_ctx *ctx, int32_t which, double *host);

@@ -63,6 +63,8 @@ def lib():
     L.wolfd2_b200_set_trajectories.argtypes = [C.c_void_p, C.POINTER(Traject)] + [c_f64p] * 9 + [c_i32p]
     L.wolfd2_b200_get_particles.argtypes = [C.c_void_p] + [c_f64p] * 4 + [c_i32p]
     L.wolfd2_b200_node_averages.argtypes = [C.c_void_p, C.c_int32] + [c_f64p] * 4
+    L.wolfd2_b200_set_probes.argtypes = [C.c_void_p, C.c_int32, c_i32p, c_i32p, C.c_int32]
+    L.wolfd2_b200_get_probe_records.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_i32p, c_i32p]
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_download_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_upload_metric_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_f64p]
@@ -267,6 +269,24 @@ class Context:
         _check(lib().wolfd2_b200_compare_global(self._h, glob._h if glob is not None else None, which, C.byref(n), C.byref(m)),
                "wolfd2_b200_compare_global")
         return int(n.value), float(m.value)
+
+    def set_probes(self, iTS, jTS, freq=1):
+        """Time-series monitor points (SaveTimeSrs): sampled inside every freq-th step from the resident fields."""
+        i = np.ascontiguousarray(iTS, dtype=np.int32)
+        j = np.ascontiguousarray(jTS, dtype=np.int32)
+        self._nprobes = int(i.size)
+        _check(lib().wolfd2_b200_set_probes(self._h, i.size, i.ctypes.data_as(c_i32p), j.ctypes.data_as(c_i32p), int(freq)),
+               "wolfd2_b200_set_probes")
+
+    def probe_records(self):
+        """(steps[nrec], records[nrec][npoints][8]) gathered since the last call; columns u, v, p, t, uss, vss, pss, tss."""
+        n = C.c_int32(0)
+        _check(lib().wolfd2_b200_get_probe_records(self._h, 0, None, None, C.byref(n)), "wolfd2_b200_get_probe_records")
+        out = np.zeros((max(n.value, 1), self._nprobes, 8))
+        steps = np.zeros(max(n.value, 1), dtype=np.int32)
+        _check(lib().wolfd2_b200_get_probe_records(self._h, n.value, out.ctypes.data_as(c_f64p), steps.ctypes.data_as(c_i32p),
+                                                   C.byref(n)), "wolfd2_b200_get_probe_records")
+        return steps[:n.value], out[:n.value]
 
     def upload(self, which, arr):
         assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]

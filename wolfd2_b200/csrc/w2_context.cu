@@ -258,6 +258,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     w2_atd_release(c);
     w2_traj_release(c);
+    w2_probes_release(c);
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);

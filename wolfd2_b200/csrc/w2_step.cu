@@ -119,6 +119,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     // :1000-1024; enqueued before the closing event so that the step time includes the particle integration
     // (the norms above do not depend on it; after a divergence abort the particle state is as undefined as the fields)
     if (c->traj && c->traj->active) W2_TRY(w2_traject_step(c));
+    W2_TRY(w2_probes_step(c));                      // :984-995 time-series monitor points
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
     W2_TRY(w2_norm_fetch(c, thermal || atd ? 4 : 3, dif)); // syncs the stream
