@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
     double lmax = 0.0;
 
     constexpr unsigned ROWB = SF_STRIDE * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8, PAIRB = SF_TPS * 8;
-    const unsigned sbase = smem_u32(smem_raw);
+    unsigned sbase = smem_u32(smem_raw);
+    asm volatile("" : "+r"(sbase));   // opaque: keeps the shared window base in a register instead of re-deriving it per row
     const unsigned aP = sbase, aB = sbase + RINGB, aU = sbase + 2 * RINGB, aV = sbase + 3 * RINGB, aBar = sbase + 4 * RINGB;
     const unsigned base8 = (SF_PADL + kk0) * 8;
 
@@ -299,10 +300,10 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
                 qdv[u] = w2_div_fast(sumv[u], a3v[u], okv[u]);
                 all_ok = all_ok && (okv[u] || !valid[u]);
             }
-            if (!all_ok) {   // operands outside the fast path's range (tiny or huge numerators, ...): the full division
+            if (!all_ok) {   // operands outside the fast path's range (zero, tiny or huge numerators, ...)
 #pragma unroll
                 for (int u = 0; u < SF_CPT; ++u)
-                    if (!okv[u] && valid[u]) qdv[u] = sumv[u] / a3v[u];
+                    if (!okv[u] && valid[u]) qdv[u] = w2_div_slow(sumv[u], a3v[u]);
             }
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {
