@@ -222,6 +222,18 @@ int wolfd2_b200_node_averages(wolfd2_ctx *ctx, int32_t set, double *util, double
 int wolfd2_b200_set_probes(wolfd2_ctx *ctx, int32_t npoints, const int32_t *iTS, const int32_t *jTS, int32_t freq);
 int wolfd2_b200_get_probe_records(wolfd2_ctx *ctx, int32_t maxrec, double *out, int32_t *steps, int32_t *nrec);
 
+/* Time averaging, the reference's -D_TIMEAVG_ mode, on the resident fields.  wolfd2_b200_timeavg(ctx, op): op 0 = begin
+ * (src/main.f:510-541: the nineteen arrays zeroed), 1 / 2 = accumulate pass 1 / pass 2 at the end of every following
+ * wolfd2_b200_step (:1107-1208: node averages via VelAvg / TAveraged / PTDAvg, then the sums), 3 = stop, 4 = release.
+ * timeavg_finish(pass, nts, uref, dlref): :1239-1297 (division by the steps taken, turbulence kinetic energy,
+ * dissipation rate (...)*uref*dlref/re).  As in the reference the run is made twice: pass 1 for the means, then --
+ * from the same initial state -- pass 2 for the fluctuations about them.  timeavg_get: array `which` = 0..18 in the order
+ * ubar vbar tbar pbar upb vpb tpb upupb vpvpb upvpb uptpb vptpb upxsb upysb vpxsb vpysb trbke dssrt dtdyb, host layout
+ * (0:mnx,0:mny); wolfd2_b200/plot3d.py save_tmavg_p3d writes SaveTmAvgP3D's file from them.  One GPU. */
+int wolfd2_b200_timeavg(wolfd2_ctx *ctx, int32_t op);
+int wolfd2_b200_timeavg_finish(wolfd2_ctx *ctx, int32_t pass, int32_t nts, double uref, double dlref);
+int wolfd2_b200_timeavg_get(wolfd2_ctx *ctx, int32_t which, double *host);
+
 /* Host <-> device copies of one field, host layout (0:mnx,0:mny). */
 int wolfd2_b200_upload_field(wolfd2_ctx *ctx, int32_t which, const double *host);
 int wolfd2_b200_download_field(wolfd2_ctx *ctx, int32_t which, double *host);

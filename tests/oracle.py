@@ -154,6 +154,27 @@ class Oracle:
                                     *[a.ctypes.data_as(_abi.c_f64p) if a is not None else None for a in f], nsteps, logs)
         return rc, [dict(nQLiter=l.nQLiter, nSorConv=l.nSorConv, dif=list(l.dif)) for l in logs]
 
+    def timeavg_accumulate(self, deck, npass, u, v, p, t, us, vs, ts, pn, acc):
+        """src/main.f:1107-1208 on the 19 accumulators `acc` (list of (0:mnx,0:mny) arrays, SaveTmAvgP3D order + gradients)."""
+        self.config(deck.mnx, deck.mny, deck.regions.mgri, deck.regions.mgrj)
+        r, m = deck.regions, deck.metrics
+        pp = (_abi.c_f64p * 19)(*[a.ctypes.data_as(_abi.c_f64p) for a in acc])
+        f = self.lib.orc_timeavg_accumulate
+        f.restype = None
+        f.argtypes = [C.c_int32] * 3 + [_abi.c_i32p] * 4 + [_abi.c_f64p] * 14 + [C.POINTER(_abi.c_f64p)]
+        f(npass, deck.nx, deck.ny, r.nReg.ctypes.data_as(_abi.c_i32p), r.nRegBrd.ctypes.data_as(_abi.c_i32p),
+          r.nRegType.ctypes.data_as(_abi.c_i32p), r.nTRgType.ctypes.data_as(_abi.c_i32p),
+          r.dTRgVal.ctypes.data_as(_abi.c_f64p),
+          *[m[k].ctypes.data_as(_abi.c_f64p) for k in ("djn", "xen", "yen", "xzn", "yzn")],
+          *[a.ctypes.data_as(_abi.c_f64p) for a in (u, v, p, t, us, vs, ts, pn)], pp)
+
+    def timeavg_finish(self, deck, npass, nts, acc):
+        pp = (_abi.c_f64p * 19)(*[a.ctypes.data_as(_abi.c_f64p) for a in acc])
+        f = self.lib.orc_timeavg_finish
+        f.restype = None
+        f.argtypes = [C.c_int32] * 4 + [C.c_double] * 3 + [C.POINTER(_abi.c_f64p)]
+        f(npass, deck.nx, deck.ny, nts, deck.uref, deck.dlref, deck.re, pp)
+
     def ss_map(self, deck, family, plane):
         """A copy of one plane of the oracle's saved map iterates."""
         ptr = self.lib.orc_ss_map(family, plane)

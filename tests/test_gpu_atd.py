@@ -17,6 +17,8 @@ pytestmark = pytest.mark.gpu
 
 TOL_SS = 1e-9       # uss, vss, tss, pss of one SmallScale call (see module docstring)
 TOL_STEP = 1e-8     # u, v, p, t after a step with the ATD blocks on (the model's output feeds the next step)
+TOL_FIRST = 1e-10   # the same after the FIRST step with the model on
+GROWTH = 200.0      # bound on the step-to-step growth of the worst error (measured: see test_steps_with_smallscale)
 TOL_POW = 1e-12     # particle state with the Chein / Tilly drag laws (pow)
 
 
@@ -225,15 +227,28 @@ def test_steps_with_smallscale(api, orc, d):
         for w, a in ((F_USS, ss[0]), (F_VSS, ss[1]), (F_PSS, ss[2]), (F_TSS, ss[3])):
             assert rel_l2(ctx.download(w), a) <= TOL_SS
         active = False
+        prev = None
         for k in range(4):
             logs = ctx.step(1)
             rc, ol = orc.step_full(d, u, v, p, t, dd, ss_fields=ss, nsteps=1)
             assert rc == 0
             assert logs[0]["nQLiter"] == ol[0]["nQLiter"] and logs[0]["nSorConv"] == ol[0]["nSorConv"], (k, logs, ol)
+            errs = {}
             for name, w, a in (("u", F_U, u), ("v", F_V, v), ("p", F_P, p), ("uss", F_USS, ss[0]), ("vss", F_VSS, ss[1]),
                                ("pss", F_PSS, ss[2]), ("tss", F_TSS, ss[3]), ("t", F_T, t)):
                 e = rel_l2(ctx.download(w), a)
                 assert e <= TOL_STEP, (k, name, e)
+                errs[name] = e
+            # The tolerance above is loose because the chaotic maps amplify the ulp-level pow/tanh differences; a
+            # genuine defect would not hide below it: the first step, before any amplification has accumulated, is
+            # held to TOL_FIRST, and from one step to the next the worst error may grow by GROWTH at most.
+            worst = max(errs.values())
+            print(f"ATD step {k}: worst rel-L2 {worst:.2e} ({max(errs, key=errs.get)})")
+            if k == 0:
+                assert worst <= TOL_FIRST, errs
+            else:
+                assert worst <= GROWTH * max(prev, 1e-15), (k, worst, prev, errs)
+            prev = worst
             np.testing.assert_allclose(logs[0]["dif"], ol[0]["dif"], rtol=1e-6, atol=1e-12)
             active = active or np.abs(ss[0]).max() > 1e-6
         assert active, "the small-scale model never switched on in this deck"

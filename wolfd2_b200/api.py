@@ -63,6 +63,9 @@ def lib():
     L.wolfd2_b200_set_trajectories.argtypes = [C.c_void_p, C.POINTER(Traject)] + [c_f64p] * 9 + [c_i32p]
     L.wolfd2_b200_get_particles.argtypes = [C.c_void_p] + [c_f64p] * 4 + [c_i32p]
     L.wolfd2_b200_node_averages.argtypes = [C.c_void_p, C.c_int32] + [c_f64p] * 4
+    L.wolfd2_b200_timeavg.argtypes = [C.c_void_p, C.c_int32]
+    L.wolfd2_b200_timeavg_finish.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double]
+    L.wolfd2_b200_timeavg_get.argtypes = [C.c_void_p, C.c_int32, c_f64p]
     L.wolfd2_b200_set_probes.argtypes = [C.c_void_p, C.c_int32, c_i32p, c_i32p, C.c_int32]
     L.wolfd2_b200_get_probe_records.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_i32p, c_i32p]
     L.wolfd2_b200_upload_field.argtypes = [C.c_void_p, C.c_int32, c_f64p]
@@ -269,6 +272,23 @@ class Context:
         _check(lib().wolfd2_b200_compare_global(self._h, glob._h if glob is not None else None, which, C.byref(n), C.byref(m)),
                "wolfd2_b200_compare_global")
         return int(n.value), float(m.value)
+
+    TIMEAVG_NAMES = ("ubar vbar tbar pbar upb vpb tpb upupb vpvpb upvpb uptpb vptpb upxsb upysb vpxsb vpysb "
+                     "trbke dssrt dtdyb").split()
+
+    def timeavg(self, op):
+        """Time-averaging mode (-D_TIMEAVG_): op 'begin', 1 / 2 (accumulate pass 1 / 2 from now on), 'stop', 'release'."""
+        code = {"begin": 0, 1: 1, 2: 2, "stop": 3, "release": 4}[op]
+        _check(lib().wolfd2_b200_timeavg(self._h, code), "wolfd2_b200_timeavg")
+
+    def timeavg_finish(self, npass, nts):
+        _check(lib().wolfd2_b200_timeavg_finish(self._h, npass, nts, self.deck.uref, self.deck.dlref), "wolfd2_b200_timeavg_finish")
+
+    def timeavg_get(self, name):
+        out = self.deck.new_field()
+        _check(lib().wolfd2_b200_timeavg_get(self._h, self.TIMEAVG_NAMES.index(name), out.ctypes.data_as(c_f64p)),
+               "wolfd2_b200_timeavg_get")
+        return out
 
     def set_probes(self, iTS, jTS, freq=1):
         """Time-series monitor points (SaveTimeSrs): sampled inside every freq-th step from the resident fields."""

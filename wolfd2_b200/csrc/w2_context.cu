@@ -235,6 +235,7 @@ static int ctx_create_body(wolfd2_ctx *c, int nx, int ny, int rank, int world, c
     W2_TRY(balloc(c, &c->tmask, 1));
     W2_TRY(falloc(c, &c->heat_s));
     W2_CUDA(cudaMalloc((void **)&c->dth, sizeof(W2Thermal)));
+    W2_CUDA(cudaMemset(c->dth, 0, sizeof(W2Thermal)));   // no heat sources, internal faces: TAveraged is then the plain average
     c->th.pe = 1.0;
     // chain arrays are read in whole segments by the tridiagonal solver: pad generously
     const long long nmax = ((long long)nx * (long long)ny / 4096 + 3) * 4096;
@@ -259,6 +260,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     w2_atd_release(c);
     w2_traj_release(c);
     w2_probes_release(c);
+    w2_timeavg_release(c);
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);

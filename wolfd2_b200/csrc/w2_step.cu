@@ -120,6 +120,7 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     // (the norms above do not depend on it; after a divergence abort the particle state is as undefined as the fields)
     if (c->traj && c->traj->active) W2_TRY(w2_traject_step(c));
     W2_TRY(w2_probes_step(c));                      // :984-995 time-series monitor points
+    W2_TRY(w2_timeavg_step(c));                     // :1107-1208 time-average accumulation
     cudaEventRecord(c->ev[6], s);
     double dif[4] = {0, 0, 0, 0};
     W2_TRY(w2_norm_fetch(c, thermal || atd ? 4 : 3, dif)); // syncs the stream

@@ -117,6 +117,35 @@ def save_std_vars_p3d(prefix, nx, ny, u, v, p, t=None, us=None, vs=None, ps=None
     return nvars
 
 
+TMAVG_ORDER = "ubar vbar - tbar pbar upb vpb tpb upupb vpvpb upvpb uptpb vptpb trbke dssrt dtdyb".split()
+TMAVG_NAMES = ["Avgd. U-vel ; Avgd. Velocity", "Avgd. V-vel", "Avgd. W-vel (null)", "Avgd. T", "Avgd. P", "Avgd. up", "Avgd. vp",
+               "Avgd. tp", "Avgd. up * up", "Avgd. vp * vp", "Avgd. up * vp", "Avgd. up * tp", "Avgd. vp * tp",
+               "Avgd. Turb. Kinetic En.", "Avgd. Dissipation Rate ", "Avgd. dT*/dy*"]
+
+
+def save_tmavg_p3d(prefix, nx, ny, arrays, form=FT_UNFORMATTED):
+    """SaveTmAvgP3D (src/file_manip.f:899-1012): `prefix.qqq` with 16 SINGLE-precision planes (sngl(...), the third a
+    null W-velocity) and `prefix.nam`.  arrays: dict name -> (0:mnx,0:mny) array (Context.timeavg_get)."""
+    zero = np.zeros((ny, nx), dtype=np.float32)
+    planes = [zero if k == "-" else _nodes(arrays[k], nx, ny).astype(np.float32) for k in TMAVG_ORDER]
+    if form == FT_UNFORMATTED:
+        with open(prefix + ".qqq", "wb") as f:
+            _write_record(f, struct.pack("<iii", nx, ny, len(planes)))
+            _write_record(f, b"".join(pl.astype("<f4").tobytes() for pl in planes))
+    elif form == FT_FORMATTED:
+        with open(prefix + ".qqq", "w") as f:
+            f.write(f" {nx:11d} {ny:11d} {len(planes):11d}\n")
+            flat = np.concatenate([pl.ravel() for pl in planes])
+            for k in range(0, flat.size, 5):        # list-directed REAL*4: five per line in gfortran's layout
+                f.write(" " + " ".join(f"{x:15.8E}" for x in flat[k:k + 5]) + "\n")
+    else:
+        raise ValueError("* Wrong nForm flag passed to SaveTmAvgP3D")
+    with open(prefix + ".nam", "w") as f:
+        for line in TMAVG_NAMES:
+            f.write(" " + line + "\n")
+    return len(planes)
+
+
 def read_std_vars_p3d(path, form=FT_UNFORMATTED):
     """Read a `.qqq` file back: (nx, ny, [planes (ny, nx)])."""
     if form == FT_UNFORMATTED:
