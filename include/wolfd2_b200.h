@@ -276,7 +276,8 @@ void wolfd2_b200_host_free(void *p);
  * A0..A1 (its rows J0..J1 plus HG halo rows, clipped to 0..ny+1); the arrays it passes to create_slab /
  * upload / download / step_host hold those rows only, host row 0 = global row A0, so mny >= A1-A0.
  * params and region tables stay global.  Results are bit-identical to the one-GPU run.
- * Supported: ppe_solver 5/6, Cartesian grid, nx >= 254, no OUTLT2 faces. */
+ * Supported: ppe_solver 5/6, Cartesian grid, nx >= 254; every face type (the OUTLT2 recurrences along west / east faces
+ * cross the slabs through peer-mapped gather buffers and need CUDA IPC between the GPUs). */
 /* out = {J0, J1, A0, A1, HG} for `rank` of `world` */
 int wolfd2_b200_slab_layout(int32_t nx, int32_t ny, int32_t world, int32_t rank, int32_t out[5]);
 /* NCCL communicator over the ranks: rank 0 makes the 128-byte id, the launcher hands it to every rank

@@ -32,6 +32,12 @@ def cases():
                                         msorit=300, sorrel=1.3), 2
     yield "bstep400x128", deck.backward_step(400, ny=128, re=50.0, dt=stable_dt(400, 128, 50.0), fully_dev=True,
                                              sortol=1e-5, msorit=300, sorrel=1.3), 2
+    # mass-conserving outlets (OUTLT2): the ghost fill of an east / west face is a recurrence along the whole face,
+    # i.e. across the slabs (w2_bc.cu bc_scan_slab)
+    yield "channel320x96_mass_cons", deck.channel(320, ny=96, re=50.0, dt=stable_dt(320, 96, 50.0), fully_dev=False,
+                                                  sortol=1e-5, msorit=300, sorrel=1.3), 3
+    yield "bstep400x128_mass_cons", deck.backward_step(400, ny=128, re=50.0, dt=stable_dt(400, 128, 50.0), fully_dev=False,
+                                                       sortol=1e-5, msorit=300, sorrel=1.3), 2
     yield "cavity512x2048", deck.cavity(512, ny=2048, re=400.0, dt=stable_dt(512, 2048, 400.0), sortol=1e-7, msorit=60,
                                         sorrel=1.7), 2
     yield "cavity512x2048_filter", deck.cavity(512, ny=2048, re=400.0, dt=stable_dt(512, 2048, 400.0), sortol=1e-7,

@@ -11,6 +11,8 @@
 // memory, one thread runs the carried recurrence over the chunk from there, and the chunk is written
 // back in parallel (a 4096-point face: 50 us instead of 2 ms of dependent global loads).
 // HBM traffic is negligible (kernel K3).
+#include <string.h>
+
 #include "w2.cuh"
 
 #define BC_THREADS 1024
@@ -50,10 +52,59 @@ __device__ __forceinline__ void bc_scan(double *s1, double *s2, double prev0, do
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long bc_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The same recurrence on a row slab (west / east faces: k is the row index): the addends of the rows lo..hi are spread
+// over the ranks.  Each rank forms those of the rows it updates (E0..E1) and stores them -- and the start value, if it
+// updates row lo-1 -- into EVERY rank's gather buffer (peer stores over NVLink), publishes the scan number in every
+// rank's flag word and waits for all the others: a barrier across the GPUs.  Then every rank runs the whole recurrence
+// from its own copy, i.e. exactly the additions of bc_scan in the same order, and keeps the rows it holds (jlo..jhi).
+// Buffers alternate with the parity of the scan number: nobody can be two scans ahead of a rank that is still reading.
+template <class T1, class T2, class P0, class Put>
+__device__ __forceinline__ void bc_scan_slab(double *s1, double *s2, const W2BcPeer &bp, unsigned long long seq, double sgn, int lo,
+                                             int hi, int jlo, int jhi, T1 t1, T2 t2, P0 prev0, Put put) {
+    const int ld = bp.ld, half = (int)(seq & 1ull);
+    const size_t boff = (size_t)half * (2 * (size_t)ld + 2);
+    for (int k = max(lo, bp.E0) + (int)threadIdx.x; k <= min(hi, bp.E1); k += BC_THREADS) {
+        const double a = t1(k), b = t2(k);
+        for (int r = 0; r < bp.world; ++r) {
+            double *g = reinterpret_cast<double *>(bp.g[r] + 1) + boff;
+            g[k] = a; g[ld + k] = b;
+        }
+    }
+    if (threadIdx.x == 0 && lo - 1 >= bp.E0 && lo - 1 <= bp.E1) {
+        const double p0 = prev0();
+        for (int r = 0; r < bp.world; ++r) (reinterpret_cast<double *>(bp.g[r] + 1) + boff)[2 * ld] = p0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int r = 0; r < bp.world; ++r) {
+            volatile unsigned long long *fl = &bp.g[r]->flag[bp.rank];
+            *fl = seq;
+        }
+    }
+    if ((int)threadIdx.x < bp.world) {
+        const long long t0 = clock64();
+        while (bc_ld_acquire_sys(&bp.g[bp.rank]->flag[threadIdx.x]) < seq)
+            if (clock64() - t0 > 20000000000ll) { bp.g[bp.rank]->timeout = 1; break; }   // ~10 s: a peer is gone
+    }
+    __syncthreads();
+    const double *g = reinterpret_cast<const double *>(bp.g[bp.rank] + 1) + boff;
+    bc_scan(s1, s2, g[2 * ld], sgn, lo, hi,
+            [&](int k) { return __ldcg(g + k); }, [&](int k) { return __ldcg(g + ld + k); },
+            [&](int k, double x) { if (k >= jlo && k <= jhi) put(k, x); });
+}
+
 template <bool kOutflowOnly>
 __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__restrict__ R, int pitch,
-                                                            int jlo, int jhi, double *u, double *v, const int *done) {
+                                                            int jlo, int jhi, double *u, double *v, const int *done, W2BcPeer bp) {
     if (done != nullptr && *done) return;   // VelOutflowBCs of a speculatively enqueued QL iteration
+    unsigned long long scan = bp.seq0;      // slab runs: one number per OUTLT2 west / east face, in visiting order
     const double dZero = 0.0, dTwo = 2.0, dThree = 3.0, dFour = 4.0, dFive = 5.0, dEight = 8.0;
     __shared__ double sc1[BC_CHUNK], sc2[BC_CHUNK + 1];   // bc_scan staging
     const int nreg = R->nreg;
@@ -87,10 +138,11 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
                 }
                 __syncthreads();
                 // :612-613  v(iW,j) = -v(iW,j-1) + 5*(...) + 8*(...)
-                bc_scan(sc1, sc2, V(iW, jS), -1.0, jS + 1, jN,
-                        [&](int j) { return dFive * (V(iW + 1, j) - V(iW + 1, j - 1)); },
-                        [&](int j) { return dEight * (U(iW + 1, j) - U(iW, j)); },
-                        [&](int j, double x) { V(iW, j) = x; });
+                auto t1 = [&](int j) { return dFive * (V(iW + 1, j) - V(iW + 1, j - 1)); };
+                auto t2 = [&](int j) { return dEight * (U(iW + 1, j) - U(iW, j)); };
+                auto put = [&](int j, double x) { V(iW, j) = x; };
+                if (bp.world > 1) bc_scan_slab(sc1, sc2, bp, scan++, -1.0, jS + 1, jN, jlo, jhi, t1, t2, [&]() { return V(iW, jS); }, put);
+                else bc_scan(sc1, sc2, V(iW, jS), -1.0, jS + 1, jN, t1, t2, put);
             }
             __syncthreads();
         }
@@ -118,10 +170,11 @@ __global__ void __launch_bounds__(BC_THREADS) vel_bc_kernel(const W2Regions *__r
                 PFORJ(j, jS + 1, jN) U(iE, j) = U(iE - 1, j) - (V(iE, j) - V(iE, j - 1));
                 __syncthreads();
                 // :684-687  x - 4*(...) is x + (-(4*(...))): negation is exact
-                bc_scan(sc1, sc2, V(iE + 1, jS), 1.0, jS + 1, jN - 1,
-                        [&](int j) { return dThree * (V(iE, j - 1) - V(iE, j)); },
-                        [&](int j) { return -(dFour * (U(iE, j) - U(iE - 1, j))); },
-                        [&](int j, double x) { V(iE + 1, j) = x; });
+                auto t1 = [&](int j) { return dThree * (V(iE, j - 1) - V(iE, j)); };
+                auto t2 = [&](int j) { return -(dFour * (U(iE, j) - U(iE - 1, j))); };
+                auto put = [&](int j, double x) { V(iE + 1, j) = x; };
+                if (bp.world > 1) bc_scan_slab(sc1, sc2, bp, scan++, 1.0, jS + 1, jN - 1, jlo, jhi, t1, t2, [&]() { return V(iE + 1, jS); }, put);
+                else bc_scan(sc1, sc2, V(iE + 1, jS), 1.0, jS + 1, jN - 1, t1, t2, put);
             }
             __syncthreads();
         }
@@ -251,8 +304,31 @@ __global__ void __launch_bounds__(BC_THREADS) pres_bc_kernel(const W2Regions *__
     }
 }
 
+// slab runs: the peer plumbing of the OUTLT2 west / east recurrences (bc_scan_slab); every launch of the ghost-fill
+// kernels takes as many scan numbers as the deck has such faces, on every rank alike
+static int bc_peer(wolfd2_ctx *c, W2BcPeer *bp) {
+    memset(bp, 0, sizeof(*bp));
+    bp->rank = c->rank; bp->world = 1;
+    if (c->world == 1) return W2_OK;
+    int nscan = 0;
+    for (int q = 0; q < c->hreg.nreg; ++q)
+        nscan += (c->hreg.bd[q][W2_WEST - 1] == W2_BM_OUTLT2) + (c->hreg.bd[q][W2_EAST - 1] == W2_BM_OUTLT2);
+    if (nscan == 0) return W2_OK;
+    if (c->peer.state != 1) {
+        w2_set_error("multi-GPU runs need CUDA IPC peer mapping for OUTLT2 (mass_cons) faces on west / east borders");
+        return W2_ERR_UNSUPPORTED;
+    }
+    bp->world = c->world; bp->ld = c->ny + 2; bp->E0 = c->E0; bp->E1 = c->E1;
+    bp->seq0 = c->peer.bc_seq + 1;
+    c->peer.bc_seq += nscan;
+    for (int r = 0; r < c->world; ++r) bp->g[r] = c->peer.bcg[r];
+    return W2_OK;
+}
+
 int w2_vel_bc(wolfd2_ctx *c, double *u, double *v) {
-    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, nullptr);
+    W2BcPeer bp;
+    W2_TRY(bc_peer(c, &bp));
+    vel_bc_kernel<false><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, nullptr, bp);
     c->launches[3]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;
@@ -264,7 +340,9 @@ int w2_outflow_bc(wolfd2_ctx *c, double *u, double *v, const int *done) {
         for (int k = 0; k < 4; ++k)
             if (c->hreg.bd[q][k] == W2_BM_OUTLT1 || c->hreg.bd[q][k] == W2_BM_OUTLT2) any = true;
     if (!any) return W2_OK;
-    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, done);
+    W2BcPeer bp;
+    W2_TRY(bc_peer(c, &bp));
+    vel_bc_kernel<true><<<1, BC_THREADS, 0, c->stream>>>(c->dreg, c->pitch, c->A0, c->A1, u, v, done, bp);
     c->launches[1]++;
     W2_CUDA(cudaGetLastError());
     return W2_OK;

@@ -345,14 +345,19 @@ extern "C" int wolfd2_b200_create_slab(wolfd2_ctx **out, const wolfd2_params *pa
         W2Regions r;
         rc = w2_fill_regions(&r, par->nx, par->ny, reg->nReg, reg->nRegBrd, reg->nRegType, reg->nMomBdTp,
                              reg->dBCVal, reg->dPRporos, reg->dPRporc1, reg->dPRporc2);
-        if (rc == W2_OK && world > 1)   // the OUTLT2 ghost fills are recurrences along the whole face (bound_cond.f:611-614)
-            for (int q = 0; q < r.nreg && rc == W2_OK; ++q)
-                for (int k = 0; k < 4; ++k)
-                    if (r.bd[q][k] == W2_BM_OUTLT2) {
-                        w2_set_error("multi-GPU runs do not support OUTLT2 faces (region %d face %d)", q + 1, k + 1);
-                        rc = W2_ERR_UNSUPPORTED;
-                        break;
-                    }
+        if (rc == W2_OK && world > 1) {   // OUTLT2 west / east faces: recurrences along the face, across the slabs (w2_bc.cu)
+            bool o2 = false;
+            for (int q = 0; q < r.nreg; ++q) o2 |= r.bd[q][W2_WEST - 1] == W2_BM_OUTLT2 || r.bd[q][W2_EAST - 1] == W2_BM_OUTLT2;
+            if (o2) {
+                for (int k = 0; k < 2 && rc == W2_OK; ++k)
+                    if (!c->sorf_buf[k]) rc = w2_alloc_field(c, &c->sorf_buf[k]);   // the peer set-up exports them
+                if (rc == W2_OK) rc = w2_peer_setup(c);
+                if (rc == W2_OK && c->peer.state != 1) {
+                    w2_set_error("multi-GPU runs need CUDA IPC peer mapping for OUTLT2 (mass_cons) faces on west / east borders");
+                    rc = W2_ERR_UNSUPPORTED;
+                }
+            }
+        }
         if (rc == W2_OK) rc = w2_ctx_set_regions(c, &r);
     }
     if (rc == W2_OK) {

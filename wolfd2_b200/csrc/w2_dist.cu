@@ -147,7 +147,7 @@ int w2_peer_setup(wolfd2_ctx *c) {
     const char *e = getenv("W2_SOR_P2P");
     // every rank must take the same branch: the decision depends only on the environment and the world size
     if (c->world == 1 || c->world > W2_MAXRANKS || (e && atoi(e) == 0)) return W2_OK;
-    struct Handles { cudaIpcMemHandle_t a, b, m; int ok; int pad[15]; };
+    struct Handles { cudaIpcMemHandle_t a, b, m, g; int ok; int pad[15]; };
     static_assert(sizeof(Handles) % 8 == 0, "handle record must be a multiple of 8 bytes");
     Handles mine;
     memset(&mine, 0, sizeof(mine));
@@ -156,6 +156,10 @@ int w2_peer_setup(wolfd2_ctx *c) {
     ok = ok && cudaIpcGetMemHandle(&mine.a, c->sorf_buf[0] + c->row_off) == cudaSuccess;
     ok = ok && cudaIpcGetMemHandle(&mine.b, c->sorf_buf[1] + c->row_off) == cudaSuccess;
     ok = ok && cudaIpcGetMemHandle(&mine.m, mail) == cudaSuccess;
+    W2BcGather *bcg = nullptr;
+    const size_t bcg_bytes = sizeof(W2BcGather) + (size_t)2 * (2 * (size_t)(c->ny + 2) + 2) * sizeof(double);
+    ok = ok && cudaMalloc((void **)&bcg, bcg_bytes) == cudaSuccess && cudaMemset(bcg, 0, bcg_bytes) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.g, bcg) == cudaSuccess;
     mine.ok = ok ? 1 : 0;
     cudaGetLastError();
     Handles *d_all = nullptr, *h_all = (Handles *)malloc(sizeof(Handles) * c->world);
@@ -172,11 +176,15 @@ int w2_peer_setup(wolfd2_ctx *c) {
     P.nopened = 0;
     if (all_ok) {
         for (int r = 0; r < c->world && opened_ok; ++r) {
-            if (r == c->rank) { P.mail[r] = mail; continue; }
+            if (r == c->rank) { P.mail[r] = mail; P.bcg[r] = bcg; continue; }
             void *m = nullptr;
             if (cudaIpcOpenMemHandle(&m, h_all[r].m, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
             P.opened[P.nopened++] = m;
             P.mail[r] = (W2Mail *)m;
+            void *gq = nullptr;
+            if (cudaIpcOpenMemHandle(&gq, h_all[r].g, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
+            P.opened[P.nopened++] = gq;
+            P.bcg[r] = (W2BcGather *)gq;
             if (r == c->rank - 1 || r == c->rank + 1) {
                 void *a = nullptr, *b = nullptr;
                 if (cudaIpcOpenMemHandle(&a, h_all[r].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; break; }
@@ -206,6 +214,7 @@ int w2_peer_setup(wolfd2_ctx *c) {
         for (int k = 0; k < P.nopened; ++k) cudaIpcCloseMemHandle(P.opened[k]);
         P.nopened = 0;
         cudaFree(mail);
+        cudaFree(bcg);
         return W2_OK;
     }
     P.state = 1;
@@ -215,7 +224,7 @@ int w2_peer_setup(wolfd2_ctx *c) {
 void w2_peer_release(wolfd2_ctx *c) {
     W2Peer &P = c->peer;
     for (int k = 0; k < P.nopened; ++k) cudaIpcCloseMemHandle(P.opened[k]);
-    if (P.state == 1) cudaFree(P.mail[c->rank]);
+    if (P.state == 1) { cudaFree(P.mail[c->rank]); cudaFree(P.bcg[c->rank]); }
     memset(&P, 0, sizeof(P));
 }
 

@@ -649,6 +649,8 @@ int w2_sor_fused_result(wolfd2_ctx *c, int *nSorConv, int *converged, int *iters
         int to = 0;
         W2_CUDA(cudaMemcpy(&to, &c->peer.mail[c->rank]->timeout, sizeof(int), cudaMemcpyDeviceToHost));
         if (to) { w2_set_error("fused SOR: timed out waiting for a peer GPU (rank %d of %d)", c->rank, c->world); return W2_ERR_CUDA; }
+        W2_CUDA(cudaMemcpy(&to, &c->peer.bcg[c->rank]->timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (to) { w2_set_error("OUTLT2 ghost fill: timed out waiting for a peer GPU (rank %d of %d)", c->rank, c->world); return W2_ERR_CUDA; }
     }
     if (converged) *converged = h.nconv > 0;
     if (nSorConv) *nSorConv = h.nconv > 0 ? h.nconv : c->par.msorit;
