@@ -30,21 +30,28 @@ def test_fused_sor_pipeline_equals_plain_sweeps_bitwise(api, n):
     import bench
     d = bench.make_deck("cavity", n, True, 2, 24)
     res = {}
-    for T in (0, 1, 2):
+    # (T, resident): the plain half-sweep kernels, the streamed fused pipeline with one and two iterations per pass, and
+    # -- where the grid fits (1024^2) -- the shared-memory-resident cooperative kernel that is the default there
+    variants = [(0, 0), (1, 0), (2, 0)] + ([(2, 1)] if n <= 1024 else [])
+    for T, resident in variants:
         api.set_option("sor_fused_T", T)
+        api.set_option("sor_resident", resident)
         try:
             with api.Context(d) as ctx:
                 for w, f in zip((api.F_U, api.F_V, api.F_P), _vortex(d)):
                     ctx.upload(w, f)
                 ctx.coldstart()
                 lg = ctx.step(2)
-                res[T] = (lg, ctx.download(api.F_U), ctx.download(api.F_V), ctx.download(api.F_P))
+                res[(T, resident)] = (lg, ctx.download(api.F_U), ctx.download(api.F_V), ctx.download(api.F_P))
         finally:
             api.set_option("sor_fused_T", -1)
-    for T in (1, 2):
-        assert res[T][0][-1]["dif"] == res[0][0][-1]["dif"]
-        for a, b in zip(res[T][1:], res[0][1:]):
-            assert np.array_equal(a, b)
+            api.set_option("sor_resident", 1)
+    for key in variants[1:]:
+        assert res[key][0][-1]["dif"] == res[(0, 0)][0][-1]["dif"], key
+        assert [l["nSorConv"] for l in res[key][0]] == [l["nSorConv"] for l in res[(0, 0)][0]], key
+        for a, b in zip(res[key][1:], res[(0, 0)][1:]):
+            assert np.array_equal(a, b), key
+    res[2] = res[(2, 0)]
     u = res[2][1]
     assert np.isfinite(u).all() and np.abs(u).max() <= 2.0
 

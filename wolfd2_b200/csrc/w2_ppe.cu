@@ -257,6 +257,8 @@ void rhs_cross_launch(wolfd2_ctx *c, double *p) {
 int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv, int *converged, double **p_final,
                  int *iters_done);
 int w2_sor_fused_result(wolfd2_ctx *c, int *nSorConv, int *converged, int *iters_done);
+bool w2_sor_resident_ok(const wolfd2_ctx *c);
+int w2_sor_resident(wolfd2_ctx *c, double *p);
 
 // Outcome and device time of the last fused solve (the stream has been synchronised since it was enqueued).
 int w2_sor_collect(wolfd2_ctx *c, int *nSorConv, int *converged) {
@@ -314,6 +316,9 @@ static int ppe_impl(wolfd2_ctx *c, const double *u, const double *v, double *p, 
     static_assert(sizeof(SorCtl) <= 64 * sizeof(int), "ctl block too large");
 
     int T = (rb_point && cart && nx >= 254 && ny >= 8) ? fused_T() : 0;
+    // small grids (1024^2 and below): the whole solve in one cooperative launch, p resident in shared memory
+    const bool resident = rb_point && cart && fused_T() > 0 && w2_sor_resident_ok(c);
+    if (resident) T = 0;
     if (c->world > 1) {
         if (!(rb_point && cart && nx >= 254)) {
             w2_set_error("multi-GPU runs support ppe_solver 5/6 on a Cartesian grid with nx >= 254 only");
@@ -328,6 +333,24 @@ static int ppe_impl(wolfd2_ctx *c, const double *u, const double *v, double *p, 
     div_rhs_kernel<<<g2, 256, 0, c->stream>>>(nx, bj0, bj1, pitch, par.dk, c->met.xeu, c->met.yeu, c->met.xzv, c->met.yzv, u, v,
                                               c->pmask, has_mask, T > 0, b, cart ? nullptr : c->div);
     c->launches[2]++;
+    if (resident) {
+        if (c->sor_pending) {
+            W2_CUDA(cudaStreamSynchronize(c->stream));
+            c->host_syncs++;
+            W2_TRY(w2_sor_collect(c, &c->sor_saved[0], &c->sor_saved[1]));
+            c->sor_saved[2] = 1;
+        }
+        cudaEventRecord(c->ev[4], c->stream);
+        W2_TRY(w2_sor_resident(c, p));
+        cudaEventRecord(c->ev[5], c->stream);
+        c->sor_pending = 1;
+        if (!deferred) {
+            W2_CUDA(cudaStreamSynchronize(c->stream));
+            c->host_syncs++;
+            W2_TRY(w2_sor_collect(c, nSorConv, converged));
+        }
+        return W2_OK;
+    }
     if (T > 0) {
         // fused red/black pipeline (w2_sor_fused.cu); c->div is free on Cartesian grids and serves as
         // the second pressure buffer
