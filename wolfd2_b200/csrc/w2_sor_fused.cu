@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
             if (!all_ok) {   // operands outside the fast path's range (zero, tiny or huge numerators, ...)
 #pragma unroll
                 for (int u = 0; u < SF_CPT; ++u)
-                    if (!okv[u] && valid[u]) qdv[u] = w2_div_slow(sumv[u], a3v[u]);
+                    if (!okv[u] && valid[u]) qdv[u] = w2_div_detour(sumv[u], a3v[u]);
             }
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {

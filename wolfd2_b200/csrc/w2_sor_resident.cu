@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(SR_T, 1) sor_rb_resident_kernel(SorRArgs a) {
                 if (!all_ok) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (!okv[k] && ((own >> (2 * (r0 + k) + c)) & 1u)) qdv[k] = w2_div_slow(sumv[k], a3v[k]);
+                        if (!okv[k] && ((own >> (2 * (r0 + k) + c)) & 1u)) qdv[k] = w2_div_detour(sumv[k], a3v[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -164,7 +164,7 @@ static bool resident_plan(const wolfd2_ctx *c, int *rows_per_cta, int *nblocks, 
     const int rm = rpc <= 4 ? 4 : 8;
     const int hw = (nx + 3) >> 1, W = 2 * hw;
     const size_t bytes = (size_t)((rm + 2) + rm + (rm + 1)) * W * sizeof(double);
-    if (bytes > 227 * 1024) return false;
+    if (bytes > 227 * 1024 - 1024) return false;
     *rows_per_cta = rpc; *nblocks = (rows + rpc - 1) / rpc; *rmax = rm; *smem = bytes;
     return true;
 }
@@ -192,7 +192,8 @@ int w2_sor_resident(wolfd2_ctx *c, double *p) {
     const void *fn = rm == 4 ? (const void *)sor_rb_resident_kernel<4> : (const void *)sor_rb_resident_kernel<8>;
     static bool attr[W2_MAXDEV][2] = {};
     if (!attr[c->device % W2_MAXDEV][rm == 8]) {
-        W2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // (the kernel also holds 256 bytes of static shared memory: the opt-in limit covers both)
+        W2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr[c->device % W2_MAXDEV][rm == 8] = true;
     }
     W2_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(SR_T), args, smem, c->stream));
