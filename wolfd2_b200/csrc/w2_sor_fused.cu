@@ -120,20 +120,6 @@ __device__ __forceinline__ void mbar_wait_a(unsigned bar_addr, unsigned parity) 
         "DONE:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
 }
 
-// step barrier of the streaming loop: every thread arrives once per trip and waits for the phase to complete later
-__device__ __forceinline__ void step_arrive(unsigned bar_addr) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
-}
-__device__ __forceinline__ void step_wait(unsigned bar_addr, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "SW_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra SW_DONE;\n\t"
-        "bra SW_LOOP;\n\t"
-        "SW_DONE:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
-}
-
 __global__ void sorf_ctl_reset(SorFCtl *c) {
     c->done = 0; c->m = 0; c->nconv = 0; c->ticket = 0; c->cur = 0; c->redo = 0;
     for (int k = 0; k < 8; ++k) c->slot[k] = 0ull;
@@ -167,7 +153,7 @@ __device__ __forceinline__ void sorf_close_pass(SorFCtl *ctl, int Tp, int cur, d
 
 template <int T> struct SorFCfg {
     static constexpr int R = (T == 1) ? 8 : 13;      // ring depth in rows (T=2: 108 KB -> two CTAs per SM)
-    static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + (R + 1) * sizeof(unsigned long long);   // R row barriers + the step barrier
+    static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
 };
 
 // The same kernel serves one GPU (rows 2..ny, the last CTA closes the pass) and one rank's row slab (rows
@@ -214,7 +200,6 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
 
     if (tid == 0) {
         for (int k = 0; k < R; ++k) mbar_init(&bars[k], 1);
-        mbar_init(&bars[R], blockDim.x);   // step barrier of the streaming loop
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the pad cells once (read by edge threads, never used by owned cells)
@@ -286,16 +271,6 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
     double *gst = pdst + (size_t)pitch * q + (i0 >> 1) + kk0;   // store address of pair kk0's even cell in row q
     const bool last_stage = stage == NS;
     const int r_end = jB + 4 * T - 1;
-    // Operands of the row this stage relaxes NEXT that do not depend on the other stages: right-hand side, the four
-    // coefficients, the diagonal and its reciprocal (the longest dependent chain of an update).  They are formed at the
-    // end of a trip, between the arrival at the step barrier and the wait for it, i.e. while the slower warps of the
-    // CTA are still relaxing: ncu r02 showed 31 % of all stall samples on the block barrier.  The barrier is an
-    // mbarrier because the same threads arrive and, later, wait.  (The first trip relaxes nothing: q < qlo.)
-    double c_bb[SF_CPT], c_a1[SF_CPT], c_a2[SF_CPT], c_a4[SF_CPT], c_a5[SF_CPT], c_a3[SF_CPT], c_y[SF_CPT];
-#pragma unroll
-    for (int u = 0; u < SF_CPT; ++u) { c_bb[u] = 0.0; c_a1[u] = 0.0; c_a2[u] = 0.0; c_a4[u] = 0.0; c_a5[u] = 0.0; c_a3[u] = 1.0; c_y[u] = 1.0; }
-    const unsigned aStep = aBar + 8 * R;       // the step barrier sits behind the R row barriers
-    unsigned s_par = 0;
 #pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
         if (r <= jL1) {
@@ -306,9 +281,9 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         if (any_row && (unsigned)(q - qlo) <= qspan) {
             const bool row_owned = (unsigned)(q - jA) <= jspan;
             // straight-line code for all SF_CPT cells of this thread: every operand is loaded and every quotient formed
-            // before anything is branched on, so the independent updates overlap; cells that are not unknowns compute
-            // on whatever the ring holds and are simply not stored
-            double pcv[SF_CPT], sumv[SF_CPT], qdv[SF_CPT];
+            // (w2_div_fast) before anything is branched on, so the independent updates overlap; cells that are not
+            // unknowns compute on whatever the ring holds and are simply not stored
+            double pcv[SF_CPT], sumv[SF_CPT], a3v[SF_CPT], qdv[SF_CPT], bbv[SF_CPT];
             bool okv[SF_CPT], valid[SF_CPT];
             bool all_ok = true;
 #pragma unroll
@@ -316,29 +291,31 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
                 valid[u] = (vmask >> (2 * u + par)) & 1u;
                 const unsigned iq = off_q + ha8 + u * PAIRB, is = off_s + ha8 + u * PAIRB, in = off_n + ha8 + u * PAIRB,
                                iw = off_q + hw8 + u * PAIRB;
+                bbv[u] = lds_f64(aB + iq);
                 pcv[u] = lds_f64(aP + iq);
+                const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
                 const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
-                sumv[u] = c_bb[u] - c_a1[u] * pS - c_a2[u] * pW - c_a4[u] * pE - c_a5[u] * pN;
-                qdv[u] = w2_div_finish(sumv[u], c_a3[u], c_y[u], okv[u]);
+                a3v[u] = -a4 - a2 - a5 - a1;
+                sumv[u] = bbv[u] - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
+                qdv[u] = w2_div_fast(sumv[u], a3v[u], okv[u]);
                 all_ok = all_ok && (okv[u] || !valid[u]);
             }
             if (!all_ok) {   // operands outside the fast path's range (zero, tiny or huge numerators, ...)
 #pragma unroll
                 for (int u = 0; u < SF_CPT; ++u)
-                    if (!okv[u] && valid[u]) qdv[u] = w2_div_detour(sumv[u], c_a3[u]);
+                    if (!okv[u] && valid[u]) qdv[u] = w2_div_detour(sumv[u], a3v[u]);
             }
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {
                 const unsigned iq = off_q + ha8 + u * PAIRB;
                 double sum = qdv[u] - pcv[u];
-                if (c_bb[u] != c_bb[u]) sum = 0.0 - pcv[u];   // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
+                if (bbv[u] != bbv[u]) sum = 0.0 - pcv[u];   // identity row (blockage): a = (0,0,1,0,0), b = 0  (:123-137)
                 if (valid[u]) sts_f64(aP + iq, pcv[u] + sorrel * sum);
                 if (valid[u] && row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
             }
         }
-        step_arrive(aStep);     // this thread's part of the time step is in shared memory
-        // the row that has just passed the last stage is final: back to HBM (each thread reads the pair it relaxed itself
-        // and its other-colour partner, which an earlier stage wrote in an earlier step)
+        __syncthreads();
+        // the row that has just passed the last stage is final: back to HBM
         if (last_stage && (unsigned)(q - jA) <= jspan) {
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {
@@ -346,19 +323,6 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
                 if ((omask >> (2 * u + 1)) & 1u) gst[hp + u * SF_TPS] = lds_f64(aP + off_q + HSTRB + base8 + u * PAIRB);
             }
         }
-        {   // next trip: row q+1, whose own ring slot is off_n and whose south row is off_q; the column parity flips
-            const unsigned nha8 = HA_SUM - ha8, nhw8 = HW_SUM - hw8;
-#pragma unroll
-            for (int u = 0; u < SF_CPT; ++u) {
-                const unsigned iq = off_n + nha8 + u * PAIRB, is = off_q + nha8 + u * PAIRB, iw = off_n + nhw8 + u * PAIRB;
-                c_bb[u] = lds_f64(aB + iq);
-                c_a1[u] = lds_f64(aV + is); c_a2[u] = lds_f64(aU + iw); c_a4[u] = lds_f64(aU + iq); c_a5[u] = lds_f64(aV + iq);
-                c_a3[u] = -c_a4[u] - c_a2[u] - c_a5[u] - c_a1[u];
-                c_y[u] = w2_rcp_seq(c_a3[u]);
-            }
-        }
-        step_wait(aStep, s_par);
-        s_par ^= 1u;
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
         if (tid < 8 && ld_row <= jL1) issue_row();
         off_s = off_q; off_q = off_n;
@@ -369,7 +333,6 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused
         ++q;
         gst += pitch;
     }
-    __syncthreads();
 
     // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
 #pragma unroll
