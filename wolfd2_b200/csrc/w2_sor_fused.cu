@@ -33,6 +33,10 @@
 // per-row costs (barrier, mbarrier wait, ring bookkeeping) are paid once per two updates: 0.2175 -> 0.2101 ms per T=2
 // pass at 4096^2.  (1 with the same straight-line update: 0.2654 ms -- every lane then pays the full quotient that the
 // old zero-numerator branch skipped; 2 with the branchy update was measured slower than 1 in round 1.)
+// Also measured and rejected (bit-exact, slower): a split-phase step barrier -- mbarrier arrive after the stores, the
+// next row's coefficients, diagonal and reciprocal formed before the wait -- 0.190 -> 0.206 ms per pass: 28 more live
+// registers and the arrive / try_wait pair cost more than the barrier skew they hide (ncu r02: 31 % of the stall
+// samples sit on the block barrier).
 #ifndef SF_CPT
 #define SF_CPT 2
 #endif
