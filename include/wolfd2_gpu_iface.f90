@@ -210,5 +210,70 @@ module wolfd2_gpu
       type(w2_metrics), intent(in) :: met
       integer(c_int32_t), value :: rank, world
     end function
+    ! metric rows streamed in window by window (create with NULL metric pointers): which = 0-based position in w2_metrics
+    integer(c_int) function wolfd2_b200_upload_metric_rows(ctx, which, jfirst, nrows, host) &
+        bind(C, name='wolfd2_b200_upload_metric_rows')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: which, jfirst, nrows
+      real(c_double), intent(in) :: host(*)
+    end function
+    ! a slab run gathered into a one-GPU context on rank 0 and compared bit for bit (verification)
+    integer(c_int) function wolfd2_b200_gather_global(slab, global, what) bind(C, name='wolfd2_b200_gather_global')
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: slab, global
+      integer(c_int32_t), value :: what
+    end function
+    integer(c_int) function wolfd2_b200_compare_global(slab, global, which, ndiff, maxabs) &
+        bind(C, name='wolfd2_b200_compare_global')
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: slab, global
+      integer(c_int32_t), value :: which
+      integer(c_int64_t), intent(out) :: ndiff
+      real(c_double), intent(out) :: maxabs
+    end function
+
+    ! time-series monitor points (SaveTimeSrs, file_manip.f:686-854; main.f:984-995): sampled inside wolfd2_b200_step
+    integer(c_int) function wolfd2_b200_set_probes(ctx, npoints, iTS, jTS, freq) bind(C, name='wolfd2_b200_set_probes')
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: npoints, freq
+      integer(c_int32_t), intent(in) :: iTS(*), jTS(*)
+    end function
+    integer(c_int) function wolfd2_b200_get_probe_records(ctx, maxrec, rec, steps, nrec) &
+        bind(C, name='wolfd2_b200_get_probe_records')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: maxrec
+      real(c_double), intent(out) :: rec(8, *)          ! rec(var, point + npoints*(record-1))
+      integer(c_int32_t), intent(out) :: steps(*), nrec
+    end function
+
+    ! time averaging (-D_TIMEAVG_): op 0 begin (main.f:517-541), 1 / 2 accumulate pass 1 / 2 in every step (:1107-1208),
+    ! 3 stop, 4 release; finish = :1239-1297; get: k = 0..18 (ubar vbar tbar pbar upb vpb tpb upupb vpvpb upvpb uptpb
+    ! vptpb upxsb upysb vpxsb vpysb trbke dssrt dtdyb)
+    integer(c_int) function wolfd2_b200_timeavg(ctx, op) bind(C, name='wolfd2_b200_timeavg')
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: op
+    end function
+    integer(c_int) function wolfd2_b200_timeavg_finish(ctx, npass, nts, uref, dlref) bind(C, name='wolfd2_b200_timeavg_finish')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: npass, nts
+      real(c_double), value :: uref, dlref
+    end function
+    integer(c_int) function wolfd2_b200_timeavg_get(ctx, k, host) bind(C, name='wolfd2_b200_timeavg_get')
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: k
+      real(c_double), intent(out) :: host(*)
+    end function
+    ! host waits issued by the last wolfd2_b200_step call (loop control lives on the device)
+    integer(c_int) function wolfd2_b200_last_host_syncs(ctx, syncs) bind(C, name='wolfd2_b200_last_host_syncs')
+      import :: c_int, c_int64_t, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), intent(out) :: syncs
+    end function
   end interface
 end module wolfd2_gpu
