@@ -286,6 +286,8 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
 // host array holds this rank's rows only: host row 0 is global row A0 (wolfd2_b200_slab_layout).
 int w2_upload2d(wolfd2_ctx *c, double *dev, const double *host, cudaStream_t stream) {
     if (dev == c->met.rau || dev == c->met.rgv) c->sorf_met_valid = 0;   // the fused SOR keeps colour-split copies
+    for (int k = 0; k < 30; ++k)
+        if (dev == (&c->met.rau)[k] && c->cart_state != -2) c->cart_state = 0;   // metrics changed: re-verify the Cartesian classes
     W2_CUDA(cudaMemcpy2DAsync(dev + c->row_off, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
                               (size_t)(c->nx + 2) * 8, (size_t)c->rows, cudaMemcpyHostToDevice,
                               stream ? stream : c->stream));
@@ -394,6 +396,7 @@ extern "C" int wolfd2_b200_upload_metric_rows(wolfd2_ctx *c, int32_t which, int3
     W2_CUDA(cudaSetDevice(c->device));
     double *dev = (&c->met.rau)[which];
     if (dev == c->met.rau || dev == c->met.rgv) c->sorf_met_valid = 0;
+    if (c->cart_state != -2) c->cart_state = 0;
     W2_CUDA(cudaMemcpy2DAsync(dev + (size_t)c->pitch * (size_t)jfirst, (size_t)c->pitch * 8, host, (size_t)(c->mnx + 1) * 8,
                               (size_t)(c->nx + 2) * 8, (size_t)nrows, cudaMemcpyHostToDevice, c->stream));
     W2_CUDA(cudaStreamSynchronize(c->stream));   // the caller reuses the host block
@@ -426,9 +429,11 @@ extern "C" void wolfd2_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern int g_sor_T;
 extern int g_mom_np_cache;
+extern int g_mom_cart;
 extern int g_sor_resident;
 extern "C" int wolfd2_b200_set_option(const char *name, int32_t value) {
     if (name && !strcmp(name, "mom_np_cache")) { g_mom_np_cache = value != 0; return W2_OK; }
+    if (name && !strcmp(name, "mom_cart")) { g_mom_cart = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_resident")) { g_sor_resident = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_fused_T")) {
         if (value < -1 || value > 2) { w2_set_error("sor_fused_T must be -1 (default), 0, 1 or 2"); return W2_ERR_BAD_ARG; }

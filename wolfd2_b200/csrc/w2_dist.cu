@@ -267,7 +267,7 @@ extern "C" int wolfd2_b200_gather_global(wolfd2_ctx *s, wolfd2_ctx *g, int32_t w
     if (what & 1) {
         double **sp = &s->met.rau, **gp = g ? &g->met.rau : nullptr;
         for (int k = 0; k < 30; ++k) W2_TRY(gather_array(s, sp[k], gp ? gp[k] : nullptr));
-        if (g) g->sorf_met_valid = 0;
+        if (g) { g->sorf_met_valid = 0; if (g->cart_state != -2) g->cart_state = 0; }
     }
     if (what & 2)
         for (int k = W2_F_U; k <= W2_F_P; ++k) W2_TRY(gather_array(s, s->fld[k], g ? g->fld[k] : nullptr));

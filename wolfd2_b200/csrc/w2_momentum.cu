@@ -18,6 +18,18 @@ __device__ __forceinline__ double a_sum4_sic(double a, double b, double c, doubl
 
 enum { NP_COMPUTE = 0, NP_SAME = 1, NP_CACHED = 2 };   // see mom_row (w2_mom_rows.inc)
 
+// The metric arrays the momentum (and thermal) rows read, with the class each has on a Cartesian grid (see MET in
+// w2_mom_rows.inc): 0 = two-dimensional, 1 = function of i only, 2 = function of j only, 3 = constant.
+#define W2_MET_LIST(X)                                                                                               \
+    X(rau, 0) X(rbu, 3) X(rbv, 3) X(rgv, 0) X(ran, 0) X(rbn, 3) X(rgn, 0) X(rac, 0) X(rbc, 3) X(rgc, 0)              \
+    X(dju, 0) X(djv, 0) X(djc, 0) X(xen, 3) X(yen, 2) X(xzn, 1) X(yzn, 3) X(xec, 3) X(yec, 2) X(xzc, 1) X(yzc, 3)    \
+    X(xeu, 3) X(yeu, 2) X(xzv, 1) X(yzv, 3) X(xzu, 1) X(yzu, 3) X(xev, 3) X(yev, 2)
+struct MomConst {   // values of the constant-class arrays (any interior entry), used by the Cartesian variant only
+#define W2_MC_FIELD(name, CLS) double name;
+    W2_MET_LIST(W2_MC_FIELD)
+#undef W2_MC_FIELD
+};
+
 struct MomArgs {
     int nx, ny, pitch;
     double dk, re, fr;
@@ -26,6 +38,8 @@ struct MomArgs {
     const double *rbn, *rgn, *rac, *rbc, *dju, *xec, *yec, *xzn, *yzn, *xeu, *yeu, *xzu, *yzu;
     // y-momentum metrics
     const double *ran, *rgc, *djv, *xen, *yen, *xzc, *yzc, *xev, *yev, *xzv, *yzv;
+    int iref, jref;     // Cartesian variant: the column / row the j-only / i-only arrays are read from (any interior one held)
+    MomConst cc;        // Cartesian variant: the constant-class arrays
     const unsigned char *xmask, *ymask;
     const double *x1;  // first-step solution, field layout
     double *np_c, *np_d;   // cache of cnvn, difn of the component being solved (null: not kept)
@@ -40,10 +54,13 @@ struct MomArgs {
     const int *done;   // device flag of the QL loop (null outside it): set = converged, later launches do nothing
 };
 
-namespace mom_np { constexpr bool kPorous = false;
+namespace mom_np { constexpr bool kPorous = false; constexpr bool kCart = false;
 #include "w2_mom_rows.inc"
 }
-namespace mom_po { constexpr bool kPorous = true;
+namespace mom_po { constexpr bool kPorous = true; constexpr bool kCart = false;
+#include "w2_mom_rows.inc"
+}
+namespace mom_ca { constexpr bool kPorous = false; constexpr bool kCart = true;   // Cartesian grid: see MET
 #include "w2_mom_rows.inc"
 }
 
@@ -112,7 +129,8 @@ struct ChainWalk {
 #endif
 static constexpr int kMomU1 = MOM_U1, kMomU2 = MOM_U2;   // (#pragma unroll does not expand macros)
 
-template <int COMP, int STEP, bool POR, int NP>
+// VAR: 0 = general metrics, 1 = porous deck (general metrics), 2 = Cartesian grid (mom_ca: see MET in w2_mom_rows.inc)
+template <int COMP, int STEP, int VAR, int NP>
 __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, long long n, double *__restrict__ out,
                                                               double *__restrict__ Vg, double *__restrict__ Wg,
                                                               double *__restrict__ seg, int *__restrict__ ext,
@@ -148,7 +166,8 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
             ci = live ? wa.i() : ci; cj = live ? wa.j : cj;
         }
         double a1, a2, a3, b;
-        if (POR) mom_po::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
+        if (VAR == 1) mom_po::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
+        else if (VAR == 2) mom_ca::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
         else mom_np::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
         a3 = (e == n - 1) ? 0.0 : a3;
         const int p = MR_PAD(el);
@@ -157,7 +176,8 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     if (ebase == 0 && t == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
         int i2, j2; double b1, b2, b3, bb;
         chain_ij<COMP>(m, 1, i2, j2);
-        if (POR) mom_po::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
+        if (VAR == 1) mom_po::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
+        else if (VAR == 2) mom_ca::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
         else mom_np::mom_row<COMP, STEP, NP>(m, i2, j2, b1, b2, b3, bb);
         s0[0] = 0.0;
         s2[0] = s2[0] * s1[0] / b2;
@@ -375,6 +395,8 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->x1;
     m.np_c = nullptr; m.np_d = nullptr;
+    m.iref = c->cart_iref; m.jref = c->cart_jref;
+    if (c->cart_state == 1) memcpy(&m.cc, c->cart_const, sizeof(MomConst)); else memset(&m.cc, 0, sizeof(MomConst));
     m.done = c->ql_active ? (const int *)(c->d_norm + W2_QL_SLOT) : nullptr;
     m.tn = c->fld[W2_F_TN]; m.heat = c->heat_s; m.tmask = c->tmask; m.pe = c->th.pe;
     m.rau = t.rau; m.rbu = t.rbu; m.rbv = t.rbv; m.rgv = t.rgv; m.djc = t.djc;
@@ -384,16 +406,22 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xcp = pm + 4 * c->nelem; m.ycp = pm + 5 * c->nelem;
 }
 
-template <int COMP, int STEP, bool POR, int NP>
+template <int COMP, int STEP, int VAR, int NP>
 static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, const double *sig1, const double **sig_out);
 
 // one split step of component COMP (sig1 / sig_out: separator values, unused hooks)
 template <int COMP, int STEP>
 static int mom_solve(wolfd2_ctx *c, MomArgs &m, long long n, double *out, int np, const double *sig1, const double **sig_out) {
-    if (c->hreg.has_porous) return mom_solve_impl<COMP, STEP, true, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
-    if (STEP == 1 && np == NP_SAME) return mom_solve_impl<COMP, STEP, false, (STEP == 1 ? NP_SAME : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
-    if (STEP == 1 && np == NP_CACHED) return mom_solve_impl<COMP, STEP, false, (STEP == 1 ? NP_CACHED : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
-    return mom_solve_impl<COMP, STEP, false, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
+    if (c->hreg.has_porous) return mom_solve_impl<COMP, STEP, 1, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
+    constexpr int S1 = STEP == 1;
+    if (c->cart_state == 1) {   // Cartesian grid, verified on the uploaded arrays (w2_mom_cart_prepare)
+        if (S1 && np == NP_SAME) return mom_solve_impl<COMP, STEP, 2, (S1 ? NP_SAME : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+        if (S1 && np == NP_CACHED) return mom_solve_impl<COMP, STEP, 2, (S1 ? NP_CACHED : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+        return mom_solve_impl<COMP, STEP, 2, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
+    }
+    if (S1 && np == NP_SAME) return mom_solve_impl<COMP, STEP, 0, (S1 ? NP_SAME : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+    if (S1 && np == NP_CACHED) return mom_solve_impl<COMP, STEP, 0, (S1 ? NP_CACHED : NP_COMPUTE)>(c, m, n, out, sig1, sig_out);
+    return mom_solve_impl<COMP, STEP, 0, NP_COMPUTE>(c, m, n, out, sig1, sig_out);
 }
 
 // Chain unknowns [lo, hi) that lie in the rows this rank updates.  The level-0 segments keep their GLOBAL
@@ -440,12 +468,12 @@ static int mom_tail_exchange(wolfd2_ctx *c, double *out) {
     return w2_send_recv_pieces(c, up, nup, dn, ndn);
 }
 
-template <int COMP, int STEP, bool POR, int NP>
+template <int COMP, int STEP, int VAR, int NP>
 static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, const double *sig1, const double **sig_out) {
     static bool attr[W2_MAXDEV] = {};   // the attribute is per device: one flag per device id
     const size_t smem = (size_t)4 * MR_LEN * sizeof(double);
     if (!attr[c->device % W2_MAXDEV]) {
-        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, POR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        W2_CUDA(cudaFuncSetAttribute(mom_reduce_kernel<COMP, STEP, VAR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr[c->device % W2_MAXDEV] = true;
     }
     W2TriWork &w = c->tri;
@@ -465,7 +493,7 @@ static int mom_solve_impl(wolfd2_ctx *c, MomArgs &m, long long n, double *out, c
     }
     double *V0 = w.V0 - s_lo * TRI_S, *W0 = w.W0 - s_lo * TRI_S;
     int *ext = w.ext - 2 * s_lo;
-    mom_reduce_kernel<COMP, STEP, POR, NP><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(
+    mom_reduce_kernel<COMP, STEP, VAR, NP><<<(unsigned)(s_hi - s_lo), TRI_T, smem, c->stream>>>(
         m, n, out, V0, W0, w.lv[0].seg, ext, nseg, direct, s_lo);
     c->launches[1]++;
     if (sig_out) *sig_out = nullptr;
@@ -528,8 +556,84 @@ int w2_thermal_solve(wolfd2_ctx *c, double *dts) {
     fill_args(c, m);
     const long long n = (long long)(c->nx - 1) * (c->ny - 1);
     const double *sig1 = nullptr;
-    W2_TRY((mom_solve_impl<2, 1, false, NP_COMPUTE>(c, m, n, c->x1, nullptr, &sig1)));
-    W2_TRY((mom_solve_impl<2, 2, false, NP_COMPUTE>(c, m, n, dts, sig1, nullptr)));
+    W2_TRY((mom_solve_impl<2, 1, 0, NP_COMPUTE>(c, m, n, c->x1, nullptr, &sig1)));
+    W2_TRY((mom_solve_impl<2, 2, 0, NP_COMPUTE>(c, m, n, dts, sig1, nullptr)));
+    return W2_OK;
+}
+
+// ---- Cartesian-grid variant: verification of the metric classes (MET in w2_mom_rows.inc) -----------------------------
+struct CartCheck { const double *a[32]; int cls[32]; int n; };
+// Every array of class 1 / 2 / 3 must be, bit for bit, a function of i only / of j only / one constant on 1..nx x 1..ny
+// and +0 on the ring i = 0, nx+1, j = 0, ny+1 (the rows this rank holds).  bad[k] counts the violations of array k.
+__global__ void __launch_bounds__(256) mom_cart_check_kernel(CartCheck cc, int nx, int ny, int jlo, int jhi, int iref, int jref,
+                                                             int pitch, unsigned int *bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nx + 1) return;
+    for (int k = 0; k < cc.n; ++k) {
+        const int cls = cc.cls[k];
+        if (cls == 0) continue;
+        const double *a = cc.a[k];
+        const long long cref = __double_as_longlong(a[IDX(iref, jref)]);
+        unsigned int nb = 0;
+        for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
+            const long long v = __double_as_longlong(a[IDX(i, j)]);
+            const bool inner = i >= 1 && i <= nx && j >= 1 && j <= ny;
+            long long want;
+            if (!inner) want = 0;                                            // +0.0
+            else if (cls == 1) want = __double_as_longlong(a[IDX(i, jref)]);
+            else if (cls == 2) want = __double_as_longlong(a[IDX(iref, j)]);
+            else want = cref;
+            nb += v != want;
+        }
+        if (nb) atomicAdd(bad + k, nb);
+    }
+}
+
+int g_mom_cart = 1;   // option "mom_cart": 0 = never use the Cartesian-grid variant
+
+// Decide (once per set of uploaded metrics) whether the Cartesian variant may be used: every rank checks the rows it
+// holds, the ranks agree on the outcome.  Collective on several GPUs: called at the top of w2_nauxmomentum.
+static int mom_cart_prepare(wolfd2_ctx *c) {
+    if (c->cart_state != 0) return W2_OK;
+    c->cart_state = -1;
+    if (!g_mom_cart || c->hreg.has_porous) return W2_OK;
+    const int jlo = c->A0, jhi = c->A1;
+    const int j1 = jlo > 1 ? jlo : 1, j2 = jhi < c->ny ? jhi : c->ny;
+    if (j2 < j1) return W2_OK;
+    c->cart_iref = 1; c->cart_jref = j1;
+    CartCheck cc;
+    memset(&cc, 0, sizeof(cc));
+    const W2Metrics &t = c->met;
+#define W2_CC_ADD(name, CLS) cc.a[cc.n] = t.name; cc.cls[cc.n] = (CLS); ++cc.n;
+    W2_MET_LIST(W2_CC_ADD)
+#undef W2_CC_ADD
+    unsigned int *bad = (unsigned int *)(c->d_norm + 48);     // 32 counters in the spare norm slots
+    W2_CUDA(cudaMemsetAsync(bad, 0, 32 * sizeof(unsigned int), c->stream));
+    dim3 g((c->nx + 2 + 255) / 256, (jhi - jlo + 1) < 1024 ? (jhi - jlo + 1) : 1024);
+    mom_cart_check_kernel<<<g, 256, 0, c->stream>>>(cc, c->nx, c->ny, jlo, jhi, c->cart_iref, c->cart_jref, c->pitch, bad);
+    W2_CUDA(cudaGetLastError());
+    unsigned int hbad[32];
+    W2_CUDA(cudaMemcpyAsync(hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, c->stream));
+    W2_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long any = 0;
+    for (int k = 0; k < cc.n; ++k) any |= hbad[k] != 0;
+    if (c->world > 1) {   // the same variant on every rank (not needed for the bits, needed for the same kernel sequence timing only)
+        unsigned long long *d = c->d_norm + 47;
+        W2_CUDA(cudaMemcpyAsync(d, &any, 8, cudaMemcpyHostToDevice, c->stream));
+        W2_TRY(w2_allreduce_max_u64(c, d, 1));
+        W2_CUDA(cudaMemcpyAsync(&any, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        W2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (any) return W2_OK;
+    MomConst mc;
+    memset(&mc, 0, sizeof(mc));
+#define W2_CC_GET(name, CLS) \
+    if ((CLS) == 3) W2_CUDA(cudaMemcpy(&mc.name, t.name + (size_t)c->cart_iref + (size_t)c->pitch * (size_t)c->cart_jref, 8, cudaMemcpyDeviceToHost));
+    W2_MET_LIST(W2_CC_GET)
+#undef W2_CC_GET
+    static_assert(sizeof(MomConst) <= sizeof(c->cart_const), "cart_const too small");
+    memcpy(c->cart_const, &mc, sizeof(mc));
+    c->cart_state = 1;
     return W2_OK;
 }
 
@@ -558,6 +662,7 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
     int *ctl = (int *)(c->d_norm + W2_QL_SLOT);
     int *hctl = (int *)(c->h_norm + W2_QL_SLOT);     // pinned: [2*k], [2*k+1] = flag, count after iteration k (k = 0: final)
     if (nQLiter) *nQLiter = -1;  // :111
+    W2_TRY(mom_cart_prepare(c));
     if (!c->ev_ql[0]) for (int k = 0; k < 2; ++k) W2_CUDA(cudaEventCreateWithFlags(&c->ev_ql[k], cudaEventDisableTiming));
     ql_ctl_reset<<<1, 1, 0, c->stream>>>(ctl);
     if (init_star) {

@@ -216,6 +216,7 @@ static wolfd2_ctx *shim_ctx(int nx, int ny, const char *who) {
     }
     if (!g_shim) {
         SHIM_TRY(w2_ctx_create_raw(&g_shim, nx, ny), who);
+        g_shim->cart_state = -2;   // the literal shims get new metric arrays with every call: always the general variant
         memset(&g_shim->par, 0, sizeof(g_shim->par));
         g_shim->par.nx = nx; g_shim->par.ny = ny;
     }
