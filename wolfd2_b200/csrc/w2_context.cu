@@ -379,7 +379,7 @@ extern "C" int wolfd2_b200_upload_field(wolfd2_ctx *c, int32_t which, const doub
     if (!c->fld[which]) { w2_set_error("field %d does not exist in this context (small-scale model off)", which); return W2_ERR_BAD_ARG; }
     W2_CUDA(cudaSetDevice(c->device));
     W2_TRY(w2_upload2d(c, c->fld[which], host));
-    if (which == W2_F_D || which == W2_F_DN) c->dn_valid = 0;
+    if (which == W2_F_D || which == W2_F_DN) { c->dn_valid = 0; c->d_nonzero = 1; }
     W2_CUDA(cudaStreamSynchronize(c->stream));
     return W2_OK;
 }

@@ -51,6 +51,7 @@ struct MomArgs {
     int porous;
     const W2Regions *R;
     const unsigned char *xd1, *xd2, *yd1, *yd2, *xcp, *ycp;
+    int buoy;          // 0: d and dn are +0 everywhere (never written since allocation): the buoyancy term is +0 and b - (+0) == b bit for bit
     const int *done;   // device flag of the QL loop (null outside it): set = converged, later launches do nothing
 };
 
@@ -395,6 +396,8 @@ static void fill_args(wolfd2_ctx *c, MomArgs &m) {
     m.xmask = c->xmask; m.ymask = c->ymask;
     m.x1 = c->x1;
     m.np_c = nullptr; m.np_d = nullptr;
+    // (+0 needs dk > 0 and 0 < fr < inf; anything else keeps the term)
+    m.buoy = c->d_nonzero || !(c->par.dk > 0.0 && c->par.dk < 1.0e300 && c->par.fr > 0.0 && c->par.fr < 1.0e300);
     m.iref = c->cart_iref; m.jref = c->cart_jref;
     if (c->cart_state == 1) memcpy(&m.cc, c->cart_const, sizeof(MomConst)); else memset(&m.cc, 0, sizeof(MomConst));
     m.done = c->ql_active ? (const int *)(c->d_norm + W2_QL_SLOT) : nullptr;

@@ -486,6 +486,7 @@ extern "C" void ymomentum_(const int32_t *nx, const int32_t *ny, const int32_t *
     c->par.dk = *dk; c->par.re = *re; c->par.fr = *fr;
     up_ymom(c, ran, rbn, rbc, rgc, djv, xen, yen, xzc, yzc, xev, yev, xzv, yzv, who);
     up(c, c->fld[W2_F_D], d, who); up(c, c->fld[W2_F_DN], dn, who);
+    c->d_nonzero = 1;
     up(c, c->fld[W2_F_US], us, who); up(c, c->fld[W2_F_VS], vs, who);
     up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
     up(c, c->dvs, dvs, who);
@@ -513,6 +514,7 @@ extern "C" int32_t nauxmomentum_(const int32_t *nx, const int32_t *ny, const int
     up_xmom(c, rbn, rgn, rac, rbc, dju, xec, yec, xzn, yzn, xeu, yeu, xzu, yzu, who);
     up_ymom(c, ran, rbn, rbc, rgc, djv, xen, yen, xzc, yzc, xev, yev, xzv, yzv, who);
     up(c, c->fld[W2_F_D], d, who); up(c, c->fld[W2_F_DN], dn, who);
+    c->d_nonzero = 1;
     up(c, c->fld[W2_F_UN], un, who); up(c, c->fld[W2_F_VN], vn, who);
     up(c, c->fld[W2_F_US], us, who); up(c, c->fld[W2_F_VS], vs, who);
     // dus/dvs are local to nAuxMomentum and zeroed there (:139-144)

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) eqstate_kernel(int nx, int ny, int pitch,
 }
 
 int w2_eqstate(wolfd2_ctx *c, const double *p, const double *t, double *den) {
+    c->d_nonzero = 1;
     dim3 g((c->nx - 1 + 255) / 256, (c->ny - 1) < 2048 ? (c->ny - 1) : 2048);
     eqstate_kernel<<<g, 256, 0, c->stream>>>(c->nx, c->ny, c->pitch, c->th.uref, c->th.densref, c->th.tmax, c->th.tref,
                                              c->th.rconst, p, t, den);
