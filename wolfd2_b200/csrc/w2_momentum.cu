@@ -122,8 +122,10 @@ struct ChainWalk {
 #ifndef MOM_MINB
 #define MOM_MINB (512 / TRI_T)
 #endif
+// (round 2, after the cached explicit terms and the Cartesian metric variant: U1/U2 = 2/2 4.375 ms, 1/2 4.308, 4/2 4.58,
+// 2/4 4.43, 4/4 4.63, MINB 5 (96 registers) 4.45)
 #ifndef MOM_U1
-#define MOM_U1 2   /* unknowns of the first split step assembled per unrolled loop body */
+#define MOM_U1 1   /* unknowns of the first split step assembled per unrolled loop body */
 #endif
 #ifndef MOM_U2
 #define MOM_U2 2   /* same, second split step */
