@@ -177,7 +177,10 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().wolfd2_b200_destroy(self._h)
+            try:
+                lib().wolfd2_b200_destroy(self._h)
+            except TypeError:      # interpreter shutdown: the module globals are already gone
+                pass
             self._h = None
 
     __del__ = close

@@ -26,7 +26,10 @@
 
 #include "w2.cuh"
 
+// (SF_W 128 -- four CTAs of four warps per SM, one warp per stage -- was measured at 0.203 ms per pass against 0.194.)
+#ifndef SF_W
 #define SF_W 256              // strip width held in shared memory (cells)
+#endif
 #define SF_HALF (SF_W / 2)    // cells of one colour parity per strip row
 // Column pairs per thread (threads per stage = SF_HALF / SF_CPT).  2: each thread relaxes two cells of a row as
 // straight-line code (w2_div_fast: no branch inside the update), so the two dependent fp64 chains overlap and the
@@ -164,7 +167,7 @@ template <int T> struct SorFCfg {
 // j0..j1, ext_decide != 0: the pass is closed by a follow-up kernel).  The multi-GPU plumbing lives in that
 // follow-up kernel: anything added here, even dead code, was seen to perturb the streaming loop's code.
 template <int T>
-__global__ void __launch_bounds__(T * 2 * SF_TPS, (T == 1) ? 3 : 2) sor_rb_fused_kernel(SorFArgs a) {
+__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_kernel(SorFArgs a) {
     constexpr int NS = 2 * T;                 // half-sweep stages
     constexpr int R = SorFCfg<T>::R;
     constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
