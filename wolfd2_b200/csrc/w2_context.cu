@@ -431,10 +431,12 @@ extern int g_sor_T;
 extern int g_mom_np_cache;
 extern int g_mom_cart;
 extern int g_sor_resident;
+extern int g_sor_slab_inpass;
 extern "C" int wolfd2_b200_set_option(const char *name, int32_t value) {
     if (name && !strcmp(name, "mom_np_cache")) { g_mom_np_cache = value != 0; return W2_OK; }
     if (name && !strcmp(name, "mom_cart")) { g_mom_cart = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_resident")) { g_sor_resident = value != 0; return W2_OK; }
+    if (name && !strcmp(name, "sor_slab_inpass")) { g_sor_slab_inpass = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_fused_T")) {
         if (value < -1 || value > 2) { w2_set_error("sor_fused_T must be -1 (default), 0, 1 or 2"); return W2_ERR_BAD_ARG; }
         g_sor_T = value;

@@ -55,13 +55,20 @@ struct MomArgs {
     const int *done;   // device flag of the QL loop (null outside it): set = converged, later launches do nothing
 };
 
-namespace mom_np { constexpr bool kPorous = false; constexpr bool kCart = false;
+namespace mom_np { constexpr bool kPorous = false; constexpr bool kCart = false; constexpr bool kInterior = false;
 #include "w2_mom_rows.inc"
 }
-namespace mom_po { constexpr bool kPorous = true; constexpr bool kCart = false;
+namespace mom_po { constexpr bool kPorous = true; constexpr bool kCart = false; constexpr bool kInterior = false;
 #include "w2_mom_rows.inc"
 }
-namespace mom_ca { constexpr bool kPorous = false; constexpr bool kCart = true;   // Cartesian grid: see MET
+namespace mom_ca { constexpr bool kPorous = false; constexpr bool kCart = true; constexpr bool kInterior = false;   // Cartesian grid: see MET
+#include "w2_mom_rows.inc"
+}
+// the same rows for unknowns away from the boundary (see kInterior in w2_mom_rows.inc): no ring tests, no index clamps
+namespace mom_ni { constexpr bool kPorous = false; constexpr bool kCart = false; constexpr bool kInterior = true;
+#include "w2_mom_rows.inc"
+}
+namespace mom_ci { constexpr bool kPorous = false; constexpr bool kCart = true; constexpr bool kInterior = true;
 #include "w2_mom_rows.inc"
 }
 
@@ -159,22 +166,50 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
     ChainWalk<COMP> wa(m, e0 < n ? e0 : n - 1);
     int ci = wa.i(), cj = wa.j;
     const int sq = TRI_T / wa.w, sr = TRI_T - sq * wa.w;
-#pragma unroll(STEP == 2 ? kMomU2 : kMomU1)
-    for (int q = 0; q < TRI_M; ++q) {
-        const int el = t + TRI_T * q;
-        const long long e = ebase + el;
-        const bool live = e < n;
-        if (q > 0) {
-            wa.advance_split(sq, sr);
-            ci = live ? wa.i() : ci; cj = live ? wa.j : cj;
+    constexpr int UB = (STEP == 2 ? kMomU2 : kMomU1);   // unknowns per loop body
+    static_assert(TRI_M % UB == 0, "unroll depth must divide the chunk length");
+#pragma unroll 1
+    for (int q0 = 0; q0 < TRI_M; q0 += UB) {
+        int ui[UB], uj[UB];
+        bool inner = true;
+#pragma unroll
+        for (int k = 0; k < UB; ++k) {
+            const long long e = ebase + t + TRI_T * (q0 + k);
+            const bool live = e < n;
+            if (q0 + k > 0) {
+                wa.advance_split(sq, sr);
+                ci = live ? wa.i() : ci; cj = live ? wa.j : cj;
+            }
+            ui[k] = ci; uj[k] = cj;
+            inner = inner && ci >= 2 && ci <= m.nx - 1 && cj >= 2 && cj <= m.ny - 1;
         }
-        double a1, a2, a3, b;
-        if (VAR == 1) mom_po::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
-        else if (VAR == 2) mom_ca::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
-        else mom_np::mom_row<COMP, STEP, NP>(m, ci, cj, a1, a2, a3, b);
-        a3 = (e == n - 1) ? 0.0 : a3;
-        const int p = MR_PAD(el);
-        s0[p] = live ? a1 : 0.0; s1[p] = live ? a2 : 1.0; s2[p] = live ? a3 : 0.0; s3[p] = live ? b : 0.0;
+        // Warps whose unknowns all lie away from the boundary (all but those at the ends of a grid row and in the first /
+        // last row) take the rows without ring tests and index clamps (mom_ni / mom_ci: the same numbers).  The branch is
+        // warp-uniform and encloses the whole body, so inside either side the loads of the UB unknowns still issue together.
+        double a1[UB], a2[UB], a3[UB], b[UB];
+        if (VAR != 1 && __all_sync(0xffffffffu, inner)) {
+#pragma unroll
+            for (int k = 0; k < UB; ++k) {
+                if (VAR == 2) mom_ci::mom_row<COMP, STEP, NP>(m, ui[k], uj[k], a1[k], a2[k], a3[k], b[k]);
+                else mom_ni::mom_row<COMP, STEP, NP>(m, ui[k], uj[k], a1[k], a2[k], a3[k], b[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < UB; ++k) {
+                if (VAR == 1) mom_po::mom_row<COMP, STEP, NP>(m, ui[k], uj[k], a1[k], a2[k], a3[k], b[k]);
+                else if (VAR == 2) mom_ca::mom_row<COMP, STEP, NP>(m, ui[k], uj[k], a1[k], a2[k], a3[k], b[k]);
+                else mom_np::mom_row<COMP, STEP, NP>(m, ui[k], uj[k], a1[k], a2[k], a3[k], b[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UB; ++k) {
+            const int el = t + TRI_T * (q0 + k);
+            const long long e = ebase + el;
+            const bool live = e < n;
+            const double c3 = (e == n - 1) ? 0.0 : a3[k];
+            const int p = MR_PAD(el);
+            s0[p] = live ? a1[k] : 0.0; s1[p] = live ? a2[k] : 1.0; s2[p] = live ? c3 : 0.0; s3[p] = live ? b[k] : 0.0;
+        }
     }
     if (ebase == 0 && t == 0) {   // AltTridLU first row: a(3,1)/a(2,2) (:1319) == plain Thomas with c1*d1/d2
         int i2, j2; double b1, b2, b3, bb;
@@ -214,15 +249,18 @@ __global__ void __launch_bounds__(TRI_T, MOM_MINB) mom_reduce_kernel(MomArgs m, 
         if (nzw) atomicMax(&s_ext[1], TRI_S - TRI_M * t);
     }
     __syncthreads();   // core's shared arrays are dead; s_ext final
-    // ---- phase C: transpose back and write coalesced
+    // ---- phase C: transpose back and write coalesced (spike entries only where they will be read: el < extV,
+    // el >= TRI_S - extW -- a quarter of the segment each at 4096^2)
+    const int extV = s_ext[0], extW = s_ext[1];
+    const bool putV = !direct && TRI_M * t < extV, putW = !direct && TRI_M * t + TRI_M - 1 >= TRI_S - extW;
 #pragma unroll
     for (int k = 0; k < TRI_M; ++k) {
         const int p = 9 * t + k;
         s0[p] = Ye[k];
-        if (!direct) { s1[p] = Ve[k]; s2[p] = We[k]; }
+        if (putV) s1[p] = Ve[k];
+        if (putW) s2[p] = We[k];
     }
     __syncthreads();
-    const int extV = s_ext[0], extW = s_ext[1];
     ChainWalk<COMP> wc(m, ebase + t);
 #pragma unroll 1
     for (int q = 0; q < TRI_M; ++q) {

@@ -166,8 +166,15 @@ template <int T> struct SorFCfg {
 // The same kernel serves one GPU (rows 2..ny, the last CTA closes the pass) and one rank's row slab (rows
 // j0..j1, ext_decide != 0: the pass is closed by a follow-up kernel).  The multi-GPU plumbing lives in that
 // follow-up kernel: anything added here, even dead code, was seen to perturb the streaming loop's code.
-template <int T>
-__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_kernel(SorFArgs a) {
+// Closing a pass on a row slab (peer-memory path): publish this slab's max-norms and the pass number in every rank's
+// mailbox, wait for the same record from every rank -- a barrier across the GPUs -- and take the common decision of
+// sorf_close_pass.  Run by the first warp of the slab's last CTA (sorf_body<T, true>) or of sorf_edge_kernel.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p);
+template <class ARGS>
+__device__ __forceinline__ void sorf_slab_close(const ARGS &a, int T, int cur, int tid);
+
+template <int T, bool SLAB, class ARGS>
+__device__ __forceinline__ void sorf_body(const ARGS &a) {
     constexpr int NS = 2 * T;                 // half-sweep stages
     constexpr int R = SorFCfg<T>::R;
     constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
@@ -183,6 +190,8 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF
     const int cur = ctl->cur;
     const double *__restrict__ psrc = cur ? a.pB : a.pA;
     double *__restrict__ pdst = cur ? a.pA : a.pB;
+    double *nbr_lo = nullptr, *nbr_hi = nullptr;   // slab runs: the neighbours' copies of pdst (null at a physical boundary)
+    if constexpr (SLAB) { nbr_lo = cur ? a.nbrA[0] : a.nbrB[0]; nbr_hi = cur ? a.nbrA[1] : a.nbrB[1]; }
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sP = reinterpret_cast<double *>(smem_raw);
@@ -324,10 +333,25 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF
         __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
         if (last_stage && (unsigned)(q - jA) <= jspan) {
+            // slab runs: the first / last 2T rows of the slab are the neighbours' halo rows -- the same words go straight
+            // into the neighbour's destination buffer (peer stores over NVLink), so that no copy kernel follows the pass
+            double *nst = nullptr;
+            if constexpr (SLAB) {
+                double *nd = (q - a.j0 < H) ? nbr_lo : (a.j1 - q < H) ? nbr_hi : nullptr;
+                if (nd != nullptr) nst = nd + (gst - pdst);
+            }
 #pragma unroll
             for (int u = 0; u < SF_CPT; ++u) {
-                if ((omask >> (2 * u)) & 1u) gst[u * SF_TPS] = lds_f64(aP + off_q + base8 + u * PAIRB);
-                if ((omask >> (2 * u + 1)) & 1u) gst[hp + u * SF_TPS] = lds_f64(aP + off_q + HSTRB + base8 + u * PAIRB);
+                if ((omask >> (2 * u)) & 1u) {
+                    const double x = lds_f64(aP + off_q + base8 + u * PAIRB);
+                    gst[u * SF_TPS] = x;
+                    if (SLAB && nst != nullptr) nst[u * SF_TPS] = x;
+                }
+                if ((omask >> (2 * u + 1)) & 1u) {
+                    const double x = lds_f64(aP + off_q + HSTRB + base8 + u * PAIRB);
+                    gst[hp + u * SF_TPS] = x;
+                    if (SLAB && nst != nullptr) nst[hp + u * SF_TPS] = x;
+                }
             }
         }
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
@@ -349,15 +373,39 @@ __global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF
         if (tid == 0 && t < Tp) atomicMax(&ctl->slot[t], w2_dbits(m));
     }
     // ---- the last CTA closes the pass
-    if (tid == 0 && !a.ext_decide) {
-        __threadfence();
-        const int total = gridDim.x * gridDim.y;
-        if (atomicAdd(&ctl->ticket, 1) == total - 1) {
+    if constexpr (SLAB) {
+        __shared__ int s_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();                     // this CTA's peer stores are visible before its ticket
+            s_last = atomicAdd(&ctl->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+        }
+        __syncthreads();
+        if (s_last && tid < 32) sorf_slab_close(a, T, cur, tid);
+    } else {
+        if (tid == 0 && !a.ext_decide) {
             __threadfence();
-            sorf_close_pass(ctl, Tp, cur, a.sortol, a.msorit);
-            __threadfence();
+            const int total = gridDim.x * gridDim.y;
+            if (atomicAdd(&ctl->ticket, 1) == total - 1) {
+                __threadfence();
+                sorf_close_pass(ctl, Tp, cur, a.sortol, a.msorit);
+                __threadfence();
+            }
         }
     }
+}
+
+// The same code serves one GPU (rows 2..ny, the last CTA closes the pass; also the NCCL slab path, closed by a follow-up
+// kernel) and one rank's row slab over peer memory (SLAB: edge rows stored to the neighbours by the pass itself, the pass
+// closed across the GPUs by the slab's last CTA).  Two kernels, so that the one-GPU kernel's parameter block and code are
+// not touched by the slab plumbing.
+template <int T>
+__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_kernel(SorFArgs a) {
+    sorf_body<T, false>(a);
+}
+template <int T>
+__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_slab_kernel(SorFSlabArgs a) {
+    sorf_body<T, true>(a);
 }
 
 // Several GPUs: every rank's slots hold the max over its slab; after the all-reduce one thread per rank
@@ -368,45 +416,20 @@ __global__ void sorf_decide_kernel(SorFCtl *ctl, int T, double sortol, int msori
     sorf_close_pass(ctl, Tp, ctl->cur, sortol, msorit);
 }
 
-// Peer-memory path: the kernel that follows every slab pass.  (1) The slab's first / last 2T rows are the
-// neighbours' halo rows: CTA (strip, side) copies its columns of them (just written, still in L2) into the
-// neighbour's destination buffer with plain stores over NVLink.  (2) The last CTA to finish publishes this
-// slab's max-norms and the pass number in every rank's mailbox (system-scope release), then (3) its first warp
-// waits for the same record from every rank -- a barrier across the GPUs -- and takes the common decision.
+// Peer-memory path (no NCCL call inside the loop): the slab kernel stores the slab's first / last 2T rows, as they
+// become final, into the neighbours' destination buffers as well (sorf_body<T, true>), and the first warp of the LAST CTA
+// to finish closes the pass across the GPUs: (1) it publishes this slab's max-norms and the pass number in every rank's
+// mailbox (system-scope release), (2) waits for the same record from every rank -- a barrier across the GPUs -- and
+// (3) takes the common decision.  (Round 1 did (1)-(3) and the edge copy in a kernel of its own after every pass:
+// two more launch gaps per pass.)
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void __launch_bounds__(256) sorf_edge_kernel(SorFSlabArgs a, int T) {
+template <class ARGS>
+__device__ __forceinline__ void sorf_slab_close(const ARGS &a, int T, int cur, int tid) {
     SorFCtl *ctl = a.ctl;
-    if (ctl->done) return;
-    __shared__ int s_last;
-    const int H = 2 * T, tid = threadIdx.x;
-    const int cur = ctl->cur;                       // the pass just run wrote the other buffer
-    const double *pdst = cur ? a.pA : a.pB;
-    const int sd = blockIdx.y;                      // 0: rows j0.. to rank-1, 1: rows ..j1 to rank+1
-    double *nd = cur ? a.nbrA[sd] : a.nbrB[sd];
-    if (nd != nullptr) {
-        const int i0 = blockIdx.x * a.own_w;
-        const bool physL = blockIdx.x == 0, physR = (i0 + SF_W - 1 >= a.nx + 1);
-        const int own_lo = physL ? 2 : i0 + H;
-        const int own_hi = physR ? a.nx : min(a.nx, i0 + H + a.own_w - 1);
-        const int ow = own_hi - own_lo + 1, hp = a.pitch >> 1;
-        const int row0 = sd ? a.j1 - H + 1 : a.j0;
-        for (int k = tid; k < H * ow; k += blockDim.x) {
-            const int rr = k / ow, i = own_lo + (k - rr * ow);
-            const size_t off = (size_t)a.pitch * (size_t)(row0 + rr) + (size_t)(i & 1) * hp + (size_t)(i >> 1);
-            nd[off] = pdst[off];
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();                     // this CTA's peer stores are visible before its ticket
-        s_last = atomicAdd(&ctl->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
-    }
-    __syncthreads();
-    if (!s_last || tid >= 32) return;
     W2Mail *me = a.mail[a.rank];
     const unsigned long long seq = me->my_seq + 1ull;
     const int par = (int)(seq & 1ull);
@@ -444,6 +467,40 @@ __global__ void __launch_bounds__(256) sorf_edge_kernel(SorFSlabArgs a, int T) {
         ctl->slot[t] = m;
     }
     sorf_close_pass(ctl, Tp, cur, a.sortol, a.msorit);
+}
+
+// The follow-up kernel of the default peer-memory path (option "sor_slab_inpass" 0): after the unchanged one-GPU pass
+// kernel, CTA (strip, side) copies its columns of the slab's first / last 2T rows (just written, still in L2) into the
+// neighbour's destination buffer with plain stores over NVLink; the last CTA to finish closes the pass across the GPUs.
+__global__ void __launch_bounds__(256) sorf_edge_kernel(SorFSlabArgs a, int T) {
+    SorFCtl *ctl = a.ctl;
+    if (ctl->done) return;
+    __shared__ int s_last;
+    const int H = 2 * T, tid = threadIdx.x;
+    const int cur = ctl->cur;                       // the pass just run wrote the other buffer
+    const double *pdst = cur ? a.pA : a.pB;
+    const int sd = blockIdx.y;                      // 0: rows j0.. to rank-1, 1: rows ..j1 to rank+1
+    double *nd = cur ? a.nbrA[sd] : a.nbrB[sd];
+    if (nd != nullptr) {
+        const int i0 = blockIdx.x * a.own_w;
+        const bool physL = blockIdx.x == 0, physR = (i0 + SF_W - 1 >= a.nx + 1);
+        const int own_lo = physL ? 2 : i0 + H;
+        const int own_hi = physR ? a.nx : min(a.nx, i0 + H + a.own_w - 1);
+        const int ow = own_hi - own_lo + 1, hp = a.pitch >> 1;
+        const int row0 = sd ? a.j1 - H + 1 : a.j0;
+        for (int k = tid; k < H * ow; k += blockDim.x) {
+            const int rr = k / ow, i = own_lo + (k - rr * ow);
+            const size_t off = (size_t)a.pitch * (size_t)(row0 + rr) + (size_t)(i & 1) * hp + (size_t)(i >> 1);
+            nd[off] = pdst[off];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();                     // this CTA's peer stores are visible before its ticket
+        s_last = atomicAdd(&ctl->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) sorf_slab_close(a, T, cur, tid);
 }
 
 // Start-of-solve barrier: tells every rank that this rank's two pressure buffers are initialised (so peer
@@ -507,6 +564,11 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 
 // ---------------------------------------------------------------------------------------- host
 
+// option "sor_slab_inpass": 1 = on several GPUs the pass kernel itself stores the edge rows to the neighbours and closes the
+// pass (sor_rb_fused_slab_kernel: no follow-up launch, but 10 more registers in the streaming loop); 0 = the unchanged
+// one-GPU pass kernel followed by sorf_edge_kernel (the path every committed multi-GPU result was measured with)
+int g_sor_slab_inpass = 0;
+
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
     const size_t smem = SorFCfg<T>::smem;
@@ -516,6 +578,17 @@ static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
         attr_set[c->device % W2_MAXDEV] = true;
     }
     sor_rb_fused_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
+    return W2_OK;
+}
+template <int T>
+static int launch_fused_slab(wolfd2_ctx *c, const SorFSlabArgs &a, dim3 grid) {
+    const size_t smem = SorFCfg<T>::smem;
+    static bool attr_set[W2_MAXDEV] = {};   // per device
+    if (!attr_set[c->device % W2_MAXDEV]) {
+        W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_slab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[c->device % W2_MAXDEV] = true;
+    }
+    sor_rb_fused_slab_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
     return W2_OK;
 }
 template <int T>
@@ -609,14 +682,22 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         }
         const int n = chunk < passes_max - queued ? chunk : passes_max - queued;
         for (int q = 0; q < n; ++q) {
-            if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
-            else W2_TRY(launch_fused<2>(c, a, grid));
+            if (a.ext_decide == 2 && g_sor_slab_inpass) {
+                // slab run over peer memory, in-pass variant: the pass stores its edge rows to the neighbours and closes
+                // itself across the GPUs
+                if (T == 1) W2_TRY(launch_fused_slab<1>(c, a, grid));
+                else W2_TRY(launch_fused_slab<2>(c, a, grid));
+            } else {
+                if (T == 1) W2_TRY(launch_fused<1>(c, a, grid));
+                else W2_TRY(launch_fused<2>(c, a, grid));
+            }
             c->launches[2]++;
-            if (a.ext_decide == 2) {
+            if (a.ext_decide == 2 && !g_sor_slab_inpass) {
                 // slab run over peer memory: edge rows and max-norms go to the peers, then the common decision
                 sorf_edge_kernel<<<dim3(a.nstrips, 2), 256, 0, c->stream>>>(a, T);
                 c->launches[2]++;
-            } else if (a.ext_decide == 1) {
+            }
+            if (a.ext_decide == 1) {
                 // slab run: global max-norms, the common decision, then the 2T halo rows of the iterate.
                 // Which buffer was written is known on the device only; the other one's halos are already
                 // right, so both are exchanged (a few hundred KB).

@@ -84,10 +84,10 @@ __global__ void __launch_bounds__(SR_T, 1) sor_rb_resident_kernel(SorRArgs a) {
                 for (int k = 0; k < 4; ++k) {              // straight-line code: every quotient is formed before anything is branched on
                     const int r = r0 + k, j = jA + r, i = 2 + ((c + j) & 1) + 2 * t;
                     const bool ex = (own >> (2 * r + c)) & 1u;
-                    const int ic = ex ? i : 2;             // cells that do not exist compute on cell (2, jA) and store nothing
-                    const int rr = ex ? r : 0;
-                    const int q = sr_col(ic, hw), qw = sr_col(ic - 1, hw);
-                    const double *rowP = sP + (rr + 1) * W;
+                    const int ic = ex ? i : 2;             // cells that do not exist compute on cell (2, jA) and store nothing;
+                    const int rr = ex ? r : 0;             // their five "pressures" come from rows of rgv, which nobody writes
+                    const int q = sr_col(ic, hw), qw = sr_col(ic - 1, hw);   // (racecheck r02: reads of p(2,jA) raced with its owner's store)
+                    const double *rowP = ex ? sP + (rr + 1) * W : sV + W;
                     const double pc = rowP[q], pW = rowP[qw], pE = rowP[qw + 1], pS = rowP[q - W], pN = rowP[q + W];
                     const double a1 = sV[rr * W + q], a5 = sV[(rr + 1) * W + q], a2 = sU[rr * W + qw], a4 = sU[rr * W + q];
                     a3v[k] = -a4 - a2 - a5 - a1;

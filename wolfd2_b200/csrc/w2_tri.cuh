@@ -20,6 +20,21 @@ __device__ __forceinline__ double tri_rcp(double x) {
     return __fma_rn(y, e, y);
 }
 
+// a*b + c of the elimination.  The library is built with -fmad=false so that the stencils keep the reference's rounding;
+// the elimination order of this solver differs from AltTridLU's anyway (tolerances: DESIGN.md section 5), so its
+// multiply-adds are fused explicitly: one rounding instead of two, and a third fewer fp64 instructions in the core.
+// (-DTRI_FMA=0 restores the unfused arithmetic of rounds 1 and 2a.)
+#ifndef TRI_FMA
+#define TRI_FMA 1
+#endif
+__device__ __forceinline__ double tri_fma(double a, double b, double c) {
+#if TRI_FMA
+    return __fma_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+
 // Input: this thread's TRI_M consecutive rows (A,D,C,B).  Output: for each of them the coefficients of
 //   x = Ye - Sg[g-1]*Ve - Sg[g]*We
 // where Sg[g] is the CTA's separator (its last unknown) and Sg[g-1] that of the previous segment, plus
@@ -39,16 +54,16 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
         cp[0] = C[0] * inv; y[0] = B[0] * inv; v[0] = A[0] * inv;
 #pragma unroll
         for (int k = 1; k <= L; ++k) {
-            inv = tri_rcp(D[k] - A[k] * cp[k - 1]);
+            inv = tri_rcp(tri_fma(-A[k], cp[k - 1], D[k]));
             cp[k] = C[k] * inv;
-            y[k] = (B[k] - A[k] * y[k - 1]) * inv;
+            y[k] = tri_fma(-A[k], y[k - 1], B[k]) * inv;
             v[k] = (-A[k] * v[k - 1]) * inv;
         }
         w[L] = cp[L];
 #pragma unroll
         for (int k = L - 1; k >= 0; --k) {
-            y[k] = y[k] - cp[k] * y[k + 1];
-            v[k] = v[k] - cp[k] * v[k + 1];
+            y[k] = tri_fma(-cp[k], y[k + 1], y[k]);
+            v[k] = tri_fma(-cp[k], v[k + 1], v[k]);
             w[k] = -cp[k] * w[k + 1];
         }
     }
@@ -60,10 +75,10 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
     if (t < TRI_T - 1) {
         const double yF = sY[t + 1], vF = sV[t + 1], wF = sW[t + 1];
         rA = -ar * v[L];
-        rD = dr - ar * w[L] - cr * vF;
+        rD = tri_fma(-cr, vF, tri_fma(-ar, w[L], dr));
         rC = -cr * wF;
-        rY = br - ar * y[L];
-        rY = rY - cr * yF;
+        rY = tri_fma(-ar, y[L], br);
+        rY = tri_fma(-cr, yF, rY);
         rV = 0.0; rW = 0.0;
         if (t == 0) { rV = rA; rA = 0.0; }
         if (t == TRI_T - 2) { rW = rC; rC = 0.0; }
@@ -82,10 +97,10 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
         if (lo >= 0) { aL = sA[lo]; dL = sD[lo]; cL = sC[lo]; yL = sY[lo]; vL = sV[lo]; wL = sW[lo]; }
         if (hi < TRI_T) { aH = sA[hi]; dH = sD[hi]; cH = sC[hi]; yH = sY[hi]; vH = sV[hi]; wH = sW[hi]; }
         const double al = -rA * tri_rcp(dL), ga = -rC * tri_rcp(dH);
-        rD = rD + al * cL + ga * aH;
-        rY = rY + al * yL + ga * yH;
-        rV = rV + al * vL + ga * vH;
-        rW = rW + al * wL + ga * wH;
+        rD = tri_fma(ga, aH, tri_fma(al, cL, rD));
+        rY = tri_fma(ga, yH, tri_fma(al, yL, rY));
+        rV = tri_fma(ga, vH, tri_fma(al, vL, rV));
+        rW = tri_fma(ga, wH, tri_fma(al, wL, rW));
         rA = al * aL;
         rC = ga * cH;
         __syncthreads();
@@ -102,9 +117,9 @@ __device__ __forceinline__ void tri_cta_core(const double (&A)[TRI_M], const dou
     // --- per-element coefficients of the segment-level representation
 #pragma unroll
     for (int k = 0; k <= L; ++k) {
-        Ye[k] = y[k] - py * v[k] - sy * w[k];
-        Ve[k] = -(pv * v[k] + sv * w[k]);
-        We[k] = -(pw * v[k] + sw * w[k]);
+        Ye[k] = tri_fma(-sy, w[k], tri_fma(-py, v[k], y[k]));
+        Ve[k] = -tri_fma(sv, w[k], pv * v[k]);
+        We[k] = -tri_fma(sw, w[k], pw * v[k]);
     }
     Ye[TRI_M - 1] = sy; Ve[TRI_M - 1] = sv; We[TRI_M - 1] = sw;
 
