@@ -49,6 +49,10 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     local = int(os.environ.get("LOCAL_RANK", rank))
     slab.init_comm(dist, local)
+    for kv in os.environ.get("W2_OPTS", "").split(","):   # e.g. W2_OPTS=sor_slab_inpass=1 (A/B of a library option)
+        if kv:
+            k, v = kv.split("=")
+            api.set_option(k, int(v))
     failures = []
     for name, g, nsteps in cases():
         try:

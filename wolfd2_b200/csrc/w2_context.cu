@@ -269,6 +269,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     ffree(c, c->heat_s); cudaFree(c->dth);
     w2_peer_release(c);   // before the buffers the peers have mapped go away
     for (int k = 0; k < 4; ++k) ffree(c, c->sorf_buf[k]);
+    if (c->sorf_coef) cudaFree(c->sorf_coef);
     cudaFree(c->ta); cudaFree(c->td); cudaFree(c->tc); cudaFree(c->tb); cudaFree(c->tx);
     w2_tri_release(c);
     cudaFree(c->d_norm); cudaFree(c->d_flags); cudaFree(c->dreg);

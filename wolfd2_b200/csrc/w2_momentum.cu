@@ -126,8 +126,10 @@ struct ChainWalk {
 // Resident CTAs per SM and unroll depth, swept on B200 after phase A became straight-line code (momentum ms/step at
 // 4096^2, Q=2): MINB/U1/U2 = 5/2/4 5.64, 4/2/4 5.15, 4/2/2 5.11, 4/1/4 5.33, 4/4/4 5.33, 4/2/8 5.71, 3/2/4 5.66, 6/2/4 7.08
 // (80 registers: spills).  128 registers per thread hold more loads in flight than a fifth CTA hides.
+// (round 2b, after the interior-row variant below took ~110 instructions and 12 loads per unknown out of phase A:
+// MINB 4 (128 registers) 4.13-4.17 ms, 5 (96 registers, no spills on the hot variants) 3.94-3.98, 6 (80 registers) 4.46)
 #ifndef MOM_MINB
-#define MOM_MINB (512 / TRI_T)
+#define MOM_MINB 5
 #endif
 // (round 2, after the cached explicit terms and the Cartesian metric variant: U1/U2 = 2/2 4.375 ms, 1/2 4.308, 4/2 4.58,
 // 2/4 4.43, 4/4 4.63, MINB 5 (96 registers) 4.45)

@@ -44,6 +44,12 @@
 #define SF_CPT 2
 #endif
 #define SF_TPS (SF_HALF / SF_CPT)
+#ifndef SF_DIAG
+#define SF_DIAG 0             // timing experiments only (wrong results): 1 no update arithmetic, 2 no store-back, 4 no step barrier, 8 no TMA
+#endif
+#ifndef SF_BAL_STORE
+#define SF_BAL_STORE 1        // finished rows are stored by all threads of the CTA (0: by the last stage's threads, round 2a)
+#endif
 #define SF_PADL 2             // pad cells on each side of a half row (keeps TMA destinations 16-byte aligned)
 #define SF_HSTR (SF_HALF + 2 * SF_PADL)   // one half row in shared memory
 #define SF_STRIDE (2 * SF_HSTR)           // shared row stride in doubles: [even-i half | odd-i half]
@@ -75,6 +81,10 @@ struct SorFArgs {
     const double *rau, *rgv, *b;
     double *pA, *pB;
     SorFCtl *ctl;
+    // b, rau, rgv once more, tiled for the kernel: tile (strip s, row j) = 6 * SF_HALF consecutive doubles at
+    // coef + ((size_t)s * crows + j) * SF_CTILE (the pointer is shifted so that j is the global row index)
+    const double *coef;
+    long long crows;
 };
 
 // one rank's slab: rows j0..j0+2T-1 also go to the south neighbour's halo, j1-2T+1..j1 to the north one's.
@@ -158,9 +168,14 @@ __device__ __forceinline__ void sorf_close_pass(SorFCtl *ctl, int Tp, int cur, d
     ctl->last_dif = last;
 }
 
+// One ring slot holds one grid row of the strip: the iterate p in the padded colour-split layout (SF_STRIDE doubles),
+// followed by the row's coefficient tile -- b, rau, rgv, each [even-i half | odd-i half] of SF_HALF doubles, dense --
+// exactly as it lies in the tiled coefficient array (sorf_tile_kernel), so that ONE bulk copy brings it in.
+#define SF_CTILE (6 * SF_HALF)                  // doubles per coefficient tile (one strip, one row): 6 KB
+#define SF_SLOT (SF_STRIDE + SF_CTILE)          // doubles per ring slot
 template <int T> struct SorFCfg {
-    static constexpr int R = (T == 1) ? 8 : 13;      // ring depth in rows (T=2: 108 KB -> two CTAs per SM)
-    static constexpr size_t smem = (size_t)4 * R * SF_STRIDE * sizeof(double) + R * sizeof(unsigned long long);
+    static constexpr int R = (T == 1) ? 8 : 13;      // ring depth in rows (T=2: 105 KB -> two CTAs per SM)
+    static constexpr size_t smem = (size_t)R * SF_SLOT * sizeof(double) + R * sizeof(unsigned long long);
 };
 
 // The same kernel serves one GPU (rows 2..ny, the last CTA closes the pass) and one rank's row slab (rows
@@ -180,8 +195,9 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     constexpr int LIVE = 4 * T + 1;           // rows between the newest and the one being stored
     constexpr int D = R - LIVE - 1;           // prefetch distance (rows)
     constexpr int H = 2 * T;                  // halo columns/rows on a non-physical side
-    constexpr int RS = R * SF_STRIDE;
+    constexpr int RS = R * SF_SLOT;
     static_assert(D >= 2, "ring too shallow");
+    static_assert((SF_STRIDE * 8) % 16 == 0 && (SF_SLOT * 8) % 16 == 0, "bulk-copy destinations must be 16-byte aligned");
 
     SorFCtl *ctl = a.ctl;
     if (ctl->done) return;
@@ -194,11 +210,8 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     if constexpr (SLAB) { nbr_lo = cur ? a.nbrA[0] : a.nbrB[0]; nbr_hi = cur ? a.nbrA[1] : a.nbrB[1]; }
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sP = reinterpret_cast<double *>(smem_raw);
-    double *sB = sP + RS;
-    double *sU = sB + RS;   // rau
-    double *sV = sU + RS;   // rgv
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sV + RS);
+    double *sP = reinterpret_cast<double *>(smem_raw);    // ring slots: [p row | coefficient tile]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sP + RS);
     __shared__ double red[32];
 
     const int tid = threadIdx.x;
@@ -221,33 +234,42 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     // zero the pad cells once (read by edge threads, never used by owned cells)
     for (int k = tid; k < R * 8; k += blockDim.x) {
         const int row = k >> 3, q = k & 7;   // pads: 0,1 | 130,131 | 132,133 | 262,263
-        const int off = row * SF_STRIDE + (q >> 2) * SF_HSTR + ((q & 3) < 2 ? (q & 3) : SF_HALF + (q & 3));
-        sP[off] = 0.0; sB[off] = 0.0; sU[off] = 0.0; sV[off] = 0.0;
+        const int off = row * SF_SLOT + (q >> 2) * SF_HSTR + ((q & 3) < 2 ? (q & 3) : SF_HALF + (q & 3));
+        sP[off] = 0.0;   // (the coefficient tiles have no pads: an edge thread reads a neighbouring word of the tile instead)
     }
     __syncthreads();
 
-    // ---- producer state (lanes 0..7 of warp 0, one bulk copy each): next row to request and its ring slot
+    // ---- producer state (lanes 0..2 of warp 0, one bulk copy each): next row to request and its ring slot.
+    // Every bulk copy costs the SM's copy engine about the same whatever its size (measured: halving the number of copies
+    // of a row at equal bytes took 13 % off the pass), so a row arrives in three copies -- the two colour halves of p (1 KB
+    // each; p is written by the kernel itself in the colour-split field layout) and the coefficient tile (6 KB) -- instead
+    // of the eight 1 KB copies of round 2a.
     const int hp = pitch >> 1;                       // half pitch: start of the odd-i half of a row
+    constexpr int NLD = 3;
     int ld_row = jL0, ld_slot = 0;
     unsigned ld_off = 0;
-    // lane l copies array (l>>1) in {p, b, rau, rgv}, half (l&1) in {even i, odd i}; 1 KB each
     const double *ld_src = nullptr;
     double *ld_dst = nullptr;
-    if (tid < 8) {
-        const int arr = tid >> 1, half = tid & 1;
-        const double *g = arr == 0 ? psrc : arr == 1 ? a.b : arr == 2 ? a.rau : a.rgv;
-        ld_src = g + (size_t)pitch * jL0 + (i0 >> 1) + (half ? hp : 0);   // i0 is a multiple of 4: 16-byte aligned
-        ld_dst = sP + arr * RS + half * SF_HSTR + SF_PADL;
+    unsigned ld_bytes = SF_HALF * 8;
+    size_t ld_step = (size_t)pitch;
+    if (tid < 2) {           // p: even-i / odd-i half of the strip's columns
+        ld_src = psrc + (size_t)pitch * jL0 + (i0 >> 1) + (tid ? hp : 0);   // i0 is a multiple of 4: 16-byte aligned
+        ld_dst = sP + tid * SF_HSTR + SF_PADL;
+    } else if (tid == 2) {   // the row's coefficient tile
+        ld_src = a.coef + ((size_t)strip * (size_t)a.crows + (size_t)jL0) * SF_CTILE;
+        ld_dst = sP + SF_STRIDE;
+        ld_bytes = SF_CTILE * 8;
+        ld_step = SF_CTILE;
     }
-    auto issue_row = [&]() {   // executed by lanes 0..7 together
-        if (tid == 0) mbar_expect_tx(&bars[ld_slot], 4u * SF_W * 8u);
-        tma_load_1d(ld_dst + ld_off, ld_src, SF_HALF * 8, &bars[ld_slot]);
-        ++ld_row; ld_src += pitch;
-        ld_off += SF_STRIDE; ++ld_slot;
+    auto issue_row = [&]() {   // executed by lanes 0..NLD-1 together
+        if (tid == 0) mbar_expect_tx(&bars[ld_slot], (2u * SF_HALF + SF_CTILE) * 8u);
+        tma_load_1d(ld_dst + ld_off, ld_src, ld_bytes, &bars[ld_slot]);
+        ++ld_row; ld_src += ld_step;
+        ld_off += SF_SLOT; ++ld_slot;
         if (ld_slot == R) { ld_slot = 0; ld_off = 0; }
     };
-    if (tid < 8)
-        for (int n = 0; n <= D && ld_row <= jL1; ++n) issue_row();
+    if (tid < NLD)
+        for (int n = 0; n <= D && ld_row <= jL1 && !(SF_DIAG & 8); ++n) issue_row();
 
     // ---- consumer state (all shared-memory addresses are 32-bit byte addresses)
     const int stage = tid / SF_TPS + 1;       // 1..NS, SF_TPS threads per stage
@@ -269,11 +291,14 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     const double sorrel = a.sorrel;
     double lmax = 0.0;
 
-    constexpr unsigned ROWB = SF_STRIDE * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8, PAIRB = SF_TPS * 8;
+    constexpr unsigned ROWB = SF_SLOT * 8, RINGB = RS * 8, HSTRB = SF_HSTR * 8, PAIRB = SF_TPS * 8;
+    constexpr unsigned CHALFB = SF_HALF * 8;                       // one colour half of one array inside a tile
     unsigned sbase = smem_u32(smem_raw);
     asm volatile("" : "+r"(sbase));   // opaque: keeps the shared window base in a register instead of re-deriving it per row
-    const unsigned aP = sbase, aB = sbase + RINGB, aU = sbase + 2 * RINGB, aV = sbase + 3 * RINGB, aBar = sbase + 4 * RINGB;
+    // byte addresses inside a slot: p at 0, then the tile: b, rau, rgv
+    const unsigned aP = sbase, aB = sbase + SF_STRIDE * 8, aU = aB + 2 * CHALFB, aV = aB + 4 * CHALFB, aBar = sbase + RINGB;
     const unsigned base8 = (SF_PADL + kk0) * 8;
+    const unsigned cbase8 = kk0 * 8;                               // the same pair inside a (pad-free) tile half
 
     int q = jL0 - 2 * stage + 1;              // row relaxed by this stage at time step r = jL0
     auto ring_off = [&](int row) { int m = (row - jL0) % R; if (m < 0) m += R; return (unsigned)m * ROWB; };
@@ -283,14 +308,38 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     unsigned ha8 = base8 + par * HSTRB;
     unsigned hw8 = par ? base8 : base8 + HSTRB - 8;
     const unsigned HA_SUM = 2 * base8 + HSTRB, HW_SUM = 2 * base8 + HSTRB - 8;
+    // the same two positions in a coefficient tile (no pads; pair 0's west neighbour of an even cell is the word before
+    // the odd half -- some finite coefficient, used by the strip's outermost halo cell only, whose result nobody reads)
+    unsigned ca8 = cbase8 + par * CHALFB;
+    unsigned cw8 = par ? cbase8 : cbase8 + CHALFB - 8;
+    const unsigned CA_SUM = 2 * cbase8 + CHALFB, CW_SUM = 2 * cbase8 + CHALFB - 8;
     unsigned w_bar = aBar, w_par = 0;
+#if SF_BAL_STORE
+    // Store-back of a finished row, shared by ALL threads of the CTA (cell c = tid + k*blockDim of the row's SF_W cells,
+    // [even-i half | odd-i half]) instead of by the two warps of the last stage: those warps were the longest path between
+    // two block barriers (update + 4 loads and stores per thread), and every other warp waited for them.
+    constexpr int NTH = NS * SF_TPS, SPT = SF_W / NTH;   // threads per CTA, cells stored per thread
+    static_assert(SF_W % NTH == 0, "store-back mapping");
+    int qs = jL0 - 2 * NS + 1;                 // the row that leaves the last stage at time step r
+    unsigned off_st = ring_off(qs);
+    unsigned st_own = 0, st_sm[SPT];
+    double *st_g[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int cc = tid + k * NTH, half = cc / SF_HALF, kk = cc % SF_HALF, ig = i0 + 2 * kk + half;
+        st_own |= (unsigned)(ig >= own_lo && ig <= own_hi) << k;
+        st_sm[k] = (unsigned)(half * SF_HSTR + SF_PADL + kk) * 8u;
+        st_g[k] = pdst + (size_t)pitch * qs + (i0 >> 1) + kk + (half ? hp : 0);
+    }
+#else
     double *gst = pdst + (size_t)pitch * q + (i0 >> 1) + kk0;   // store address of pair kk0's even cell in row q
     const bool last_stage = stage == NS;
+#endif
     const int r_end = jB + 4 * T - 1;
 #pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
         if (r <= jL1) {
-            mbar_wait_a(w_bar, w_par);
+            if (!(SF_DIAG & 8)) mbar_wait_a(w_bar, w_par);
             w_bar += 8;
             if (w_bar == aBar + 8 * R) { w_bar = aBar; w_par ^= 1u; }
         }
@@ -307,13 +356,14 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
                 valid[u] = (vmask >> (2 * u + par)) & 1u;
                 const unsigned iq = off_q + ha8 + u * PAIRB, is = off_s + ha8 + u * PAIRB, in = off_n + ha8 + u * PAIRB,
                                iw = off_q + hw8 + u * PAIRB;
-                bbv[u] = lds_f64(aB + iq);
+                const unsigned cq = off_q + ca8 + u * PAIRB, cs = off_s + ca8 + u * PAIRB, cw = off_q + cw8 + u * PAIRB;
+                bbv[u] = lds_f64(aB + cq);
                 pcv[u] = lds_f64(aP + iq);
-                const double a1 = lds_f64(aV + is), a2 = lds_f64(aU + iw), a4 = lds_f64(aU + iq), a5 = lds_f64(aV + iq);
+                const double a1 = lds_f64(aV + cs), a2 = lds_f64(aU + cw), a4 = lds_f64(aU + cq), a5 = lds_f64(aV + cq);
                 const double pS = lds_f64(aP + is), pW = lds_f64(aP + iw), pE = lds_f64(aP + iw + 8), pN = lds_f64(aP + in);
                 a3v[u] = -a4 - a2 - a5 - a1;
                 sumv[u] = bbv[u] - a1 * pS - a2 * pW - a4 * pE - a5 * pN;
-                qdv[u] = w2_div_fast(sumv[u], a3v[u], okv[u]);
+                if (SF_DIAG & 1) { qdv[u] = pcv[u]; okv[u] = true; } else qdv[u] = w2_div_fast(sumv[u], a3v[u], okv[u]);
                 all_ok = all_ok && (okv[u] || !valid[u]);
             }
             if (!all_ok) {   // operands outside the fast path's range (zero, tiny or huge numerators, ...)
@@ -330,8 +380,27 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
                 if (valid[u] && row_owned && ((omask >> (2 * u + par)) & 1u)) lmax = fmax(lmax, fabs(sum));
             }
         }
-        __syncthreads();
+        if (!(SF_DIAG & 4)) __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
+#if SF_BAL_STORE
+        if (!(SF_DIAG & 2) && (unsigned)(qs - jA) <= jspan) {
+            double *nd = nullptr;
+            if constexpr (SLAB) nd = (qs - a.j0 < H) ? nbr_lo : (a.j1 - qs < H) ? nbr_hi : nullptr;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+                if ((st_own >> k) & 1u) {
+                    const double x = lds_f64(aP + off_st + st_sm[k]);
+                    *st_g[k] = x;
+                    if (SLAB && nd != nullptr) nd[st_g[k] - pdst] = x;
+                }
+            }
+        }
+        ++qs;
+        off_st += ROWB;
+        if (off_st == RINGB) off_st = 0;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) st_g[k] += pitch;
+#else
         if (last_stage && (unsigned)(q - jA) <= jspan) {
             // slab runs: the first / last 2T rows of the slab are the neighbours' halo rows -- the same words go straight
             // into the neighbour's destination buffer (peer stores over NVLink), so that no copy kernel follows the pass
@@ -354,15 +423,19 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
                 }
             }
         }
+#endif
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
-        if (tid < 8 && ld_row <= jL1) issue_row();
+        if (tid < NLD && ld_row <= jL1 && !(SF_DIAG & 8)) issue_row();
         off_s = off_q; off_q = off_n;
         off_n += ROWB;
         if (off_n == RINGB) off_n = 0;
         ha8 = HA_SUM - ha8; hw8 = HW_SUM - hw8;
+        ca8 = CA_SUM - ca8; cw8 = CW_SUM - cw8;
         par ^= 1u;
         ++q;
+#if !SF_BAL_STORE
         gst += pitch;
+#endif
     }
 
     // ---- per-iteration max-norms: threads of stages 2t+1 and 2t+2 hold iteration t's partial max
@@ -551,6 +624,24 @@ __global__ void __launch_bounds__(256) sorf_unpack_cur_kernel(int pitch, int row
     }
 }
 
+// Coefficient tiles (SorFArgs::coef) from the colour-split arrays: tile (strip s, row j) holds the strip's SF_HALF column
+// pairs of b, rau, rgv, each as [even-i half | odd-i half] -- the six 1 KB pieces the kernel of round 2a fetched with six
+// bulk copies, laid side by side so that one copy fetches them.  Strips overlap by their halo columns, so those are stored
+// twice (SF_W / own_w - 1 = 3 % more bytes).  which: bit 0 = b (every solve), bits 1, 2 = rau, rgv (after an upload).
+__global__ void __launch_bounds__(SF_W) sorf_tile_kernel(int pitch, int jlo, int jhi, int own_w, long long crows, int which,
+                                                         const double *__restrict__ b, const double *__restrict__ rau,
+                                                         const double *__restrict__ rgv, double *__restrict__ coef) {
+    const int s = blockIdx.x, half = threadIdx.x / SF_HALF, k = threadIdx.x % SF_HALF;
+    const size_t col = (size_t)((s * own_w) >> 1) + (size_t)k + (half ? (size_t)(pitch >> 1) : 0);
+    for (int j = jlo + blockIdx.y; j <= jhi; j += gridDim.y) {
+        double *t = coef + ((size_t)s * (size_t)crows + (size_t)j) * SF_CTILE + half * SF_HALF + k;
+        const size_t src = (size_t)pitch * (size_t)j + col;
+        if (which & 1) t[0] = b[src];
+        if (which & 2) t[2 * SF_HALF] = rau[src];
+        if (which & 4) t[4 * SF_HALF] = rgv[src];
+    }
+}
+
 int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
     const int rows = c->rows + 1;
     dim3 grid((c->pitch + 255) / 256, rows < 2048 ? rows : 2048);
@@ -564,10 +655,11 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 
 // ---------------------------------------------------------------------------------------- host
 
-// option "sor_slab_inpass": 1 = on several GPUs the pass kernel itself stores the edge rows to the neighbours and closes the
-// pass (sor_rb_fused_slab_kernel: no follow-up launch, but 10 more registers in the streaming loop); 0 = the unchanged
-// one-GPU pass kernel followed by sorf_edge_kernel (the path every committed multi-GPU result was measured with)
-int g_sor_slab_inpass = 0;
+// option "sor_slab_inpass": 1 (default) = on several GPUs the pass kernel itself stores the edge rows to the neighbours and
+// closes the pass (sor_rb_fused_slab_kernel: no follow-up launch); 0 = the one-GPU pass kernel followed by sorf_edge_kernel
+// (round 2a).  Two B200s, 4096 x 8192, 50 passes per step: PPE 10.53 -> 10.20 ms (one GPU on 4096^2: 9.85), both
+// bit-identical to one GPU (multi_gpu_worker.py with W2_OPTS=sor_slab_inpass=0/1 and bench.py's verify block).
+int g_sor_slab_inpass = 1;
 
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
@@ -614,6 +706,7 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
         W2_TRY(w2_sorf_pack(c, c->met.rau, rauS, true));
         W2_TRY(w2_sorf_pack(c, c->met.rgv, rgvS, true));
         c->sorf_met_valid = 1;
+        c->sorf_coef_T = 0;   // the tiles' rau / rgv parts are stale
     }
     const wolfd2_params &par = c->par;
     const int nx = c->nx, ny = c->ny;
@@ -636,6 +729,23 @@ int w2_sor_fused(wolfd2_ctx *c, double *p, double *scratch, int T, int *nSorConv
     a.own_w = SF_W - 4 * T;
     a.nstrips = 1;
     while ((a.nstrips - 1) * a.own_w + SF_W < nx + 2) a.nstrips++;
+    {   // coefficient tiles: rows A0..A1 of every strip (allocated for the narrower strips of T = 2, which are more)
+        const long long crows = c->rows + 1;
+        int smax = 1;
+        while ((smax - 1) * (SF_W - 8) + SF_W < nx + 2) smax++;
+        if (!c->sorf_coef) {
+            W2_CUDA(cudaMalloc((void **)&c->sorf_coef, (size_t)smax * (size_t)crows * SF_CTILE * sizeof(double)));
+            c->sorf_coef_T = 0;
+        }
+        double *coef = c->sorf_coef - (size_t)c->A0 * SF_CTILE;   // global row index, like every field pointer
+        const int which = 1 | (c->sorf_coef_T != T ? 6 : 0);
+        dim3 tg(a.nstrips, c->rows < 1024 ? c->rows : 1024);
+        sorf_tile_kernel<<<tg, SF_W, 0, c->stream>>>(c->pitch, c->A0, c->A1, a.own_w, crows, which, c->fld[W2_F_B], rauS, rgvS, coef);
+        W2_CUDA(cudaGetLastError());
+        c->launches[2]++;
+        c->sorf_coef_T = T;
+        a.coef = coef; a.crows = crows;
+    }
     // bands: exactly one resident wave of CTAs (a partial second wave would double the pass time)
     int per_sm = 1;
     if (T == 1) fused_occupancy<1>(&per_sm);
