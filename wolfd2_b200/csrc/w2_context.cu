@@ -264,7 +264,7 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     double **mp = &c->met.rau;
     for (int k = 0; k < 30; ++k) ffree(c, mp[k]);
     for (int k = 0; k < W2_F_COUNT; ++k) ffree(c, c->fld[k]);
-    ffree(c, c->dus); ffree(c, c->dvs); ffree(c, c->div); ffree(c, c->x1); ffree(c, c->qh);
+    ffree(c, c->dus); ffree(c, c->dvs); ffree(c, c->div); ffree(c, c->x1); ffree(c, c->x1b); ffree(c, c->qh);
     bfree(c, c->pmask); bfree(c, c->xmask); bfree(c, c->ymask); bfree(c, c->pormap); bfree(c, c->tmask);
     ffree(c, c->heat_s); cudaFree(c->dth);
     w2_peer_release(c);   // before the buffers the peers have mapped go away
@@ -279,6 +279,9 @@ extern "C" void wolfd2_b200_destroy(wolfd2_ctx *c) {
     for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->ev_p) cudaEventDestroy(c->ev_p);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c);
 }
@@ -433,10 +436,12 @@ extern int g_mom_np_cache;
 extern int g_mom_cart;
 extern int g_sor_resident;
 extern int g_sor_slab_inpass;
+extern int g_mom_two_streams;
 extern "C" int wolfd2_b200_set_option(const char *name, int32_t value) {
     if (name && !strcmp(name, "mom_np_cache")) { g_mom_np_cache = value != 0; return W2_OK; }
     if (name && !strcmp(name, "mom_cart")) { g_mom_cart = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_resident")) { g_sor_resident = value != 0; return W2_OK; }
+    if (name && !strcmp(name, "mom_two_streams")) { g_mom_two_streams = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_slab_inpass")) { g_sor_slab_inpass = value != 0; return W2_OK; }
     if (name && !strcmp(name, "sor_fused_T")) {
         if (value < -1 || value > 2) { w2_set_error("sor_fused_T must be -1 (default), 0, 1 or 2"); return W2_ERR_BAD_ARG; }

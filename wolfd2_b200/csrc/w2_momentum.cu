@@ -682,6 +682,30 @@ static int mom_cart_prepare(wolfd2_ctx *c) {
     return W2_OK;
 }
 
+int g_mom_two_streams = 1;   // option "mom_two_streams": 0 = XMomentum and YMomentum one after the other on one stream
+
+// Second stream and second set of work arrays for YMomentum (one GPU).  If the extra memory (three field-sized arrays) is
+// not there, the solve stays on one stream.
+static bool mom2_ready(wolfd2_ctx *c) {
+    if (!g_mom_two_streams || c->world > 1 || c->mom2_state < 0) return false;
+    if (c->mom2_state == 1) return true;
+    c->mom2_state = -1;
+    bool ok = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess
+              && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess
+              && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && w2_alloc_field(c, &c->x1b) == W2_OK;
+    ok = ok && w2_tri_prepare_second(c) == W2_OK;
+    if (!ok) { cudaGetLastError(); return false; }   // (whatever was allocated is released with the context)
+    c->mom2_state = 1;
+    return true;
+}
+// swap the stream and the work arrays the momentum launchers use (c->stream, c->x1, c->tri) with the second set
+static void mom2_swap(wolfd2_ctx *c) {
+    cudaStream_t s = c->stream; c->stream = c->stream2; c->stream2 = s;
+    double *x = c->x1; c->x1 = c->x1b; c->x1b = x;
+    W2TriWork w = c->tri; c->tri = c->tri2; c->tri2 = w;
+}
+
 int g_mom_np_cache = 1;   // option "mom_np_cache": 0 = always evaluate cnvn / difn from un, vn (tests compare both ways)
 
 __global__ void ql_ctl_reset(int *ctl) { ctl[0] = 0; ctl[1] = -1; }
@@ -736,8 +760,19 @@ int w2_nauxmomentum(wolfd2_ctx *c, int init_star, int *nQLiter) {
         rc = w2_outflow_bc(c, us, vs, ctl);  // :133
         const int np = !cache_ok ? NP_COMPUTE : m > 1 ? NP_CACHED : (!init_star && !has_outlet) ? NP_SAME : NP_COMPUTE;
         // dus, dvs are zero outside the ranges XMomentum/YMomentum write (:139-144 re-zeroes the same cells)
+        const bool two = rc == W2_OK && mom2_ready(c);
+        if (two) {   // fork: the second stream starts where this one stands (us, vs of this iteration are final)
+            cudaEventRecord(c->ev_fork, c->stream);
+            cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+        }
         if (rc == W2_OK) rc = w2_xmomentum(c, c->dus, np, keep);   // :147
+        if (two) mom2_swap(c);
         if (rc == W2_OK) rc = w2_ymomentum(c, c->dvs, np, keep);   // :158
+        if (two) {   // join: the update below needs dus and dvs
+            cudaEventRecord(c->ev_join, c->stream);
+            mom2_swap(c);
+            cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+        }
         if (rc != W2_OK) break;
         cudaMemsetAsync(c->d_norm + 8, 0, 2 * sizeof(unsigned long long), c->stream);
         int jlo = 1, jhi = ny;

@@ -47,6 +47,10 @@
 #ifndef SF_DIAG
 #define SF_DIAG 0             // timing experiments only (wrong results): 1 no update arithmetic, 2 no store-back, 4 no step barrier, 8 no TMA
 #endif
+#ifndef SF_PWARP
+#define SF_PWARP 0            // 1: an extra warp that only issues the bulk copies -- measured 0.1805 against 0.1728 ms per pass
+#endif
+#define SF_NTHREADS(T) ((T) * 2 * SF_TPS + 32 * SF_PWARP)
 #ifndef SF_BAL_STORE
 #define SF_BAL_STORE 1        // finished rows are stored by all threads of the CTA (0: by the last stage's threads, round 2a)
 #endif
@@ -252,23 +256,26 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     double *ld_dst = nullptr;
     unsigned ld_bytes = SF_HALF * 8;
     size_t ld_step = (size_t)pitch;
-    if (tid < 2) {           // p: even-i / odd-i half of the strip's columns
-        ld_src = psrc + (size_t)pitch * jL0 + (i0 >> 1) + (tid ? hp : 0);   // i0 is a multiple of 4: 16-byte aligned
-        ld_dst = sP + tid * SF_HSTR + SF_PADL;
-    } else if (tid == 2) {   // the row's coefficient tile
+    // (SF_PWARP: the copies issued by the first lanes of an extra warp that does nothing else and reaches the step barrier
+    // at once.  Measured slower: issuing a copy does not hold up the warp that does it; the ninth warp only costs.)
+    const int ptid = SF_PWARP ? tid - NS * SF_TPS : tid;   // producer lane number (negative: not a producer)
+    if (ptid >= 0 && ptid < 2) {           // p: even-i / odd-i half of the strip's columns
+        ld_src = psrc + (size_t)pitch * jL0 + (i0 >> 1) + (ptid ? hp : 0);   // i0 is a multiple of 4: 16-byte aligned
+        ld_dst = sP + ptid * SF_HSTR + SF_PADL;
+    } else if (ptid == 2) {   // the row's coefficient tile
         ld_src = a.coef + ((size_t)strip * (size_t)a.crows + (size_t)jL0) * SF_CTILE;
         ld_dst = sP + SF_STRIDE;
         ld_bytes = SF_CTILE * 8;
         ld_step = SF_CTILE;
     }
     auto issue_row = [&]() {   // executed by lanes 0..NLD-1 together
-        if (tid == 0) mbar_expect_tx(&bars[ld_slot], (2u * SF_HALF + SF_CTILE) * 8u);
+        if (ptid == 0) mbar_expect_tx(&bars[ld_slot], (2u * SF_HALF + SF_CTILE) * 8u);
         tma_load_1d(ld_dst + ld_off, ld_src, ld_bytes, &bars[ld_slot]);
         ++ld_row; ld_src += ld_step;
         ld_off += SF_SLOT; ++ld_slot;
         if (ld_slot == R) { ld_slot = 0; ld_off = 0; }
     };
-    if (tid < NLD)
+    if (ptid >= 0 && ptid < NLD)
         for (int n = 0; n <= D && ld_row <= jL1 && !(SF_DIAG & 8); ++n) issue_row();
 
     // ---- consumer state (all shared-memory addresses are 32-bit byte addresses)
@@ -338,7 +345,7 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
     const int r_end = jB + 4 * T - 1;
 #pragma unroll 1
     for (int r = jL0; r <= r_end; ++r) {
-        if (r <= jL1) {
+        if (r <= jL1 && (!SF_PWARP || ptid < 0)) {
             if (!(SF_DIAG & 8)) mbar_wait_a(w_bar, w_par);
             w_bar += 8;
             if (w_bar == aBar + 8 * R) { w_bar = aBar; w_par ^= 1u; }
@@ -383,7 +390,7 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
         if (!(SF_DIAG & 4)) __syncthreads();
         // the row that has just passed the last stage is final: back to HBM
 #if SF_BAL_STORE
-        if (!(SF_DIAG & 2) && (unsigned)(qs - jA) <= jspan) {
+        if (!(SF_DIAG & 2) && (unsigned)(qs - jA) <= jspan && (!SF_PWARP || tid < NTH)) {
             double *nd = nullptr;
             if constexpr (SLAB) nd = (qs - a.j0 < H) ? nbr_lo : (a.j1 - qs < H) ? nbr_hi : nullptr;
 #pragma unroll
@@ -425,7 +432,7 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
         }
 #endif
         // refill: the slot being overwritten held row r-4T-1, dead since the barrier above
-        if (tid < NLD && ld_row <= jL1 && !(SF_DIAG & 8)) issue_row();
+        if (ptid >= 0 && ptid < NLD && ld_row <= jL1 && !(SF_DIAG & 8)) issue_row();
         off_s = off_q; off_q = off_n;
         off_n += ROWB;
         if (off_n == RINGB) off_n = 0;
@@ -473,11 +480,11 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
 // closed across the GPUs by the slab's last CTA).  Two kernels, so that the one-GPU kernel's parameter block and code are
 // not touched by the slab plumbing.
 template <int T>
-__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_kernel(SorFArgs a) {
+__global__ void __launch_bounds__(SF_NTHREADS(T), ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_kernel(SorFArgs a) {
     sorf_body<T, false>(a);
 }
 template <int T>
-__global__ void __launch_bounds__(T * 2 * SF_TPS, ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_slab_kernel(SorFSlabArgs a) {
+__global__ void __launch_bounds__(SF_NTHREADS(T), ((T == 1) ? 3 : 2) * (256 / SF_W)) sor_rb_fused_slab_kernel(SorFSlabArgs a) {
     sorf_body<T, true>(a);
 }
 
@@ -669,7 +676,7 @@ static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[c->device % W2_MAXDEV] = true;
     }
-    sor_rb_fused_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
+    sor_rb_fused_kernel<T><<<grid, SF_NTHREADS(T), smem, c->stream>>>(a);
     return W2_OK;
 }
 template <int T>
@@ -680,14 +687,14 @@ static int launch_fused_slab(wolfd2_ctx *c, const SorFSlabArgs &a, dim3 grid) {
         W2_CUDA(cudaFuncSetAttribute(sor_rb_fused_slab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[c->device % W2_MAXDEV] = true;
     }
-    sor_rb_fused_slab_kernel<T><<<grid, T * 2 * SF_TPS, smem, c->stream>>>(a);
+    sor_rb_fused_slab_kernel<T><<<grid, SF_NTHREADS(T), smem, c->stream>>>(a);
     return W2_OK;
 }
 template <int T>
 static int fused_occupancy(int *per_sm) {
     const size_t smem = SorFCfg<T>::smem;
     cudaFuncSetAttribute(sor_rb_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, sor_rb_fused_kernel<T>, T * 2 * SF_TPS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, sor_rb_fused_kernel<T>, SF_NTHREADS(T), smem);
     return W2_OK;
 }
 

@@ -152,11 +152,10 @@ static long long round_up(long long x, long long m) { return (x + m - 1) / m * m
 
 // nmax: unknowns of the (global) chain, sizes the segment tables and the upper levels; cap0: unknowns whose
 // level-0 spikes this rank stores (= nmax on one GPU)
-int w2_tri_prepare(wolfd2_ctx *c, long long nmax, long long cap0) {
-    W2TriWork &w = c->tri;
+static int tri_prepare(W2TriWork &w, long long nmax, long long cap0, bool with_y0) {
     memset(&w, 0, sizeof(w));
     w.cap = round_up(cap0, TRI_S) + TRI_S;
-    W2_CUDA(cudaMalloc((void **)&w.Y0, w.cap * sizeof(double)));
+    if (with_y0) W2_CUDA(cudaMalloc((void **)&w.Y0, w.cap * sizeof(double)));
     W2_CUDA(cudaMalloc((void **)&w.V0, w.cap * sizeof(double)));
     W2_CUDA(cudaMalloc((void **)&w.W0, w.cap * sizeof(double)));
     long long n = nmax;
@@ -182,9 +181,14 @@ int w2_tri_prepare(wolfd2_ctx *c, long long nmax, long long cap0) {
     w.nlevels = l;
     return W2_OK;
 }
+int w2_tri_prepare(wolfd2_ctx *c, long long nmax, long long cap0) {
+    c->tri_nmax = nmax;
+    return tri_prepare(c->tri, nmax, cap0, true);
+}
+// the work arrays of the second momentum stream (one GPU; the momentum kernels write Y in the field layout: no Y0)
+int w2_tri_prepare_second(wolfd2_ctx *c) { return tri_prepare(c->tri2, c->tri_nmax, c->tri_nmax, false); }
 
-void w2_tri_release(wolfd2_ctx *c) {
-    W2TriWork &w = c->tri;
+static void tri_release(W2TriWork &w) {
     cudaFree(w.Y0); cudaFree(w.V0); cudaFree(w.W0); cudaFree(w.ext);
     for (int l = 0; l < w.nlevels; ++l) {
         if (l > 0) { cudaFree(w.lv[l].Y); cudaFree(w.lv[l].V); cudaFree(w.lv[l].W); cudaFree(w.lv[l].x); }
@@ -192,6 +196,7 @@ void w2_tri_release(wolfd2_ctx *c) {
     }
     memset(&w, 0, sizeof(w));
 }
+void w2_tri_release(wolfd2_ctx *c) { tri_release(c->tri); tri_release(c->tri2); }
 
 // Levels >= 1: solve the separator system whose rows are formed from the level-0 segment records in
 // tri.lv[0].seg (nseg0 of them).  On return *sigma points at the nseg0 separator values.
