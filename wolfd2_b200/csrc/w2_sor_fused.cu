@@ -47,6 +47,10 @@
 #ifndef SF_DIAG
 #define SF_DIAG 0             // timing experiments only (wrong results): 1 no update arithmetic, 2 no store-back, 4 no step barrier, 8 no TMA
 #endif
+// (Measured and rejected, round 2b: cp.async.bulk.prefetch.L2 of the rows to come -- the ring holds only D + 1 = 4 rows in
+// flight and there is no shared memory for more.  Per row and array piece, 8 rows ahead: 0.193 -> 0.243 ms per pass; on the
+// tiled coefficients, whose rows are contiguous, one prefetch for 4 / 8 / 16 / 32 rows: 0.1727 -> 0.176 / 0.176 / 0.183 /
+// 0.206 ms.  The prefetches compete with the demand copies instead of shortening them.)
 #ifndef SF_PWARP
 #define SF_PWARP 0            // 1: an extra warp that only issues the bulk copies -- measured 0.1805 against 0.1728 ms per pass
 #endif

@@ -38,10 +38,20 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     const bool atd = c->atd && c->atd->ss.nsmallscl == 1;
     cudaStream_t s = c->stream;
     cudaEventRecord(c->ev[0], s);
+    // Cold flow without the ATD model runs ONE momentum-energy pass, during which nothing reads u, v: un <- u (:696-704) and
+    // u <- us (:864-870) are then exchanges of the buffer pointers instead of copies (every user takes c->fld[...] at call
+    // time), and the only copy left is us <- un.  Four of the six field copies of a step: 64 of its 96 copied bytes per cell.
+    const bool swap_uv = !thermal && !atd && c->par.nmeiter > 0;
+    auto swap_fld = [&](int a, int b) { double *t_ = c->fld[a]; c->fld[a] = c->fld[b]; c->fld[b] = t_; };
     // :696-704  time-level n copies (without the thermal energy equation t is identically zero; d only
     // changes through EqState, so dn is refreshed only then)
-    W2_TRY(w2_copy_field(c, un, u));
-    W2_TRY(w2_copy_field(c, vn, v));
+    if (swap_uv) {
+        swap_fld(W2_F_U, W2_F_UN); swap_fld(W2_F_V, W2_F_VN);
+        u = c->fld[W2_F_U]; v = c->fld[W2_F_V]; un = c->fld[W2_F_UN]; vn = c->fld[W2_F_VN];
+    } else {
+        W2_TRY(w2_copy_field(c, un, u));
+        W2_TRY(w2_copy_field(c, vn, v));
+    }
     if (thermal || atd) W2_TRY(w2_copy_field(c, tn, t));   // with the ATD model t carries tss even in cold flow
     if (atd) {                                             // :706-727
         W2Atd *a = c->atd;
@@ -59,8 +69,8 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
     int nQL = -1, nSor = 0, conv = 0;
     for (int l = 1; l <= nme; ++l) {                         // momentum-energy iterations, :738-880
         // :741-747  starred quantities
-        W2_TRY(w2_copy_field(c, us, u));
-        W2_TRY(w2_copy_field(c, vs, v));
+        W2_TRY(w2_copy_field(c, us, swap_uv ? un : u));   // (swap_uv: u's numbers are in un's buffer now)
+        W2_TRY(w2_copy_field(c, vs, swap_uv ? vn : v));
         if (thermal || eqstate) W2_TRY(w2_copy_field(c, ts, t));   // EqState reads ts (:853)
         // us == un on the first pass (not with the ATD model, where un carries uss: then the loop of :114-119 is real), so the initialisation loop of nAuxMomentum (:114-119) is a no-op there;
         // on later passes it resets us, vs to un, vn as the reference does
@@ -94,8 +104,13 @@ static int one_step(wolfd2_ctx *c, wolfd2_step_log *log) {
             W2_TRY(w2_diffmaxnorm_async(c, t, ts, 2));
             W2_TRY(w2_norm_fetch(c, 3, dme));
         }
-        W2_TRY(w2_copy_field(c, u, us));                // :864-870
-        W2_TRY(w2_copy_field(c, v, vs));
+        if (swap_uv) {                                  // :864-870
+            swap_fld(W2_F_U, W2_F_US); swap_fld(W2_F_V, W2_F_VS);
+            u = c->fld[W2_F_U]; v = c->fld[W2_F_V]; us = c->fld[W2_F_US]; vs = c->fld[W2_F_VS];
+        } else {
+            W2_TRY(w2_copy_field(c, u, us));
+            W2_TRY(w2_copy_field(c, v, vs));
+        }
         if (thermal) W2_TRY(w2_copy_field(c, t, ts));
         double dmemax = dme[0] > dme[1] ? dme[0] : dme[1];
         dmemax = dmemax > dme[2] ? dmemax : dme[2];
