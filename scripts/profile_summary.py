@@ -74,8 +74,52 @@ def raw(paths):
         print()
 
 
+def dram(path, peak=6451.2, traffic_json=None):
+    """Per-kernel time and DRAM bytes of a launch list taken with
+    --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum; optionally writes the dominant SOR
+    kernel's bytes per launch to profiles/sor_traffic.json (read by bench.py)."""
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    h = rows[0]
+    ik, iv, im, ii = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name"), h.index("ID")
+    per = OrderedDict()
+    for r in rows[1:]:
+        per.setdefault((r[ii], short(r[ik])), {})[r[im]] = float(r[iv].replace(",", ""))
+    agg = OrderedDict()
+    for (_, k), m in per.items():
+        a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += m.get("gpu__time_duration.sum", 0.0) / 1e3
+        a[2] += m.get("dram__bytes_read.sum", 0.0)
+        a[3] += m.get("dram__bytes_write.sum", 0.0)
+    tot = sum(v[1] for v in agg.values())
+    print(f"{'kernel':40s}{'n':>5s}{'avg_us':>9s}{'share%':>8s}{'rd_MB':>9s}{'wr_MB':>9s}{'GB/s':>8s}{'%peak':>7s}")
+    for k, (n, t, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        gbs = (rd + wr) / (t * 1e-6) / 1e9 if t > 0 else 0.0
+        print(f"{k:40s}{n:5d}{t / n:9.1f}{100 * t / tot:8.1f}{rd / n / 1e6:9.1f}{wr / n / 1e6:9.1f}{gbs:8.0f}{100 * gbs / peak:7.1f}")
+    groups = (("SOR (fused pass, tiles, pack/unpack, reset)", ("sor", "sorf")),
+              ("momentum (assemble+reduce, upper levels, finalize, QL update/decide)", ("mom_", "tri_", "ql_")))
+    used = set()
+    for g, keys in groups:
+        ks = [k for k in agg if k.startswith(keys)]
+        used.update(ks)
+        print(f"# {g}: {100 * sum(agg[k][1] for k in ks) / tot:.1f} %")
+    print(f"# other: {100 * sum(v[1] for k, v in agg.items() if k not in used) / tot:.1f} %")
+    print(f"# total {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches")
+    if traffic_json:
+        import json
+        k = next((k for k in agg if k.startswith("sor_rb_fused_kernel<2>")), None)
+        if k:
+            n, t, rd, wr = agg[k]
+            json.dump({"kernel": k, "iterations_per_launch": 2, "dram_bytes_per_launch": (rd + wr) / n,
+                       "dram_bytes_read": rd / n, "dram_bytes_write": wr / n, "launches_averaged": n,
+                       "source": "ncu launch list of bench.py (cavity 4096^2), mean over the launches: " + path.split("/")[-1]},
+                      open(traffic_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "dram":
+        dram(sys.argv[2], traffic_json=sys.argv[3] if len(sys.argv) > 3 else None)
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     else:
         raw(sys.argv[2:])

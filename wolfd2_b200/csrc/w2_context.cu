@@ -50,9 +50,13 @@ static int check_device() {
     return W2_OK;
 }
 
+// (cudaMemset runs on the legacy default stream, which the context's non-blocking streams do not wait for: without the
+// synchronisation the zero fill of an array allocated on first use could land AFTER the first kernel that writes it --
+// seen as a wrong first step of a fresh one-GPU context once YMomentum had a stream of its own.  Allocation is rare.)
 static int dalloc(double **p, size_t n) {
     W2_CUDA(cudaMalloc((void **)p, n * sizeof(double)));
     W2_CUDA(cudaMemset(*p, 0, n * sizeof(double)));
+    W2_CUDA(cudaDeviceSynchronize());
     return W2_OK;
 }
 // field-layout array of this rank's rows; the stored pointer is shifted so that f[i + pitch*j] takes GLOBAL j
@@ -64,6 +68,7 @@ static int falloc(wolfd2_ctx *c, double **p) {
 static int balloc(wolfd2_ctx *c, unsigned char **p, size_t planes) {
     W2_CUDA(cudaMalloc((void **)p, planes * c->nelem));
     W2_CUDA(cudaMemset(*p, 0, planes * c->nelem));
+    W2_CUDA(cudaDeviceSynchronize());
     *p -= c->row_off;
     return W2_OK;
 }

@@ -160,6 +160,7 @@ int w2_peer_setup(wolfd2_ctx *c) {
     const size_t bcg_bytes = sizeof(W2BcGather) + (size_t)2 * (2 * (size_t)(c->ny + 2) + 2) * sizeof(double);
     ok = ok && cudaMalloc((void **)&bcg, bcg_bytes) == cudaSuccess && cudaMemset(bcg, 0, bcg_bytes) == cudaSuccess;
     ok = ok && cudaIpcGetMemHandle(&mine.g, bcg) == cudaSuccess;
+    cudaDeviceSynchronize();   // the zero fills above ran on the default stream (see dalloc, w2_context.cu)
     mine.ok = ok ? 1 : 0;
     cudaGetLastError();
     Handles *d_all = nullptr, *h_all = (Handles *)malloc(sizeof(Handles) * c->world);

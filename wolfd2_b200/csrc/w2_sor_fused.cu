@@ -461,7 +461,9 @@ __device__ __forceinline__ void sorf_body(const ARGS &a) {
         __shared__ int s_last;
         __syncthreads();
         if (tid == 0) {
-            __threadfence_system();                     // this CTA's peer stores are visible before its ticket
+            // this CTA's peer stores (bands at the slab's edges only) are visible before its ticket
+            if ((jA - a.j0 < H && nbr_lo != nullptr) || (a.j1 - jB < H && nbr_hi != nullptr)) __threadfence_system();
+            else __threadfence();
             s_last = atomicAdd(&ctl->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
         }
         __syncthreads();
@@ -666,11 +668,13 @@ int w2_sorf_pack(wolfd2_ctx *c, const double *src, double *dst, bool to_split) {
 
 // ---------------------------------------------------------------------------------------- host
 
-// option "sor_slab_inpass": 1 (default) = on several GPUs the pass kernel itself stores the edge rows to the neighbours and
-// closes the pass (sor_rb_fused_slab_kernel: no follow-up launch); 0 = the one-GPU pass kernel followed by sorf_edge_kernel
-// (round 2a).  Two B200s, 4096 x 8192, 50 passes per step: PPE 10.53 -> 10.20 ms (one GPU on 4096^2: 9.85), both
-// bit-identical to one GPU (multi_gpu_worker.py with W2_OPTS=sor_slab_inpass=0/1 and bench.py's verify block).
-int g_sor_slab_inpass = 1;
+// option "sor_slab_inpass": 1 = on several GPUs the pass kernel itself stores the edge rows to the neighbours and closes the
+// pass across the GPUs (sor_rb_fused_slab_kernel: no follow-up launch); 0 (default) = the one-GPU pass kernel followed by
+// sorf_edge_kernel.  Both bit-identical to one GPU (multi_gpu_worker.py with W2_OPTS=sor_slab_inpass=0/1, bench.py's verify
+// block).  Two B200s, 4096 x 8192, 50 passes per step, PPE section: round-2a kernel 10.53 ms (edge kernel) / 10.20 ms (in
+// pass); with the tiled coefficients 9.53 / 9.75 ms (one GPU on 4096^2: 8.84) -- the slab kernel's 12 extra registers cost
+// the streaming loop more than the edge kernel's launch.
+int g_sor_slab_inpass = 0;
 
 template <int T>
 static int launch_fused(wolfd2_ctx *c, const SorFArgs &a, dim3 grid) {

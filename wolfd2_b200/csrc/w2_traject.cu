@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(128) traject_kernel(int nx, int ny, int pitch,
 static int tr_alloc_n(void **p, size_t bytes) {
     W2_CUDA(cudaMalloc(p, bytes));
     W2_CUDA(cudaMemset(*p, 0, bytes));
+    W2_CUDA(cudaDeviceSynchronize());   // the fill is on the default stream: see dalloc (w2_context.cu)
     return W2_OK;
 }
 void w2_traj_release(wolfd2_ctx *c) {
