@@ -74,7 +74,7 @@ def raw(paths):
         print()
 
 
-def dram(path, peak=6451.2, traffic_json=None):
+def dram(path, peak=6451.2, traffic_json=None, cells=16769025):
     """Per-kernel time and DRAM bytes of a launch list taken with
     --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum; optionally writes the dominant SOR
     kernel's bytes per launch to profiles/sor_traffic.json (read by bench.py)."""
@@ -110,7 +110,7 @@ def dram(path, peak=6451.2, traffic_json=None):
         k = next((k for k in agg if k.startswith("sor_rb_fused_kernel<2>")), None)
         if k:
             n, t, rd, wr = agg[k]
-            json.dump({"kernel": k, "iterations_per_launch": 2, "dram_bytes_per_launch": (rd + wr) / n,
+            json.dump({"kernel": k, "cells": cells, "iterations_per_launch": 2, "dram_bytes_per_launch": (rd + wr) / n,
                        "dram_bytes_read": rd / n, "dram_bytes_write": wr / n, "launches_averaged": n,
                        "source": "ncu launch list of bench.py (cavity 4096^2), mean over the launches: " + path.split("/")[-1]},
                       open(traffic_json, "w"), indent=1)
