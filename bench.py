@@ -398,6 +398,15 @@ def verify_against_one_gpu(ctx, d, args, dist, rank, world, nsteps=2):
         try:
             g = make_deck(args.workload, d.nx, args.fixed_work, args.q_iters, args.s_iters, ny=d.ny, lazy=True)
             glob = api.Context(g, stream_metrics=False)
+            # arrays the first step of a one-GPU context allocates on demand (the four colour-split SOR buffers, the
+            # coefficient tiles, the second momentum stream's work arrays: about 11 fields) must fit as well
+            field_bytes = 8 * (d.nx + 18) * (d.ny + 3)
+            free_b, _ = torch.cuda.mem_get_info()
+            if free_b < 11.5 * field_bytes + (1 << 30):
+                why = (f"{free_b / 1e9:.0f} GB free after creating the one-GPU context, "
+                       f"{(11.5 * field_bytes + (1 << 30)) / 1e9:.0f} GB more needed for its first step")
+                glob.close()
+                glob = None
         except Exception as e:
             why = str(e)[:200]
     flag = torch.tensor([1 if (rank != 0 or glob is not None) else 0], device="cuda")
