@@ -165,8 +165,15 @@ enum { W2_F_U = 0, W2_F_V = 1, W2_F_P = 2, W2_F_US = 3, W2_F_VS = 4, W2_F_UN = 5
 int wolfd2_b200_config(int32_t mnx, int32_t mny, int32_t mgri, int32_t mgrj);
 /* Select the CUDA device (default 0). */
 int wolfd2_b200_set_device(int32_t device);
-/* Tuning knobs that do not change results: "sor_fused_T" = 0 (one kernel per colour half-sweep),
- * 1 or 2 (red+black and T iterations fused into one pass; default 2). */
+/* Tuning knobs that do not change results (every setting yields the same bits; they exist for A/B timing and tests):
+ *   "sor_fused_T"      0 = one kernel per colour half-sweep, 1 or 2 = red+black and T iterations fused into one pass
+ *                      (default 2); -1 = default / environment W2_SOR_T
+ *   "sor_resident"     1 (default) = grids up to 1024^2 solve the PPE in one cooperative, shared-memory-resident launch
+ *   "sor_slab_inpass"  several GPUs: 1 = the pass kernel stores its edge rows to the neighbours itself, 0 (default) =
+ *                      a follow-up kernel does
+ *   "mom_np_cache"     1 (default) = the time-level-n explicit terms are cached across the QL iterations of a step
+ *   "mom_cart"         1 (default) = metric arrays that are bitwise one-dimensional / constant (checked) are read as such
+ *   "mom_two_streams"  1 (default) = one GPU: XMomentum and YMomentum of a QL iteration run on two streams */
 int wolfd2_b200_set_option(const char *name, int32_t value);
 const char *wolfd2_b200_last_error(void);
 const char *wolfd2_b200_version(void);
