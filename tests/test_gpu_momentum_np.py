@@ -96,3 +96,34 @@ def test_cartesian_metric_variant_is_bit_identical(api, k):
     assert [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l0] == [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in l1]
     for a, b in zip(f_off, f_on):
         assert np.array_equal(a, b, equal_nan=True), d.name
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 5, 6])
+def test_two_stream_momentum_is_bit_identical(api, k):
+    """One GPU: XMomentum and YMomentum of a QL iteration are independent and run on two streams with their own work
+    arrays (option mom_two_streams).  Same bits as one after the other on one stream -- from the very first step of a
+    fresh context, when the second set of arrays is allocated and zero-filled on demand (a zero fill on the default
+    stream once landed after the first kernels: w2_context.cu dalloc)."""
+    d = _cart_decks()[k]
+    d.msorit, d.mqiter, d.qtol = 60, 4, 1e-9
+    rng = np.random.default_rng(41 + k)
+    f0 = [d.new_field() for _ in range(3)]
+    for f in f0[:2]:
+        f[:d.ny + 2, :d.nx + 2] = 0.002 * rng.standard_normal((d.ny + 2, d.nx + 2))
+    res = []
+    for two in (0, 1, 1):                 # the two-stream run twice, each in a fresh context
+        api.set_option("mom_two_streams", two)
+        try:
+            with api.Context(d) as ctx:
+                for w, f in zip((api.F_U, api.F_V, api.F_P), f0):
+                    ctx.upload(w, f)
+                ctx.coldstart()
+                lg = ctx.step(3)
+                res.append((lg, [ctx.download(w) for w in (api.F_U, api.F_V, api.F_P)]))
+        finally:
+            api.set_option("mom_two_streams", 1)
+    key = lambda lg: [(a["nQLiter"], a["nSorConv"], a["dif"]) for a in lg]
+    for lg, fields in res[1:]:
+        assert key(lg) == key(res[0][0])
+        for a, b in zip(res[0][1], fields):
+            assert np.array_equal(a, b, equal_nan=True), d.name
