@@ -190,7 +190,7 @@ int w2_tri_prepare_second(wolfd2_ctx *c) { return tri_prepare(c->tri2, c->tri_nm
 
 static void tri_release(W2TriWork &w) {
     cudaFree(w.Y0); cudaFree(w.V0); cudaFree(w.W0); cudaFree(w.ext);
-    for (int l = 0; l < w.nlevels; ++l) {
+    for (int l = 0; l < 6; ++l) {   // every level: a set-up that ran out of memory half way has nlevels == 0 (cudaFree(0) is a no-op)
         if (l > 0) { cudaFree(w.lv[l].Y); cudaFree(w.lv[l].V); cudaFree(w.lv[l].W); cudaFree(w.lv[l].x); }
         cudaFree(w.lv[l].seg);
     }
