@@ -26,7 +26,9 @@
 
 #include "w2.cuh"
 
-// (SF_W 128 -- four CTAs of four warps per SM, one warp per stage -- was measured at 0.203 ms per pass against 0.194.)
+// (SF_W 128 -- four CTAs of four warps per SM, one warp per stage -- was measured at 0.203 ms per pass against 0.194;
+// SF_W 512 -- one CTA of sixteen warps per SM, half as many bulk copies per cell -- with the tiled coefficients at 0.2175
+// against 0.1727: nine strips of 504 owned columns waste 10 % at nx = 4096, and one CTA per SM has nobody to hide behind.)
 #ifndef SF_W
 #define SF_W 256              // strip width held in shared memory (cells)
 #endif
