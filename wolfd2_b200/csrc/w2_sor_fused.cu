@@ -9,7 +9,9 @@
 // Structure: each CTA owns a strip of 256 columns (256-4T of them "owned", the rest halo that is
 // recomputed redundantly -- bit-identical, since every cell's arithmetic is the same wherever it
 // runs) and streams down a band of rows.  Rows of the four arrays are staged in a shared-memory ring
-// by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), several rows ahead of use.  A software
+// by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), several rows ahead of use: three copies per
+// row -- the two colour halves of p and one 6 KB tile holding the strip's pieces of b, rau, rgv side by
+// side (sorf_tile_kernel; the copy engine's cost is per copy, not per byte).  A software
 // pipeline of 2T half-sweep stages runs on the ring: when row r has landed, stage s (s odd = black
 // of iteration (s+1)/2, s even = red) relaxes row r-2s+1 in place.  With that two-row lag every
 // stage of a time step reads only data written in earlier time steps, so all 2T stages (4 warps
