@@ -393,7 +393,7 @@ def verify_against_one_gpu(ctx, d, args, dist, rank, world, nsteps=2):
     global grid on rank 0, advance both nsteps more steps, compare u, v, p bit for bit and the log tuples."""
     import torch
     from wolfd2_b200 import api
-    glob, why = None, ""
+    glob, why, light = None, "", ""
     if rank == 0:
         try:
             g = make_deck(args.workload, d.nx, args.fixed_work, args.q_iters, args.s_iters, ny=d.ny, lazy=True)
@@ -403,10 +403,16 @@ def verify_against_one_gpu(ctx, d, args, dist, rank, world, nsteps=2):
             field_bytes = 8 * (d.nx + 18) * (d.ny + 3)
             free_b, _ = torch.cuda.mem_get_info()
             if free_b < 11.5 * field_bytes + (1 << 30):
-                why = (f"{free_b / 1e9:.0f} GB free after creating the one-GPU context, "
-                       f"{(11.5 * field_bytes + (1 << 30)) / 1e9:.0f} GB more needed for its first step")
-                glob.close()
-                glob = None
+                # Not enough for those: the one-GPU run then takes the plain half-sweep SOR kernels (no colour-split
+                # buffers, no tiles) and one momentum stream, which need nothing beyond the context itself and give
+                # the same bits (tests/test_gpu_fullsize.py) -- the slab run keeps its fused, tiled kernels.
+                if free_b > 0.25 * field_bytes + (1 << 30):
+                    light = (f"one-GPU run with the plain half-sweep SOR kernels, one momentum stream, no explicit-term cache: {free_b / 1e9:.0f} GB "
+                             f"free next to rank 0's slab, {(11.5 * field_bytes + (1 << 30)) / 1e9:.0f} GB needed for the fused path")
+                else:
+                    why = (f"{free_b / 1e9:.0f} GB free after creating the one-GPU context")
+                    glob.close()
+                    glob = None
         except Exception as e:
             why = str(e)[:200]
     flag = torch.tensor([1 if (rank != 0 or glob is not None) else 0], device="cuda")
@@ -417,7 +423,17 @@ def verify_against_one_gpu(ctx, d, args, dist, rank, world, nsteps=2):
     logs_s = ctx.step(nsteps)
     ms1 = None
     if rank == 0:
-        logs_g = glob.step(nsteps)
+        if light:   # none of these changes a bit of the result (tests/test_gpu_fullsize.py, test_gpu_momentum_np.py)
+            api.set_option("sor_fused_T", 0)
+            api.set_option("mom_two_streams", 0)
+            api.set_option("mom_np_cache", 0)      # (its cache of v's explicit terms lives in two colour-split SOR buffers)
+        try:
+            logs_g = glob.step(nsteps)
+        finally:
+            if light:
+                api.set_option("sor_fused_T", -1)
+                api.set_option("mom_two_streams", 1)
+                api.set_option("mom_np_cache", 1)
         ms1 = glob.timing()["total_ms"] / nsteps
     res = {}
     for nm, w in (("u", api.F_U), ("v", api.F_V), ("p", api.F_P)):
@@ -431,7 +447,7 @@ def verify_against_one_gpu(ctx, d, args, dist, rank, world, nsteps=2):
                "identical": bool(same_logs and all(v["cells_differing"] == 0 for v in res.values())),
                "dif_last": logs_s[-1]["dif"][:3], "dif_last_one_gpu": logs_g[-1]["dif"][:3],
                "iterations_last": [logs_s[-1]["nQLiter"], logs_s[-1]["nSorConv"]],
-               "one_gpu_ms_per_step": ms1,
+               "one_gpu_ms_per_step": ms1, **({"one_gpu_variant": light} if light else {}),
                "how": "wolfd2_b200_gather_global + wolfd2_b200_compare_global: every cell 0..nx+1 x 0..ny+1 of u, v, p "
                       "compared by bit pattern on the device after both runs advanced the same state"}
         glob.close()
